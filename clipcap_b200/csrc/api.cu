@@ -1,0 +1,54 @@
+// C-ABI odds and ends: error/version strings and the kernel-level test hooks declared at the bottom of
+// include/clipcap_b200.h.  The hooks launch exactly the kernels the engines launch (same plans, same heuristics).
+#include "common.h"
+
+extern "C" {
+
+const char* cc_last_error(void) { return cc::get_error(); }
+
+const char* cc_version(void) { return "clipcap_b200 0.1.0 sm_100a"; }
+
+int cc_op_gemm(const void* a, int64_t lda, const void* w, const float* bias, void* out, int64_t ldc, int M, int N, int K,
+               int epi, int bn, void* stream) {
+  using namespace cc;
+  CC_REQUIRE(a != nullptr && w != nullptr && out != nullptr, CC_EINVAL, "cc_op_gemm: null argument");
+  CC_TRY(check_device_sm100());
+  CC_REQUIRE(bn == 0 || bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256, CC_EINVAL,
+             "cc_op_gemm: BLOCK_N %d not in {0,16,32,64,128,256}", bn);
+  GemmPlan p;
+  CC_TRY(gemm_plan(&p, static_cast<const __half*>(a), lda, M, static_cast<const __half*>(w), N, K, epi, bias, out, ldc));
+  p.force_bn = bn;
+  return gemm_run(p, M, static_cast<cudaStream_t>(stream));
+}
+
+int cc_op_layernorm(const float* x, int64_t x_ld, const float* gamma, const float* beta, void* y, int64_t y_ld, int rows,
+                    int d, float eps, void* stream) {
+  using namespace cc;
+  CC_REQUIRE(x != nullptr && gamma != nullptr && beta != nullptr && y != nullptr, CC_EINVAL,
+             "cc_op_layernorm: null argument");
+  CC_TRY(check_device_sm100());
+  return layernorm_run(x, x_ld, gamma, beta, static_cast<__half*>(y), y_ld, rows, d, eps,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int cc_op_attention(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo, int B, int S, int H,
+                    int hd, int causal, float scale, void* stream) {
+  using namespace cc;
+  CC_REQUIRE(q != nullptr && k != nullptr && v != nullptr && o != nullptr, CC_EINVAL, "cc_op_attention: null argument");
+  CC_TRY(check_device_sm100());
+  return attention_run(static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v), ld,
+                       static_cast<__half*>(o), ldo, B, S, H, hd, causal != 0, scale, static_cast<cudaStream_t>(stream));
+}
+
+int cc_op_decode_attention(const void* qkv, void* kcache, void* vcache, const int32_t* anc, void* o, int nseq, int H,
+                           int t_max, int pos, float scale, void* stream) {
+  using namespace cc;
+  CC_REQUIRE(qkv != nullptr && kcache != nullptr && vcache != nullptr && o != nullptr, CC_EINVAL,
+             "cc_op_decode_attention: null argument");
+  CC_TRY(check_device_sm100());
+  return decode_attention_run(static_cast<const __half*>(qkv), static_cast<__half*>(kcache),
+                              static_cast<__half*>(vcache), anc, static_cast<__half*>(o), nseq, H, t_max, pos, scale,
+                              static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

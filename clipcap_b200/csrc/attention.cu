@@ -1,0 +1,410 @@
+// Attention kernels.
+//
+// (1) attn_fwd_kernel: fused softmax(Q K^T * scale [+ causal]) V for the three batched attention sites of the path —
+//     ViT self-attention (S=257, hd=64; clip encode_image), the mapper's MultiHeadAttention
+//     (clipcap/model/attention.py:17-43, S=P+K, hd=d/H) and GPT-2 prefill (causal, hd=64).  Flash-style: one warp owns
+//     16 query rows, K/V stream through double-buffered shared memory in chunks of 64 keys (cp.async), scores never
+//     leave registers (online softmax in fp32, exp2 with the scale folded in), P is re-used in registers as the A
+//     operand of the P.V product. Tensor work uses warp-level mma.m16n8k16 (fp16 in, fp32 accumulate): the tiles here
+//     (<= 257 keys x 64..128) are too small to amortise a TMEM round trip per head.
+// (2) decode_attn_kernel: one query row per (sequence, head) against the fp16 KV cache — HBM-bound streaming of
+//     K and V rows (128 B each) with 8 lanes per key, plus the in-place cache append of the step's own k,v.
+// (3) kv_scatter_kernel: prefill K,V rows -> cache.
+#include <algorithm>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cc {
+namespace {
+
+constexpr int KC = 64;  // keys per shared-memory chunk
+
+template <int HD>
+struct AttnSmem {
+  static constexpr int kRowBytes = HD * 2 + 16;  // +16 B pad: conflict-free ldmatrix without swizzling
+  static constexpr int kChunkBytes = KC * kRowBytes;
+  static constexpr int kBytes = 4 * kChunkBytes;  // {K,V} x double buffer
+};
+
+template <int HD>
+__device__ __forceinline__ void load_kv_chunk(uint32_t sk, uint32_t sv, const __half* kbase, const __half* vbase,
+                                              long long ld, int key0, int S) {
+  constexpr int CPR = HD / 8;  // 16-byte chunks per row
+  for (int i = threadIdx.x; i < KC * CPR; i += blockDim.x) {
+    const int r = i / CPR, c = i % CPR;
+    const int key = key0 + r;
+    const bool ok = key < S;
+    const long long off = static_cast<long long>(ok ? key : 0) * ld + c * 8;
+    const uint32_t so = r * AttnSmem<HD>::kRowBytes + c * 16;
+    cp_async_16(sk + so, kbase + off, ok);
+    cp_async_16(sv + so, vbase + off, ok);
+  }
+}
+
+template <int HD, bool CAUSAL>
+__global__ void __launch_bounds__(256)
+attn_fwd_kernel(const __half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v, long long ld,
+                __half* __restrict__ o, long long ldo, int S, float scale_log2) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t s0 = smem_u32(smem);
+  const int nwarps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const long long row_base = static_cast<long long>(b) * S;
+  const __half* qh = q + row_base * ld + h * HD;
+  const __half* kh = k + row_base * ld + h * HD;
+  const __half* vh = v + row_base * ld + h * HD;
+
+  const int q_lo = blockIdx.x * nwarps * 16;  // first query row of this CTA
+  const int r0 = q_lo + warp * 16;            // first query row of this warp
+  const bool warp_active = r0 < S;
+
+  // keys this CTA needs: all of them, or (causal) up to its last query row
+  int kv_end = S;
+  if (CAUSAL) {
+    const int q_hi = min(S, q_lo + nwarps * 16);
+    kv_end = q_hi;
+  }
+  const int nchunks = (kv_end + KC - 1) / KC;
+
+  // Q fragments (A operand), straight from global memory
+  uint32_t qa[HD / 16][4];
+  {
+    const int ra = r0 + g, rb = r0 + g + 8;
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      const int c = ks * 16 + 2 * t;
+      qa[ks][0] = (warp_active && ra < S) ? *reinterpret_cast<const uint32_t*>(qh + ra * ld + c) : 0u;
+      qa[ks][1] = (warp_active && rb < S) ? *reinterpret_cast<const uint32_t*>(qh + rb * ld + c) : 0u;
+      qa[ks][2] = (warp_active && ra < S) ? *reinterpret_cast<const uint32_t*>(qh + ra * ld + c + 8) : 0u;
+      qa[ks][3] = (warp_active && rb < S) ? *reinterpret_cast<const uint32_t*>(qh + rb * ld + c + 8) : 0u;
+    }
+  }
+
+  float oacc[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY};  // running max (raw scores) for rows g and g+8
+  float lrow[2] = {0.f, 0.f};              // running sum of exp
+
+  auto sK = [&](int buf) { return s0 + (buf * 2 + 0) * AttnSmem<HD>::kChunkBytes; };
+  auto sV = [&](int buf) { return s0 + (buf * 2 + 1) * AttnSmem<HD>::kChunkBytes; };
+
+  load_kv_chunk<HD>(sK(0), sV(0), kh, vh, ld, 0, S);
+  cp_async_commit();
+
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) {
+      load_kv_chunk<HD>(sK(buf ^ 1), sV(buf ^ 1), kh, vh, ld, (ch + 1) * KC, S);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    const int key0 = ch * KC;
+    const bool need = warp_active && (!CAUSAL || key0 <= r0 + 15);
+    if (need) {
+      // ---- S = Q K^T for 16 rows x 64 keys
+      float sacc[KC / 8][4];
+#pragma unroll
+      for (int i = 0; i < KC / 8; ++i) sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f;
+      const uint32_t kb = sK(buf);
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) {
+#pragma unroll
+        for (int np = 0; np < KC / 16; ++np) {
+          // matrices: (keys +0..7, dims +0..7), (keys +0..7, dims +8..15), (keys +8..15, dims +0..7), (keys +8..15, dims +8..15)
+          const int mi = lane >> 3, rr = lane & 7;
+          const int key = np * 16 + (mi >> 1) * 8 + rr;
+          const int dim = ks * 16 + (mi & 1) * 8;
+          uint32_t bf[4];
+          ldmatrix_x4(bf, kb + key * AttnSmem<HD>::kRowBytes + dim * 2);
+          mma_16816(sacc[np * 2], qa[ks], bf[0], bf[1]);
+          mma_16816(sacc[np * 2 + 1], qa[ks], bf[2], bf[3]);
+        }
+      }
+      // ---- mask + online softmax
+      float cmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < KC / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = key0 + nt * 8 + 2 * t + (e & 1);
+          const int row = r0 + g + (e >> 1) * 8;
+          bool ok = key < S;
+          if (CAUSAL) ok = ok && key <= row;
+          if (!ok) sacc[nt][e] = -INFINITY;
+          cmax[e >> 1] = fmaxf(cmax[e >> 1], sacc[nt][e]);
+        }
+      }
+      float corr[2], mnew_s[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        cmax[r] = fmaxf(cmax[r], __shfl_xor_sync(0xffffffffu, cmax[r], 1));
+        cmax[r] = fmaxf(cmax[r], __shfl_xor_sync(0xffffffffu, cmax[r], 2));
+        const float mnew = fmaxf(mrow[r], cmax[r]);
+        // rows that have seen no valid key yet keep m = -inf; guard the (-inf) - (-inf) case
+        mnew_s[r] = (mnew == -INFINITY) ? 0.f : mnew * scale_log2;
+        corr[r] = (mrow[r] == -INFINITY) ? 0.f : exp2f(mrow[r] * scale_log2 - mnew_s[r]);
+        mrow[r] = mnew;
+        lrow[r] *= corr[r];
+      }
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) {
+        oacc[i][0] *= corr[0];
+        oacc[i][1] *= corr[0];
+        oacc[i][2] *= corr[1];
+        oacc[i][3] *= corr[1];
+      }
+      float csum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < KC / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p = exp2f(sacc[nt][e] * scale_log2 - mnew_s[e >> 1]);
+          sacc[nt][e] = p;
+          csum[e >> 1] += p;
+        }
+      }
+      lrow[0] += csum[0];
+      lrow[1] += csum[1];
+
+      // ---- O += P V
+      const uint32_t vb = sV(buf);
+#pragma unroll
+      for (int kk = 0; kk < KC / 16; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_half2(sacc[2 * kk][0], sacc[2 * kk][1]);
+        pa[1] = pack_half2(sacc[2 * kk][2], sacc[2 * kk][3]);
+        pa[2] = pack_half2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+        pa[3] = pack_half2(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3]);
+#pragma unroll
+        for (int np = 0; np < HD / 16; ++np) {
+          // transposed loads: (keys +0..7, dims d0..), (keys +8..15, dims d0..), (keys +0..7, dims d0+8..), (keys +8..15, dims d0+8..)
+          const int mi = lane >> 3, rr = lane & 7;
+          const int key = kk * 16 + (mi & 1) * 8 + rr;
+          const int dim = np * 16 + (mi >> 1) * 8;
+          uint32_t bf[4];
+          ldmatrix_x4_trans(bf, vb + key * AttnSmem<HD>::kRowBytes + dim * 2);
+          mma_16816(oacc[np * 2], pa, bf[0], bf[1]);
+          mma_16816(oacc[np * 2 + 1], pa, bf[2], bf[3]);
+        }
+      }
+    }
+    __syncthreads();  // everyone done with `buf` before it is refilled two iterations later
+  }
+
+  if (warp_active) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
+      lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+    }
+    const float inv0 = lrow[0] > 0.f ? 1.f / lrow[0] : 0.f;
+    const float inv1 = lrow[1] > 0.f ? 1.f / lrow[1] : 0.f;
+    const int ra = r0 + g, rb = r0 + g + 8;
+    __half* oh = o + row_base * ldo + h * HD;
+#pragma unroll
+    for (int nt = 0; nt < HD / 8; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      if (ra < S) *reinterpret_cast<uint32_t*>(oh + ra * ldo + c) = pack_half2(oacc[nt][0] * inv0, oacc[nt][1] * inv0);
+      if (rb < S) *reinterpret_cast<uint32_t*>(oh + rb * ldo + c) = pack_half2(oacc[nt][2] * inv1, oacc[nt][3] * inv1);
+    }
+  }
+}
+
+template <int HD, bool CAUSAL>
+int launch_attn(const __half* q, const __half* k, const __half* v, int64_t ld, __half* o, int64_t ldo, int B, int S,
+                int H, float scale, cudaStream_t s) {
+  auto kern = attn_fwd_kernel<HD, CAUSAL>;
+  static bool configured = false;
+  if (!configured) {
+    CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<HD>::kBytes));
+    configured = true;
+  }
+  const int tiles = (S + 15) / 16;
+  const int nblk = (tiles + 7) / 8;
+  const int nw = (tiles + nblk - 1) / nblk;
+  dim3 grid(nblk, H, B);
+  kern<<<grid, nw * 32, AttnSmem<HD>::kBytes, s>>>(q, k, v, ld, o, ldo, S, scale * 1.4426950408889634f);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+// ------------------------------------------------------------------ decode attention over the KV cache (hd = 64)
+constexpr int DEC_WARPS = 4;
+
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+decode_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, __half* __restrict__ vcache,
+                   const int32_t* __restrict__ anc, __half* __restrict__ o, int nseq, int H, int t_max, int pos,
+                   float scale_log2) {
+  extern __shared__ float sc_all[];  // [DEC_WARPS][t_max] scores
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * DEC_WARPS + warp;
+  if (pair >= nseq * H) return;
+  const int seq = pair / H, h = pair % H;
+  const int d = H * 64;
+  float* sc = sc_all + warp * t_max;
+  const int kq = lane >> 3;  // key slot 0..3 within a pass
+  const int c = lane & 7;    // 16-byte chunk (8 dims) of the head row
+
+  const __half* qrow = qkv + static_cast<long long>(seq) * 3 * d + h * 64;
+  // append this step's k, v (lanes 0..7 copy k, 8..15 copy v)
+  {
+    const long long dst = ((static_cast<long long>(seq) * H + h) * t_max + pos) * 64;
+    if (lane < 8) *reinterpret_cast<uint4*>(kcache + dst + lane * 8) = *reinterpret_cast<const uint4*>(qrow + d + lane * 8);
+    else if (lane < 16)
+      *reinterpret_cast<uint4*>(vcache + dst + (lane - 8) * 8) = *reinterpret_cast<const uint4*>(qrow + 2 * d + (lane - 8) * 8);
+  }
+  __syncwarp();
+  __threadfence_block();
+
+  float qf[8];
+  {
+    const uint4 qq = *reinterpret_cast<const uint4*>(qrow + c * 8);
+    const __half2* hp = reinterpret_cast<const __half2*>(&qq);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(hp[i]);
+      qf[2 * i] = f.x;
+      qf[2 * i + 1] = f.y;
+    }
+  }
+  const int T = pos + 1;
+  const int32_t* arow = anc ? anc + static_cast<long long>(seq) * t_max : nullptr;
+
+  float mx = -INFINITY;
+  for (int t0 = 0; t0 < T; t0 += 4) {
+    const int tt = t0 + kq;
+    float dot = 0.f;
+    if (tt < T) {
+      const int slot = (arow && tt != pos) ? arow[tt] : seq;
+      const uint4 kk = *reinterpret_cast<const uint4*>(kcache + ((static_cast<long long>(slot) * H + h) * t_max + tt) * 64 + c * 8);
+      const __half2* hp = reinterpret_cast<const __half2*>(&kk);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(hp[i]);
+        dot += qf[2 * i] * f.x + qf[2 * i + 1] * f.y;
+      }
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    if (tt < T) {
+      if (c == 0) sc[tt] = dot;
+      mx = fmaxf(mx, dot);
+    }
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  __syncwarp();
+
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  float lsum = 0.f;
+  const float mxs = mx * scale_log2;
+  for (int t0 = 0; t0 < T; t0 += 4) {
+    const int tt = t0 + kq;
+    if (tt < T) {
+      const float p = exp2f(sc[tt] * scale_log2 - mxs);
+      lsum += p;
+      const int slot = (arow && tt != pos) ? arow[tt] : seq;
+      const uint4 vv = *reinterpret_cast<const uint4*>(vcache + ((static_cast<long long>(slot) * H + h) * t_max + tt) * 64 + c * 8);
+      const __half2* hp = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(hp[i]);
+        acc[2 * i] += p * f.x;
+        acc[2 * i + 1] += p * f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+  lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+  if (kq == 0) {
+    const float inv = 1.f / lsum;
+    uint4 out;
+    out.x = pack_half2(acc[0] * inv, acc[1] * inv);
+    out.y = pack_half2(acc[2] * inv, acc[3] * inv);
+    out.z = pack_half2(acc[4] * inv, acc[5] * inv);
+    out.w = pack_half2(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(o + static_cast<long long>(seq) * d + h * 64 + c * 8) = out;
+  }
+}
+
+__global__ void kv_scatter_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache,
+                                  __half* __restrict__ vcache, int nseq, int T, int H, int t_max, int pos0,
+                                  int slot_stride) {
+  // one thread per 16-byte chunk of one (seq, t, head) row, k and v
+  const long long n = static_cast<long long>(nseq) * T * H * 8;
+  const int d = H * 64;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = i & 7;
+    long long r = i >> 3;
+    const int h = r % H;
+    r /= H;
+    const int t = r % T;
+    const int seq = r / T;
+    const __half* src = qkv + (static_cast<long long>(seq) * T + t) * 3 * d + h * 64 + c * 8;
+    const long long dst = ((static_cast<long long>(seq) * slot_stride * H + h) * t_max + pos0 + t) * 64 + c * 8;
+    *reinterpret_cast<uint4*>(kcache + dst) = *reinterpret_cast<const uint4*>(src + d);
+    *reinterpret_cast<uint4*>(vcache + dst) = *reinterpret_cast<const uint4*>(src + 2 * d);
+  }
+}
+
+}  // namespace
+
+int attention_run(const __half* q, const __half* k, const __half* v, int64_t ld, __half* o, int64_t ldo, int B, int S,
+                  int H, int hd, bool causal, float scale, cudaStream_t s) {
+  CC_REQUIRE(B > 0 && S > 0 && H > 0, CC_ESHAPE, "attention: bad shape B=%d S=%d H=%d", B, S, H);
+  CC_REQUIRE(ld % 8 == 0 && ldo % 2 == 0, CC_EALIGN, "attention: ld must be a multiple of 8 elements");
+  CC_REQUIRE(H <= 65535 && B <= 65535, CC_ESHAPE, "attention: grid too large (H=%d B=%d)", H, B);
+#define CC_ATTN_CASE(HD)                                                                         \
+  if (hd == HD)                                                                                  \
+    return causal ? launch_attn<HD, true>(q, k, v, ld, o, ldo, B, S, H, scale, s)                \
+                  : launch_attn<HD, false>(q, k, v, ld, o, ldo, B, S, H, scale, s);
+  CC_ATTN_CASE(48)
+  CC_ATTN_CASE(64)
+  CC_ATTN_CASE(96)
+  CC_ATTN_CASE(128)
+#undef CC_ATTN_CASE
+  set_error("attention: head dim %d not supported (48, 64, 96, 128)", hd);
+  return CC_ESHAPE;
+}
+
+int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, const int32_t* anc, __half* o, int nseq,
+                         int H, int t_max, int pos, float scale, cudaStream_t s) {
+  CC_REQUIRE(pos >= 0 && pos < t_max, CC_ESHAPE, "decode attention: position %d outside cache (t_max %d)", pos, t_max);
+  CC_REQUIRE(t_max <= 2048, CC_ESHAPE, "decode attention: t_max %d > 2048", t_max);
+  const int pairs = nseq * H;
+  const int grid = (pairs + DEC_WARPS - 1) / DEC_WARPS;
+  const size_t smem = static_cast<size_t>(DEC_WARPS) * t_max * sizeof(float);
+  decode_attn_kernel<<<grid, DEC_WARPS * 32, smem, s>>>(qkv, kcache, vcache, anc, o, nseq, H, t_max, pos,
+                                                        scale * 1.4426950408889634f);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+int kv_scatter_run(const __half* qkv, __half* kcache, __half* vcache, int nseq, int T, int H, int t_max, int pos0,
+                   int slot_stride, cudaStream_t s) {
+  CC_REQUIRE(pos0 + T <= t_max, CC_ESHAPE, "kv scatter: %d + %d positions exceed cache length %d", pos0, T, t_max);
+  const long long n = static_cast<long long>(nseq) * T * H * 8;
+  const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 148LL * 16));
+  kv_scatter_kernel<<<grid, 256, 0, s>>>(qkv, kcache, vcache, nseq, T, H, t_max, pos0, slot_stride);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+}  // namespace cc

@@ -1,0 +1,194 @@
+// Shared host-side declarations for libclipcap_b200: status/error plumbing, device buffers, and the launchers of every
+// kernel family (GEMM, LayerNorm, attention, element-wise glue). Engines (vit.cu, mapper.cu, gpt2.cu) compose these.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/clipcap_b200.h"
+
+namespace cc {
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define CC_CUDA(expr)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess) {                                                                          \
+      cc::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));            \
+      return CC_ECUDA;                                                                                 \
+    }                                                                                                  \
+  } while (0)
+
+#define CC_TRY(expr)              \
+  do {                            \
+    int s__ = (expr);             \
+    if (s__ != CC_OK) return s__; \
+  } while (0)
+
+#define CC_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) {                  \
+      cc::set_error(__VA_ARGS__);   \
+      return (code);                \
+    }                               \
+  } while (0)
+
+// ------------------------------------------------------------------ device memory owned by an engine handle
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int alloc(size_t n);
+  void release();
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct Arena {  // owns every allocation of one engine; freed in one go
+  std::vector<void*> ptrs;
+  size_t total = 0;
+  int alloc(void** out, size_t bytes);
+  template <class T>
+  int alloc_t(T** out, size_t count) {
+    return alloc(reinterpret_cast<void**>(out), count * sizeof(T));
+  }
+  void release();
+  ~Arena() { release(); }
+};
+
+int check_device_sm100();  // CC_EARCH unless the current device is compute capability 10.x
+int num_sms();
+
+// ------------------------------------------------------------------ weights lookup
+// Finds `name` among the caller's tensors, checks the element count, and returns a device fp32 pointer. Host pointers
+// are staged through the arena.
+int find_weight(const cc_tensor* w, int n, const std::string& name, int64_t expect_numel, Arena& arena,
+                const float** out);
+
+// ------------------------------------------------------------------ GEMM: C[M,N] = A[M,K] * W[N,K]^T (+ epilogue)
+enum Epi {
+  EPI_F16_NONE = 0,   // C16 = acc + bias
+  EPI_F16_RELU,       // C16 = relu(acc + bias)
+  EPI_F16_QUICKGELU,  // C16 = x * sigmoid(1.702 x)
+  EPI_F16_GELU_NEW,   // C16 = 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+  EPI_F16_TANH,       // C16 = tanh(acc + bias)
+  EPI_F32,            // C32 = acc + bias
+  EPI_RESID_F32,      // C32 += acc + bias       (in-place fp32 residual stream)
+  EPI_ARGMAX,         // keys[m] = max over n of pack(acc, n)   (fused greedy LM head; no logits written)
+  EPI_COUNT
+};
+
+struct GemmPlan {
+  CUtensorMap map_a;     // A: [rows, K] fp16, row stride lda
+  CUtensorMap map_b[5];  // W: [N, K] fp16, one box height per BLOCK_N in {16, 32, 64, 128, 256}
+  int max_rows = 0, N = 0, K = 0;
+  int epi = EPI_F16_NONE;
+  const float* bias = nullptr;
+  void* out = nullptr;  // half* / float* / unsigned long long* by epilogue
+  int64_t ldc = 0;
+  int force_bn = 0;  // 0 = heuristic
+};
+
+// Encodes the tensor maps. `a` must stay at this address with >= max_rows rows readable.
+int gemm_plan(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __half* w, int N, int K, int epi,
+              const float* bias, void* out, int64_t ldc);
+int gemm_run(const GemmPlan& p, int M, cudaStream_t s);
+int gemm_pick_bn(int M, int N);
+
+// pack(acc, n) used by EPI_ARGMAX: high 32 bits = order-preserving float key, low 32 bits = ~n (ties -> lowest index)
+__host__ __device__ inline uint32_t argmax_key_index(unsigned long long key) { return ~static_cast<uint32_t>(key); }
+
+// ------------------------------------------------------------------ LayerNorm (fp32 in, fp16 out), row-strided
+int layernorm_run(const float* x, int64_t x_ld, const float* gamma, const float* beta, __half* y, int64_t y_ld, int rows,
+                  int d, float eps, cudaStream_t s);
+
+// ------------------------------------------------------------------ attention
+// Full / causal self-attention over packed projections. q,k,v point at the first element of their column block inside
+// one [B*S, ld] fp16 matrix (head h at column h*hd); o is [B*S, ldo] fp16. hd in {48, 64, 96, 128}.
+int attention_run(const __half* q, const __half* k, const __half* v, int64_t ld, __half* o, int64_t ldo, int B, int S,
+                  int H, int hd, bool causal, float scale, cudaStream_t s);
+
+// KV cache: [layer][k|v][slot][head][t_max][64] fp16. Decode step: append this step's k,v (from qkv[nseq,3d]) at position
+// `pos` of slot `seq`, then attend over positions 0..pos, position t being read from slot anc[seq*t_max + t]
+// (anc == nullptr: the sequence's own slot).
+int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, const int32_t* anc, __half* o, int nseq,
+                         int H, int t_max, int pos, float scale, cudaStream_t s);
+// Prefill: scatter k,v of [nseq*T, 3d] into the cache at positions pos0 .. pos0+T-1 of slot seq*slot_stride.
+int kv_scatter_run(const __half* qkv, __half* kcache, __half* vcache, int nseq, int T, int H, int t_max, int pos0,
+                   int slot_stride, cudaStream_t s);
+
+// ------------------------------------------------------------------ element-wise glue (elementwise.cu)
+int convert_to_f16_run(const void* src, int src_dtype, __half* dst, int64_t n, cudaStream_t s);
+int convert_from_f32_run(const float* src, int64_t src_ld, void* dst, int dst_dtype, int rows, int cols, cudaStream_t s);
+int convert_to_f32_run(const void* src, int src_dtype, float* dst, int64_t n, cudaStream_t s);
+// weights: fp32 [rows, cols] (optionally transposed on the fly) -> fp16 [rows_out, ld_out] zero padded
+int pack_weight_run(const float* src, int rows, int cols, bool transpose, __half* dst, int64_t ld_out, cudaStream_t s);
+// ViT
+int vit_im2col_run(const void* pixels, int dtype, __half* out, int B, int img, int patch, int k_pad, cudaStream_t s);
+int vit_embed_lnpre_run(const float* patches, const float* cls, const float* pos, const float* g, const float* b,
+                        float* h, int B, int T, int w, float eps, cudaStream_t s);
+int l2_normalize_run(float* x, int rows, int cols, cudaStream_t s);
+// mapper
+int mapper_fill_const_run(float* h, const float* prefix_const, const float* pos_emb, int B, int P, int K, int d,
+                          cudaStream_t s);
+// GPT-2
+int gpt2_embed_prefix_run(const void* embeds, int dtype, const float* wpe, float* h, int B, int T, int d, int pos0,
+                          cudaStream_t s);
+int gpt2_embed_tokens_run(const int32_t* tokens, int64_t tok_stride, const float* wte, const float* wpe, float* h, int n,
+                          int d, int pos, int V, cudaStream_t s);
+int gather_rows_run(const int32_t* ids, const float* table, void* out, int out_dtype, int n, int d, int V,
+                    cudaStream_t s);
+
+// ------------------------------------------------------------------ create-time weight helpers (stack.cu)
+// Copies n fp32 values (device pointer) into the engine's arena so the caller's tensors need not outlive *_create.
+int keep_f32(Arena& arena, const float* src_dev, size_t n, const float** out);
+// fp32 [rows, cols] -> arena-owned fp16 [rows_out, ld_out] (rows_out = cols if transpose else rows), zero padded.
+int pack_f16(Arena& arena, const float* src_dev, int rows, int cols, bool transpose, int64_t ld_out, const __half** out);
+
+// ------------------------------------------------------------------ pre-LN transformer block stack (stack.cu)
+// The three stacks of the path share one block shape:
+//   h += Wo * attn(LN1(h) * Wqkv + bqkv) + bo ;  h += W2 * act(LN2(h) * W1 + b1) + b2
+// ViT (OpenAI CLIP ResidualAttentionBlock: QuickGELU, full attention), the mapper's TransformerLayer
+// (clipcap/model/mapper.py:91-110: ReLU, no qkv bias, full attention) and the GPT-2 block (HF modeling_gpt2.py:262-310:
+// gelu_new, causal).  h is the fp32 residual stream; every GEMM operand is fp16.
+struct LayerW {
+  const float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  const __half *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;  // [3d,d] [d,d] [dff,d] [d,dff]
+  const float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;   // nullable
+};
+
+struct KvCache {  // GPT-2 only: [layer][slot][head][t_max][64] fp16, K and V separate
+  __half* k = nullptr;
+  __half* v = nullptr;
+  int slots = 0, t_max = 0;
+  size_t layer_elems = 0;
+};
+
+struct Stack {
+  int d = 0, dff = 0, H = 0, hd = 0, act_epi = EPI_F16_NONE, max_rows = 0;
+  bool causal = false;
+  float eps = 1e-5f, scale = 1.f;
+  float* h = nullptr;  // [max_rows, d] fp32 residual stream
+  __half *ln16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *mlp16 = nullptr;
+  std::vector<LayerW> layers;
+  std::vector<GemmPlan> p_qkv, p_o, p_1, p_2;
+  int launches = 0;  // kernels enqueued since the counter was last reset
+
+  int init(Arena& arena, int d_, int dff_, int H_, int act_epi_, bool causal_, float eps_, int max_rows_);
+  int plan();  // after `layers` is filled
+  // Full-sequence pass of layer l over B sequences of S rows (rows b*S .. b*S+S-1 of h). If `kv` is given the layer's
+  // K,V rows are also scattered into the cache at positions 0..S-1 of slot b*slot_stride.
+  int layer_full(int l, int B, int S, KvCache* kv, int slot_stride, cudaStream_t s);
+  // One decode step of layer l for nseq single-row sequences at cache position pos.
+  int layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int pos, cudaStream_t s);
+};
+
+}  // namespace cc

@@ -1,0 +1,416 @@
+// tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  with a fused epilogue.
+//
+// Both operands are fp16, K-major ("TN"): activations are row-major [M,K]; weights are stored [N,K] exactly as
+// torch.nn.Linear keeps them (GPT-2's Conv1D [K,N] weights are transposed once at pack time). Accumulation is fp32 in
+// tensor memory.
+//
+// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes {64 x 128} of A and {64 x BN} of W into a ring of
+//               128B-swizzled shared-memory stages, completion counted on `full` mbarriers.
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16) x 4 per stage into one of two
+//               TMEM accumulator buffers; tcgen05.commit releases the smem stage (`empty`) and, after the last k-block,
+//               publishes the accumulator (`tmem_full`).
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp-instruction, thread == output row), bias /
+//               activation / residual / argmax, direct global stores; then `tmem_empty` lets the MMA warp reuse the
+//               buffer, so the epilogue of tile i overlaps the main loop of tile i+1.
+// Tiles are walked n-fastest so the A row-panel and the whole W stay L2 resident.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cc {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageA = BM * BK * 2;
+  static constexpr int kStageB = BN * BK * 2;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 6);
+  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);  // two accumulator buffers, power of two >= 32
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmem = kStages * kStage + kBarBytes + 1024;  // + alignment slack
+};
+
+struct GemmArgs {
+  int M, N, K;
+  const float* bias;
+  void* out;
+  long long ldc;
+};
+
+__device__ __forceinline__ float act_quickgelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float act_gelu_new(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.f + tanhf(u));
+}
+
+template <int EPI>
+__device__ __forceinline__ float apply_act(float x) {
+  if constexpr (EPI == EPI_F16_RELU) return fmaxf(x, 0.f);
+  if constexpr (EPI == EPI_F16_QUICKGELU) return act_quickgelu(x);
+  if constexpr (EPI == EPI_F16_GELU_NEW) return act_gelu_new(x);
+  if constexpr (EPI == EPI_F16_TANH) return tanhf(x);
+  return x;
+}
+
+__device__ __forceinline__ uint32_t float_order_key(float x) {
+  const uint32_t b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs args) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStage;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = (args.M + BM - 1) / BM;
+  const int tiles_n = (args.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (args.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM;
+        const int n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::kStage;
+          const uint32_t sb = sa + Cfg::kStageA;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStage);
+          tma_load_2d(&map_a, full_bar(stage), sa, kb * BK, m0);
+          tma_load_2d(&map_b, full_bar(stage), sb, kb * BK, n0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(tempty_bar(as), ((it >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStage;
+          const uint32_t sb = sa + Cfg::kStageA;
+          const uint64_t da = umma_desc_kmajor_sw128(sa);
+          const uint64_t db = umma_desc_kmajor_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(as));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    constexpr int CH = BN < 32 ? BN : 32;  // columns per tcgen05.ld
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const int m0 = (tile / tiles_n) * BM;
+      const int n0 = (tile % tiles_n) * BN;
+      const int m = m0 + row_in_tile;
+      const bool row_ok = m < args.M;
+      mbar_wait(tfull_bar(as), (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+
+      float best = -INFINITY;
+      int best_n = 0x7fffffff;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / CH; ++c) {
+        const int nc = n0 + c * CH;
+        if (nc >= args.N) break;  // warp-uniform
+        uint32_t r[CH];
+        if constexpr (CH == 32) tmem_ld_x32(t_row + c * CH, r);
+        else tmem_ld_x16(t_row + c * CH, r);
+        tmem_ld_wait();
+        const bool full_chunk = nc + CH <= args.N;
+
+        if constexpr (EPI == EPI_ARGMAX) {
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+              const float v = __uint_as_float(r[j]);
+              if (nc + j < args.N && v > best) {  // strict > keeps the lowest index on ties
+                best = v;
+                best_n = nc + j;
+              }
+            }
+          }
+        } else {
+          float v[CH];
+          if (args.bias != nullptr) {
+            if (full_chunk) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + nc + j));
+                v[j] = __uint_as_float(r[j]) + b4.x;
+                v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+                v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+                v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j)
+                v[j] = __uint_as_float(r[j]) + (nc + j < args.N ? __ldg(args.bias + nc + j) : 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+          }
+
+          if (row_ok) {
+            if constexpr (EPI <= EPI_F16_TANH) {
+              __half* dst = reinterpret_cast<__half*>(args.out) + static_cast<long long>(m) * args.ldc + nc;
+              if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < CH; j += 8) {
+                  uint4 q;
+                  q.x = pack_half2(apply_act<EPI>(v[j]), apply_act<EPI>(v[j + 1]));
+                  q.y = pack_half2(apply_act<EPI>(v[j + 2]), apply_act<EPI>(v[j + 3]));
+                  q.z = pack_half2(apply_act<EPI>(v[j + 4]), apply_act<EPI>(v[j + 5]));
+                  q.w = pack_half2(apply_act<EPI>(v[j + 6]), apply_act<EPI>(v[j + 7]));
+                  *reinterpret_cast<uint4*>(dst + j) = q;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                  if (nc + j < args.N) dst[j] = __float2half_rn(apply_act<EPI>(v[j]));
+              }
+            } else if constexpr (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
+              float* dst = reinterpret_cast<float*>(args.out) + static_cast<long long>(m) * args.ldc + nc;
+              if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < CH; j += 4) {
+                  float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                  if constexpr (EPI == EPI_RESID_F32) {
+                    const float4 h = *reinterpret_cast<const float4*>(dst + j);
+                    o.x += h.x;
+                    o.y += h.y;
+                    o.z += h.z;
+                    o.w += h.w;
+                  }
+                  *reinterpret_cast<float4*>(dst + j) = o;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < CH; ++j)
+                  if (nc + j < args.N) {
+                    if constexpr (EPI == EPI_RESID_F32) dst[j] += v[j];
+                    else dst[j] = v[j];
+                  }
+              }
+            }
+          }
+        }
+      }
+
+      // accumulator fully read: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+
+      if constexpr (EPI == EPI_ARGMAX) {
+        if (row_ok && best_n != 0x7fffffff) {
+          const unsigned long long key = (static_cast<unsigned long long>(float_order_key(best)) << 32) |
+                                         static_cast<unsigned long long>(~static_cast<uint32_t>(best_n));
+          atomicMax(reinterpret_cast<unsigned long long*>(args.out) + m, key);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D fp16 row-major [rows, cols] with row stride ld (elements); box = {64 cols, box_rows}, 128B swizzle.
+int encode_map(CUtensorMap* m, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  CC_REQUIRE(fn != nullptr, CC_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  CC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, CC_EALIGN, "GEMM operand base %p not 16-byte aligned",
+             (const void*)base);
+  CC_REQUIRE((ld * 2) % 16 == 0, CC_EALIGN, "GEMM operand row stride %llu elements is not a multiple of 8",
+             (unsigned long long)ld);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CC_REQUIRE(r == CUDA_SUCCESS, CC_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%u",
+             (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+  return CC_OK;
+}
+
+template <int BN, int EPI>
+int launch(const GemmPlan& p, int bn_idx, int M, cudaStream_t s) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_tn_kernel<BN, EPI>;
+  if (!configured) {
+    CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    configured = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  GemmArgs a{M, p.N, p.K, p.bias, p.out, static_cast<long long>(p.ldc)};
+  kern<<<grid, GEMM_THREADS, Cfg::kSmem, s>>>(p.map_a, p.map_b[bn_idx], a);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+template <int BN>
+int launch_epi(const GemmPlan& p, int bn_idx, int M, cudaStream_t s) {
+  switch (p.epi) {
+    case EPI_F16_NONE: return launch<BN, EPI_F16_NONE>(p, bn_idx, M, s);
+    case EPI_F16_RELU: return launch<BN, EPI_F16_RELU>(p, bn_idx, M, s);
+    case EPI_F16_QUICKGELU: return launch<BN, EPI_F16_QUICKGELU>(p, bn_idx, M, s);
+    case EPI_F16_GELU_NEW: return launch<BN, EPI_F16_GELU_NEW>(p, bn_idx, M, s);
+    case EPI_F16_TANH: return launch<BN, EPI_F16_TANH>(p, bn_idx, M, s);
+    case EPI_F32: return launch<BN, EPI_F32>(p, bn_idx, M, s);
+    case EPI_RESID_F32: return launch<BN, EPI_RESID_F32>(p, bn_idx, M, s);
+    case EPI_ARGMAX: return launch<BN, EPI_ARGMAX>(p, bn_idx, M, s);
+  }
+  set_error("unknown GEMM epilogue %d", p.epi);
+  return CC_EINVAL;
+}
+
+}  // namespace
+
+int gemm_pick_bn(int M, int N) {
+  // Largest BLOCK_N that still yields at least one CTA per SM; small problems (decode, M <= 256) stream weights and
+  // want many CTAs, large ones want the 128x256 tile.
+  const int sms = num_sms();
+  const int tiles_m = (M + BM - 1) / BM;
+  static const int cand[5] = {256, 128, 64, 32, 16};
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cand[i];
+    if (bn > 16 && bn / 2 >= N) continue;  // do not use a tile mostly outside N
+    const int tiles = tiles_m * ((N + bn - 1) / bn);
+    if (tiles >= sms) return bn;
+  }
+  return 16;
+}
+
+int gemm_plan(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __half* w, int N, int K, int epi,
+              const float* bias, void* out, int64_t ldc) {
+  CC_REQUIRE(max_rows > 0 && N > 0 && K > 0, CC_ESHAPE, "gemm_plan: bad shape M=%d N=%d K=%d", max_rows, N, K);
+  CC_REQUIRE(K % 8 == 0, CC_ESHAPE, "gemm_plan: K=%d must be a multiple of 8 (16-byte rows)", K);
+  CC_REQUIRE(epi >= 0 && epi < EPI_COUNT, CC_EINVAL, "gemm_plan: bad epilogue %d", epi);
+  p->max_rows = max_rows;
+  p->N = N;
+  p->K = K;
+  p->epi = epi;
+  p->bias = bias;
+  p->out = out;
+  p->ldc = ldc;
+  CC_TRY(encode_map(&p->map_a, a, max_rows, K, lda, BM));
+  static const int bns[5] = {16, 32, 64, 128, 256};
+  for (int i = 0; i < 5; ++i) CC_TRY(encode_map(&p->map_b[i], w, N, K, K, bns[i]));
+  return CC_OK;
+}
+
+int gemm_run(const GemmPlan& p, int M, cudaStream_t s) {
+  CC_REQUIRE(M > 0 && M <= p.max_rows, CC_ESHAPE, "gemm_run: M=%d outside plan (max %d)", M, p.max_rows);
+  const int bn = p.force_bn ? p.force_bn : gemm_pick_bn(M, p.N);
+  switch (bn) {
+    case 16: return launch_epi<16>(p, 0, M, s);
+    case 32: return launch_epi<32>(p, 1, M, s);
+    case 64: return launch_epi<64>(p, 2, M, s);
+    case 128: return launch_epi<128>(p, 3, M, s);
+    case 256: return launch_epi<256>(p, 4, M, s);
+  }
+  set_error("gemm_run: unsupported BLOCK_N %d", bn);
+  return CC_EINVAL;
+}
+
+}  // namespace cc

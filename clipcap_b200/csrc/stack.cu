@@ -1,0 +1,100 @@
+// Pre-LN transformer block stack shared by the three dense stages (see common.h) + create-time weight helpers.
+#include "common.h"
+
+namespace cc {
+
+int keep_f32(Arena& arena, const float* src_dev, size_t n, const float** out) {
+  float* p = nullptr;
+  CC_TRY(arena.alloc_t(&p, n));
+  CC_CUDA(cudaMemcpy(p, src_dev, n * sizeof(float), cudaMemcpyDeviceToDevice));
+  *out = p;
+  return CC_OK;
+}
+
+int pack_f16(Arena& arena, const float* src_dev, int rows, int cols, bool transpose, int64_t ld_out, const __half** out) {
+  const int out_rows = transpose ? cols : rows;
+  __half* p = nullptr;
+  CC_TRY(arena.alloc_t(&p, static_cast<size_t>(out_rows) * ld_out));
+  CC_TRY(pack_weight_run(src_dev, rows, cols, transpose, p, ld_out, nullptr));
+  CC_CUDA(cudaStreamSynchronize(nullptr));
+  *out = p;
+  return CC_OK;
+}
+
+int Stack::init(Arena& arena, int d_, int dff_, int H_, int act_epi_, bool causal_, float eps_, int max_rows_) {
+  CC_REQUIRE(d_ > 0 && H_ > 0 && d_ % H_ == 0, CC_ESHAPE, "stack: width %d not divisible by %d heads", d_, H_);
+  CC_REQUIRE(d_ % 8 == 0 && dff_ % 8 == 0, CC_ESHAPE, "stack: widths must be multiples of 8 (d=%d dff=%d)", d_, dff_);
+  d = d_;
+  dff = dff_;
+  H = H_;
+  hd = d_ / H_;
+  CC_REQUIRE(hd == 48 || hd == 64 || hd == 96 || hd == 128, CC_ESHAPE,
+             "stack: head dim %d not supported (48, 64, 96, 128)", hd);
+  act_epi = act_epi_;
+  causal = causal_;
+  eps = eps_;
+  scale = 1.0f / sqrtf(static_cast<float>(hd));
+  max_rows = max_rows_;
+  const size_t r = static_cast<size_t>(max_rows);
+  CC_TRY(arena.alloc_t(&h, r * d));
+  CC_TRY(arena.alloc_t(&ln16, r * d));
+  CC_TRY(arena.alloc_t(&qkv16, r * 3 * d));
+  CC_TRY(arena.alloc_t(&att16, r * d));
+  CC_TRY(arena.alloc_t(&mlp16, r * dff));
+  return CC_OK;
+}
+
+int Stack::plan() {
+  const size_t L = layers.size();
+  p_qkv.resize(L);
+  p_o.resize(L);
+  p_1.resize(L);
+  p_2.resize(L);
+  for (size_t l = 0; l < L; ++l) {
+    const LayerW& w = layers[l];
+    CC_TRY(gemm_plan(&p_qkv[l], ln16, d, max_rows, w.wqkv, 3 * d, d, EPI_F16_NONE, w.bqkv, qkv16, 3 * d));
+    CC_TRY(gemm_plan(&p_o[l], att16, d, max_rows, w.wo, d, d, EPI_RESID_F32, w.bo, h, d));
+    CC_TRY(gemm_plan(&p_1[l], ln16, d, max_rows, w.w1, dff, d, act_epi, w.b1, mlp16, dff));
+    CC_TRY(gemm_plan(&p_2[l], mlp16, dff, max_rows, w.w2, d, dff, EPI_RESID_F32, w.b2, h, d));
+  }
+  return CC_OK;
+}
+
+int Stack::layer_full(int l, int B, int S, KvCache* kv, int slot_stride, cudaStream_t s) {
+  const int rows = B * S;
+  CC_REQUIRE(rows <= max_rows, CC_ESHAPE, "stack: %d x %d rows exceed the %d the handle was created for", B, S, max_rows);
+  const LayerW& w = layers[l];
+  CC_TRY(layernorm_run(h, d, w.ln1_g, w.ln1_b, ln16, d, rows, d, eps, s));
+  CC_TRY(gemm_run(p_qkv[l], rows, s));
+  CC_TRY(attention_run(qkv16, qkv16 + d, qkv16 + 2 * d, 3 * d, att16, d, B, S, H, hd, causal, scale, s));
+  launches += 3;
+  if (kv != nullptr) {
+    CC_TRY(kv_scatter_run(qkv16, kv->k + l * kv->layer_elems, kv->v + l * kv->layer_elems, B, S, H, kv->t_max, 0,
+                          slot_stride, s));
+    launches += 1;
+  }
+  CC_TRY(gemm_run(p_o[l], rows, s));
+  CC_TRY(layernorm_run(h, d, w.ln2_g, w.ln2_b, ln16, d, rows, d, eps, s));
+  CC_TRY(gemm_run(p_1[l], rows, s));
+  CC_TRY(gemm_run(p_2[l], rows, s));
+  launches += 4;
+  return CC_OK;
+}
+
+int Stack::layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int pos, cudaStream_t s) {
+  CC_REQUIRE(nseq <= max_rows && nseq <= kv->slots, CC_ESHAPE, "stack: %d sequences exceed handle capacity", nseq);
+  CC_REQUIRE(hd == 64, CC_ESHAPE, "decode attention needs head dim 64 (got %d)", hd);
+  const LayerW& w = layers[l];
+  CC_TRY(layernorm_run(h, d, w.ln1_g, w.ln1_b, ln16, d, nseq, d, eps, s));
+  CC_TRY(gemm_run(p_qkv[l], nseq, s));
+  CC_TRY(decode_attention_run(qkv16, kv->k + l * kv->layer_elems, kv->v + l * kv->layer_elems, anc, att16, nseq, H,
+                              kv->t_max, pos, scale, s));
+  CC_TRY(gemm_run(p_o[l], nseq, s));
+  CC_TRY(layernorm_run(h, d, w.ln2_g, w.ln2_b, ln16, d, nseq, d, eps, s));
+  CC_TRY(gemm_run(p_1[l], nseq, s));
+  CC_TRY(gemm_run(p_2[l], nseq, s));
+  launches += 7;
+  return CC_OK;
+}
+
+}  // namespace cc

@@ -1,0 +1,181 @@
+/*
+ * libclipcap_b200 — C ABI of the B200-native ClipCap hot path
+ * (image -> CLIP ViT-L/14 embedding -> mapper prefix -> GPT-2 autoregressive decode -> token ids).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types. Every entry point below names the reference
+ * interface (TheoCoombes/ClipCap @ f041e35, paths relative to the reference repo) that it replaces; the Python package
+ * `clipcap_b200` binds it with ctypes and mirrors the reference's Python API on top.
+ *
+ * Conventions
+ *  - Every function returns a status (CC_OK == 0, negative on error); cc_last_error() returns a thread-local message.
+ *  - All data pointers are DEVICE pointers on the device that was current at *_create time unless stated otherwise
+ *    (weights passed to *_create may be host or device pointers).
+ *  - Nothing in a forward call synchronises the host: work is enqueued on the caller's stream (a cudaStream_t passed
+ *    as void*; NULL = legacy default stream).
+ *  - A handle owns its packed fp16 weights, workspaces, KV cache and CUDA graphs, all allocated at create time for
+ *    `max_batch`. One call in flight per handle.
+ *  - The library refuses to run on anything but compute capability 10.x (CC_EARCH): there is no fallback path.
+ */
+#ifndef CLIPCAP_B200_H
+#define CLIPCAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum cc_status {
+  CC_OK = 0,
+  CC_EINVAL = -1, /* bad argument */
+  CC_ESHAPE = -2, /* unsupported / inconsistent shape */
+  CC_EALIGN = -3, /* pointer or stride alignment */
+  CC_ECUDA = -4,  /* CUDA runtime / driver error */
+  CC_ENCCL = -5,  /* collective error (reserved) */
+  CC_EARCH = -6,  /* device is not sm_100 */
+  CC_ENOMEM = -7
+};
+
+enum cc_dtype { CC_F32 = 0, CC_F16 = 1 };
+
+/* A named weight tensor in the reference's state_dict layout (fp32, contiguous, row-major). */
+typedef struct cc_tensor {
+  const char* name;
+  const void* data; /* host or device pointer */
+  int32_t dtype;    /* CC_F32 only */
+  int32_t ndim;
+  int64_t shape[4];
+} cc_tensor;
+
+const char* cc_last_error(void);
+/* "clipcap_b200 <version> sm_100a" — also proves the library was built for the right arch. */
+const char* cc_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Stage 1 — CLIP ViT image tower.
+ * Replaces: CLIPModel.forward -> clip_model.encode_image (clipcap/encoders/clip.py:112-129, :120), i.e. OpenAI CLIP
+ * VisionTransformer: conv1 patch embed (no bias) -> [CLS]+pos -> ln_pre -> L x {x += MHA(ln_1 x); x += c_proj(
+ * QuickGELU(c_fc(ln_2 x)))} -> ln_post(x[:,0]) @ proj, optional L2 normalisation (clip.py:122-123).
+ * Weight names (OpenAI `clip` state_dict, the dependency the reference loads at clip.py:134-136):
+ *   visual.conv1.weight [w,3,p,p]  visual.class_embedding [w]  visual.positional_embedding [T,w]
+ *   visual.ln_pre.{weight,bias}  visual.transformer.resblocks.{i}.{ln_1,ln_2}.{weight,bias}
+ *   ...resblocks.{i}.attn.in_proj_{weight [3w,w],bias}  ...attn.out_proj.{weight,bias}
+ *   ...resblocks.{i}.mlp.{c_fc,c_proj}.{weight,bias}  visual.ln_post.{weight,bias}  visual.proj [w,out]
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct cc_vit_cfg {
+  int32_t image_size; /* 224 */
+  int32_t patch;      /* 14  */
+  int32_t width;      /* 1024 */
+  int32_t layers;     /* 24 */
+  int32_t heads;      /* 16 (head dim must be 64) */
+  int32_t mlp_dim;    /* 4096 */
+  int32_t out_dim;    /* 768 */
+  float eps;          /* 1e-5 */
+} cc_vit_cfg;
+typedef struct cc_vit cc_vit;
+
+int cc_vit_create(cc_vit** h, const cc_vit_cfg* cfg, const cc_tensor* weights, int n_weights, int max_batch);
+/* pixels: [B,3,S,S] CLIP-normalised, dtype pix_dtype; out: [B,out_dim], dtype out_dtype. */
+int cc_vit_forward(cc_vit* h, const void* pixels, int pix_dtype, int B, int normalize, void* out, int out_dtype,
+                   void* stream);
+void cc_vit_destroy(cc_vit* h);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Stage 2 — prefix mapper.
+ * Replaces: TransformerMapper.forward (clipcap/model/mapper.py:113-130), TransformerMapperWindowed.forward
+ * (mapper.py:133-160) with Transformer/TransformerLayer/MLPTransformer (mapper.py:8-110) and MultiHeadAttention
+ * (clipcap/model/attention.py:4-43); plus the upstream-defined MLP mapper (absent from the reference).
+ * Weight names are relative to `transformer_mapper.`:
+ *   linear.{weight [P*d,E],bias}  prefix_const [K,d]  [pos_embeddings [(W)*P,d]]
+ *   transformer.layers.{i}.{norm1,norm2}.{weight,bias}  ...attn.to_queries.weight [d,d]
+ *   ...attn.to_keys_values.weight [2d,d]  ...attn.project.{weight,bias}  ...mlp.{fc1,fc2}.{weight,bias}
+ * MLP kind: model.0.{weight [K*d/2,E],bias}  model.2.{weight [K*d,K*d/2],bias}
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum cc_mapper_kind { CC_MAPPER_TRANSFORMER = 0, CC_MAPPER_WINDOWED = 1, CC_MAPPER_MLP = 2 };
+typedef struct cc_mapper_cfg {
+  int32_t kind;
+  int32_t E;       /* encoder_embedding_size */
+  int32_t d;       /* lm_embedding_size */
+  int32_t P;       /* projection_length */
+  int32_t K;       /* prefix_length */
+  int32_t H;       /* transformer_attention_heads (d/H in {48,64,96,128}) */
+  int32_t L;       /* transformer_layers */
+  int32_t W;       /* windowed: window_size + 1 (model.py:28); otherwise 1 */
+  int32_t use_pos; /* windowed: use_positional_embeddings */
+  float eps;       /* 1e-5 */
+} cc_mapper_cfg;
+typedef struct cc_mapper cc_mapper;
+
+int cc_mapper_create(cc_mapper** h, const cc_mapper_cfg* cfg, const cc_tensor* weights, int n_weights, int max_batch);
+/* emb: [B,E] (or [B,W,E] windowed); prefix: [B,K,d]. */
+int cc_mapper_forward(cc_mapper* h, const void* emb, int emb_dtype, int B, void* prefix, int prefix_dtype,
+                      void* stream);
+void cc_mapper_destroy(cc_mapper* h);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Stage 3 — GPT-2 language model and the decode loops.
+ * Replaces: model.language_model(inputs_embeds=...) .logits and get_input_embeddings() as used by
+ * clipcap/inference/base.py:76,81,117 (HF GPT2LMHeadModel arithmetic), and generate_beam (base.py:55-132; beam_size=1
+ * is the reference's greedy).
+ * Weight names are relative to `language_model.` (HF GPT-2): transformer.wte.weight [V,d]  transformer.wpe.weight
+ *   transformer.h.{i}.{ln_1,ln_2}.{weight,bias}  ...attn.c_attn.{weight [d,3d],bias}  ...attn.c_proj.{weight,bias}
+ *   ...mlp.c_fc.{weight [d,4d],bias}  ...mlp.c_proj.{weight [4d,d],bias}  transformer.ln_f.{weight,bias}
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct cc_gpt2_cfg {
+  int32_t d;     /* n_embd */
+  int32_t L;     /* n_layer */
+  int32_t H;     /* n_head (d/H must be 64) */
+  int32_t V;     /* vocab_size */
+  int32_t n_pos; /* n_positions */
+  float eps;     /* 1e-5 */
+} cc_gpt2_cfg;
+typedef struct cc_gpt2 cc_gpt2;
+
+/* max_seqs: largest B (x beam) ever decoded; max_len: largest prefix + generated length. */
+int cc_gpt2_create(cc_gpt2** h, const cc_gpt2_cfg* cfg, const cc_tensor* weights, int n_weights, int max_seqs,
+                   int max_len);
+/* embeds: [B,T,d] -> logits fp32. all_positions == 0: [B,V] of the last position (what base.py:83 consumes);
+ * otherwise [B,T,V]. */
+int cc_gpt2_logits(cc_gpt2* h, const void* embeds, int dtype, int B, int T, int all_positions, float* logits,
+                   void* stream);
+/* out[i,:] = wte[ids[i],:] (get_input_embeddings(), base.py:76,117) */
+int cc_gpt2_embed(cc_gpt2* h, const int32_t* ids, int n, void* out, int out_dtype, void* stream);
+
+enum cc_gen_mode { CC_GEN_GREEDY = 0, CC_GEN_BEAM = 1 };
+typedef struct cc_gen_cfg {
+  int32_t mode;
+  int32_t beam;         /* beam_size (BEAM) */
+  int32_t entry_length; /* tokens to generate (base.py:62) */
+  float temperature;    /* <= 0 treated as 1 (base.py:83) */
+  int32_t stop_token;   /* tokenizer.encode(eos)[0] (base.py:66) */
+} cc_gen_cfg;
+/* prefix: [B,Tp,d] input embeddings (mapper prefix, optionally followed by text-prefix embeddings, base.py:75-77).
+ * tokens: [B,entry_length] int32 — best beam per row (base.py:126-128); lengths: [B] int32 = number of valid tokens
+ * (stop token included, base.py:125); scores: [B] fp32 length-normalised log-prob of the returned beam (may be NULL).
+ * Row i equals the reference called on sample i alone. */
+int cc_generate(cc_gpt2* h, const void* prefix, int dtype, int B, int Tp, const cc_gen_cfg* g, int32_t* tokens,
+                int32_t* lengths, float* scores, void* stream);
+/* number of kernel launches (graph nodes) the last cc_generate enqueued */
+int cc_gpt2_last_launches(cc_gpt2* h);
+void cc_gpt2_destroy(cc_gpt2* h);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Kernel-level test hooks (used by tests/ and bench.py for per-kernel parity and roofline timing; same kernels the
+ * engines launch).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* C[M,N] = A[M,K] (fp16, row stride lda) x W[N,K]^T (fp16, row stride K) with epilogue `epi` (see csrc/common.h):
+ * 0..4 fp16 out with none/relu/quickgelu/gelu_new/tanh, 5 fp32 out, 6 fp32 in-place residual add, 7 fused argmax
+ * (out = uint64 keys[M], must be zeroed). bn = 0 picks BLOCK_N heuristically. */
+int cc_op_gemm(const void* a, int64_t lda, const void* w, const float* bias, void* out, int64_t ldc, int M, int N, int K,
+               int epi, int bn, void* stream);
+int cc_op_layernorm(const float* x, int64_t x_ld, const float* gamma, const float* beta, void* y, int64_t y_ld, int rows,
+                    int d, float eps, void* stream);
+int cc_op_attention(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo, int B, int S, int H,
+                    int hd, int causal, float scale, void* stream);
+int cc_op_decode_attention(const void* qkv, void* kcache, void* vcache, const int32_t* anc, void* o, int nseq, int H,
+                           int t_max, int pos, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPCAP_B200_H */
