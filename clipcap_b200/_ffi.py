@@ -64,9 +64,11 @@ PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {
     "cc_version": (C.c_char_p, []),
     "cc_vit_create": (_i, [_pp, C.POINTER(cc_vit_cfg), C.POINTER(cc_tensor), _i, _i]),
     "cc_vit_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "cc_vit_last_launches": (_i, [_vp]),
     "cc_vit_destroy": (None, [_vp]),
     "cc_mapper_create": (_i, [_pp, C.POINTER(cc_mapper_cfg), C.POINTER(cc_tensor), _i, _i]),
     "cc_mapper_forward": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
+    "cc_mapper_last_launches": (_i, [_vp]),
     "cc_mapper_destroy": (None, [_vp]),
     "cc_gpt2_create": (_i, [_pp, C.POINTER(cc_gpt2_cfg), C.POINTER(cc_tensor), _i, _i, _i]),
     "cc_gpt2_logits": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

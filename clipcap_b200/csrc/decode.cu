@@ -1,0 +1,330 @@
+// Token-selection kernels of the decode loops (clipcap/inference/base.py:80-130), batched over images.
+//   greedy  : consumes the fused-argmax keys of the LM-head GEMM (EPI_ARGMAX); generate_beam(beam_size=1) semantics.
+//   beam    : per-row log-softmax + top-`beam` (row_topk), per-image merge over beam x beam candidates with the
+//             reference's length-normalised scores, stopped-beam rule and source reordering (beam_step), final pick.
+// All state lives on the device; nothing here synchronises the host.
+#include "common.h"
+#include "decode.h"
+
+namespace cc {
+namespace {
+
+constexpr int TOPK_THREADS = 256;
+
+__global__ void gen_reset_kernel(int32_t* stopped, int32_t* lengths, unsigned long long* keys, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    stopped[i] = 0;
+    lengths[i] = 0;
+    keys[i] = 0ull;
+  }
+}
+
+// generate_beam with beam_size == 1: tokens are appended until the stop token has been emitted (base.py:117-121);
+// the returned length counts the stop token (seq_lengths starts at 1 and grows while not stopped, base.py:70,100).
+__global__ void greedy_select_kernel(unsigned long long* keys, int32_t* tokens, int entry_len, int step, int32_t* stopped,
+                                     int32_t* lengths, int stop_token, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int tok = static_cast<int>(argmax_key_index(keys[i]));
+  keys[i] = 0ull;  // re-armed for the next step's atomicMax
+  if (stopped[i]) {
+    tokens[i * entry_len + step] = 0;
+    return;
+  }
+  tokens[i * entry_len + step] = tok;
+  lengths[i] = step + 1;
+  if (tok == stop_token) stopped[i] = 1;
+}
+
+struct Cand {
+  float v;
+  int i;
+};
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+// One CTA per sequence row: lp = log(softmax(logits / T)) (base.py:83-84) and the row's `beam` best (value, token).
+// Stopped rows contribute the single candidate (0, token 0) (base.py:96-97).
+template <int BEAM_MAX>
+__global__ void __launch_bounds__(TOPK_THREADS)
+row_topk_kernel(const float* __restrict__ logits, long long ldl, int V, float inv_temp, int beam,
+                const int32_t* __restrict__ stopped, float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+  __shared__ float s_red[TOPK_THREADS / 32];
+  __shared__ float s_bv[TOPK_THREADS / 32];
+  __shared__ int s_bi[TOPK_THREADS / 32];
+  __shared__ int s_bt[TOPK_THREADS / 32];
+  __shared__ float s_m, s_sum;
+  __shared__ int s_win;
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* ov = out_val + static_cast<long long>(row) * beam;
+  int32_t* oi = out_idx + static_cast<long long>(row) * beam;
+  if (stopped != nullptr && stopped[row]) {
+    if (tid < beam) {
+      ov[tid] = tid == 0 ? 0.f : -INFINITY;
+      oi[tid] = tid == 0 ? 0 : tid;  // distinct dummy tokens; never selected ahead of finite candidates
+    }
+    return;
+  }
+  const float* x = logits + static_cast<long long>(row) * ldl;
+  Cand top[BEAM_MAX];
+#pragma unroll
+  for (int k = 0; k < BEAM_MAX; ++k) top[k] = Cand{-INFINITY, 0x7fffffff};
+  float m = -INFINITY;
+  for (int c = tid; c < V; c += TOPK_THREADS) {
+    const float v = x[c] * inv_temp;
+    m = fmaxf(m, v);
+    if (better(v, c, top[BEAM_MAX - 1].v, top[BEAM_MAX - 1].i)) {
+      top[BEAM_MAX - 1] = Cand{v, c};
+#pragma unroll
+      for (int k = BEAM_MAX - 1; k > 0; --k) {
+        if (better(top[k].v, top[k].i, top[k - 1].v, top[k - 1].i)) {
+          const Cand t = top[k];
+          top[k] = top[k - 1];
+          top[k - 1] = t;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  if (tid == 0) {
+    float mm = s_red[0];
+    for (int w = 1; w < TOPK_THREADS / 32; ++w) mm = fmaxf(mm, s_red[w]);
+    s_m = mm;
+  }
+  __syncthreads();
+  m = s_m;
+  float sum = 0.f;
+  for (int c = tid; c < V; c += TOPK_THREADS) sum += expf(x[c] * inv_temp - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    float ss = 0.f;
+    for (int w = 0; w < TOPK_THREADS / 32; ++w) ss += s_red[w];
+    s_sum = ss;
+  }
+  __syncthreads();
+  sum = s_sum;
+
+  // `beam` rounds of block-wide argmax over the heads of the per-thread sorted lists
+  int head = 0;
+  for (int r = 0; r < beam; ++r) {
+    float v = head < BEAM_MAX ? top[0].v : -INFINITY;
+    int idx = head < BEAM_MAX ? top[0].i : 0x7fffffff;
+    int who = tid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+      const int w2 = __shfl_xor_sync(0xffffffffu, who, o);
+      if (better(v2, i2, v, idx)) {
+        v = v2;
+        idx = i2;
+        who = w2;
+      }
+    }
+    if (lane == 0) {
+      s_bv[warp] = v;
+      s_bi[warp] = idx;
+      s_bt[warp] = who;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float bv = s_bv[0];
+      int bi = s_bi[0], bt = s_bt[0];
+      for (int w = 1; w < TOPK_THREADS / 32; ++w)
+        if (better(s_bv[w], s_bi[w], bv, bi)) {
+          bv = s_bv[w];
+          bi = s_bi[w];
+          bt = s_bt[w];
+        }
+      ov[r] = logf(expf(bv - m) / sum);  // softmax(-1).log() of the reference, not log_softmax
+      oi[r] = bi;
+      s_win = bt;
+    }
+    __syncthreads();
+    if (tid == s_win) {  // pop the winner's head
+#pragma unroll
+      for (int k = 0; k < BEAM_MAX - 1; ++k) top[k] = top[k + 1];
+      top[BEAM_MAX - 1] = Cand{-INFINITY, 0x7fffffff};
+      ++head;
+    }
+    __syncthreads();
+  }
+}
+
+// Step 0 (base.py:86-94): the image's single prefill row fans out into `beam` beams.
+__global__ void beam_init_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, BeamState st,
+                                 int beam, int entry_len, int t_max, int Tp, int stop_token, int n_img) {
+  const int b = blockIdx.x;
+  if (b >= n_img) return;
+  for (int j = threadIdx.x; j < beam; j += blockDim.x) {
+    const int row = b * beam + j;
+    // candidates of the prefill row were written at row index b (one logits row per image)
+    const float v = cand_val[b * beam + j];
+    const int tok = cand_idx[b * beam + j];
+    st.scores[row] = v;
+    st.seq_len[row] = 1.f;
+    st.stopped[row] = tok == stop_token ? 1 : 0;
+    st.tokens[0][static_cast<long long>(row) * entry_len] = tok;
+  }
+  for (int i = threadIdx.x; i < beam * Tp; i += blockDim.x) {
+    const int j = i / Tp, t = i % Tp;
+    st.anc[0][static_cast<long long>(b * beam + j) * t_max + t] = b * beam;  // prefill K,V live in slot b*beam
+  }
+}
+
+// Steps >= 1 (base.py:96-119). One CTA per image; thread 0 does the (beam^2)-candidate selection, all threads copy state.
+// in/out = ping-pong index of tokens/anc. `pos` = cache position written by this step's decode pass.
+template <int BEAM_MAX>
+__global__ void beam_step_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, BeamState st,
+                                 int in, int beam, int V, int entry_len, int t_max, int step, int pos, int stop_token,
+                                 int n_img) {
+  __shared__ int s_src[BEAM_MAX];
+  __shared__ int s_frozen;
+  const int b = blockIdx.x;
+  if (b >= n_img) return;
+  const int out = in ^ 1;
+  const int base = b * beam;
+  if (threadIdx.x == 0) {
+    bool all = true;
+    for (int j = 0; j < beam; ++j) all = all && st.stopped[base + j] != 0;
+    s_frozen = all ? 1 : 0;  // the reference left its loop here (base.py:120-121): state is final
+    if (all) {
+      for (int j = 0; j < beam; ++j) s_src[j] = j;
+    } else {
+      float len2[BEAM_MAX];
+      for (int j = 0; j < beam; ++j) len2[j] = st.seq_len[base + j] + (st.stopped[base + j] ? 0.f : 1.f);
+      float n_sc[BEAM_MAX], n_len[BEAM_MAX];
+      int n_tok[BEAM_MAX], n_stop[BEAM_MAX], n_src[BEAM_MAX];
+      int head[BEAM_MAX];
+      for (int j = 0; j < beam; ++j) head[j] = 0;
+      for (int r = 0; r < beam; ++r) {
+        float bv = -INFINITY;
+        long long bflat = 0x7fffffffffffffffLL;
+        int bj = -1;
+        for (int j = 0; j < beam; ++j) {
+          if (head[j] >= beam) continue;
+          const int c = (base + j) * beam + head[j];
+          const float avg = (st.scores[base + j] + cand_val[c]) / len2[j];  // scores_sum / seq_lengths (base.py:99-101)
+          const long long flat = static_cast<long long>(j) * V + cand_idx[c];
+          if (bj < 0 || avg > bv || (avg == bv && flat < bflat)) {
+            bv = avg;
+            bflat = flat;
+            bj = j;
+          }
+        }
+        const int c = (base + bj) * beam + head[bj];
+        head[bj]++;
+        n_src[r] = bj;
+        n_tok[r] = cand_idx[c];
+        n_len[r] = len2[bj];
+        n_sc[r] = bv * len2[bj];  // scores = scores_sum_average * seq_lengths (base.py:113)
+        n_stop[r] = (st.stopped[base + bj] != 0 || n_tok[r] == stop_token) ? 1 : 0;
+      }
+      for (int r = 0; r < beam; ++r) {
+        st.scores[base + r] = n_sc[r];
+        st.seq_len[base + r] = n_len[r];
+        st.stopped[base + r] = n_stop[r];
+        s_src[r] = n_src[r];
+        st.tokens[out][static_cast<long long>(base + r) * entry_len + step] = n_tok[r];
+      }
+    }
+  }
+  __syncthreads();
+  const bool frozen = s_frozen != 0;
+  // tokens: out[r][0..step-1] = in[src][..] (frozen: the whole row incl. position `step` stays as it was)
+  const int ncopy = frozen ? entry_len : step;
+  for (int i = threadIdx.x; i < beam * ncopy; i += blockDim.x) {
+    const int r = i / ncopy, t = i % ncopy;
+    st.tokens[out][static_cast<long long>(base + r) * entry_len + t] =
+        st.tokens[in][static_cast<long long>(base + s_src[r]) * entry_len + t];
+  }
+  // ancestry: positions < pos inherited from the source beam; position pos was written into the source beam's slot
+  for (int i = threadIdx.x; i < beam * (pos + 1); i += blockDim.x) {
+    const int r = i / (pos + 1), t = i % (pos + 1);
+    const int src = base + s_src[r];
+    st.anc[out][static_cast<long long>(base + r) * t_max + t] =
+        t < pos ? st.anc[in][static_cast<long long>(src) * t_max + t] : src;
+  }
+}
+
+// base.py:123-128: scores / seq_lengths, best beam, its tokens and length.
+__global__ void beam_final_kernel(BeamState st, int cur, int beam, int entry_len, int32_t* __restrict__ tokens,
+                                  int32_t* __restrict__ lengths, float* __restrict__ scores, int n_img) {
+  __shared__ int s_best;
+  const int b = blockIdx.x;
+  if (b >= n_img) return;
+  const int base = b * beam;
+  if (threadIdx.x == 0) {
+    int best = 0;
+    float bv = st.scores[base] / st.seq_len[base];
+    for (int j = 1; j < beam; ++j) {
+      const float v = st.scores[base + j] / st.seq_len[base + j];
+      if (v > bv) {
+        bv = v;
+        best = j;
+      }
+    }
+    s_best = best;
+    lengths[b] = static_cast<int32_t>(st.seq_len[base + best]);
+    scores[b] = bv;
+  }
+  __syncthreads();
+  const int len = static_cast<int>(st.seq_len[base + s_best]);
+  for (int t = threadIdx.x; t < entry_len; t += blockDim.x)
+    tokens[b * entry_len + t] = t < len ? st.tokens[cur][static_cast<long long>(base + s_best) * entry_len + t] : 0;
+}
+
+}  // namespace
+
+int gen_reset_run(int32_t* stopped, int32_t* lengths, unsigned long long* keys, int n, cudaStream_t s) {
+  gen_reset_kernel<<<(n + 255) / 256, 256, 0, s>>>(stopped, lengths, keys, n);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+int greedy_select_run(unsigned long long* keys, int32_t* tokens, int entry_len, int step, int32_t* stopped,
+                      int32_t* lengths, int stop_token, int n, cudaStream_t s) {
+  greedy_select_kernel<<<(n + 255) / 256, 256, 0, s>>>(keys, tokens, entry_len, step, stopped, lengths, stop_token, n);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+int row_topk_run(const float* logits, int64_t ldl, int V, float inv_temp, int beam, const int32_t* stopped,
+                 float* out_val, int32_t* out_idx, int rows, cudaStream_t s) {
+  CC_REQUIRE(beam >= 1 && beam <= kMaxBeam, CC_ESHAPE, "beam size %d outside 1..%d", beam, kMaxBeam);
+  row_topk_kernel<kMaxBeam><<<rows, TOPK_THREADS, 0, s>>>(logits, ldl, V, inv_temp, beam, stopped, out_val, out_idx);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+int beam_init_run(const float* cand_val, const int32_t* cand_idx, const BeamState& st, int beam, int entry_len,
+                  int t_max, int Tp, int stop_token, int n_img, cudaStream_t s) {
+  beam_init_kernel<<<n_img, 64, 0, s>>>(cand_val, cand_idx, st, beam, entry_len, t_max, Tp, stop_token, n_img);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+int beam_step_run(const float* cand_val, const int32_t* cand_idx, const BeamState& st, int in, int beam, int V,
+                  int entry_len, int t_max, int step, int pos, int stop_token, int n_img, cudaStream_t s) {
+  beam_step_kernel<kMaxBeam><<<n_img, 128, 0, s>>>(cand_val, cand_idx, st, in, beam, V, entry_len, t_max, step, pos,
+                                                    stop_token, n_img);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+int beam_final_run(const BeamState& st, int cur, int beam, int entry_len, int32_t* tokens, int32_t* lengths,
+                   float* scores, int n_img, cudaStream_t s) {
+  beam_final_kernel<<<n_img, 64, 0, s>>>(st, cur, beam, entry_len, tokens, lengths, scores, n_img);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+}  // namespace cc

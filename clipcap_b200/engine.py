@@ -1,0 +1,169 @@
+"""Thin Python owners of the C-ABI handles (include/clipcap_b200.h). Tensors in, tensors out; all arithmetic happens in
+libclipcap_b200.so on the caller's current CUDA stream. No fallbacks: a missing library or a non-sm_100 device raises."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional, Tuple
+
+import torch
+
+from . import _ffi
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"clipcap_b200: {what} must be a CUDA tensor (there is no CPU path); got device {t.device}")
+
+
+def _named(weights: Dict[str, torch.Tensor], device) -> Iterable[Tuple[str, torch.Tensor]]:
+    return [(k, v.detach().to(device=device, dtype=torch.float32).contiguous()) for k, v in weights.items()]
+
+
+class _Handle:
+    _destroy_name = ""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            getattr(_ffi.lib(), self._destroy_name)(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class VitEngine(_Handle):
+    """cc_vit_* — CLIP ViT image tower. `weights`: OpenAI-clip-named fp32 tensors (`visual.*`)."""
+    _destroy_name = "cc_vit_destroy"
+
+    def __init__(self, weights: Dict[str, torch.Tensor], image_size=224, patch=14, width=1024, layers=24, heads=16,
+                 mlp_dim=4096, out_dim=768, eps=1e-5, max_batch=256, device="cuda"):
+        super().__init__()
+        self.device = torch.device(device)
+        self.cfg = _ffi.cc_vit_cfg(image_size, patch, width, layers, heads, mlp_dim, out_dim, eps)
+        self.max_batch = max_batch
+        with torch.cuda.device(self.device):
+            arr, keep = _ffi.make_tensor_table(_named(weights, self.device))
+            _ffi.check(_ffi.lib().cc_vit_create(C.byref(self._h), C.byref(self.cfg), arr, len(keep), max_batch))
+            torch.cuda.synchronize()
+
+    def forward(self, pixels: torch.Tensor, normalize: bool = False, out_dtype: Optional[torch.dtype] = None):
+        _require_cuda(pixels, "pixels")
+        s = self.cfg.image_size
+        if pixels.dim() != 4 or tuple(pixels.shape[1:]) != (3, s, s):
+            raise ValueError(f"pixels must be [B, 3, {s}, {s}], got {tuple(pixels.shape)}")
+        pixels = pixels.contiguous()
+        out = torch.empty(pixels.shape[0], self.cfg.out_dim, device=pixels.device, dtype=out_dtype or pixels.dtype)
+        with torch.cuda.device(pixels.device):
+            _ffi.check(_ffi.lib().cc_vit_forward(self._h, pixels.data_ptr(), _ffi.torch_dtype_code(pixels),
+                                                 pixels.shape[0], int(bool(normalize)), out.data_ptr(),
+                                                 _ffi.torch_dtype_code(out), _ffi.current_stream_ptr()))
+        return out
+
+    @property
+    def last_launches(self) -> int:
+        return _ffi.lib().cc_vit_last_launches(self._h)
+
+
+class MapperEngine(_Handle):
+    """cc_mapper_* — TransformerMapper / TransformerMapperWindowed / MLP mapper. Keys relative to `transformer_mapper.`"""
+    _destroy_name = "cc_mapper_destroy"
+    KINDS = {"transformer": _ffi.CC_MAPPER_TRANSFORMER, "windowed": _ffi.CC_MAPPER_WINDOWED, "mlp": _ffi.CC_MAPPER_MLP}
+
+    def __init__(self, weights: Dict[str, torch.Tensor], kind="transformer", E=768, d=1024, P=10, K=40, H=8, L=8, W=1,
+                 use_pos=False, eps=1e-5, max_batch=256, device="cuda"):
+        super().__init__()
+        self.device = torch.device(device)
+        self.kind = kind
+        self.cfg = _ffi.cc_mapper_cfg(self.KINDS[kind], E, d, P, K, H, L, W, int(bool(use_pos)), eps)
+        self.max_batch = max_batch
+        with torch.cuda.device(self.device):
+            arr, keep = _ffi.make_tensor_table(_named(weights, self.device))
+            _ffi.check(_ffi.lib().cc_mapper_create(C.byref(self._h), C.byref(self.cfg), arr, len(keep), max_batch))
+            torch.cuda.synchronize()
+
+    def forward(self, emb: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        _require_cuda(emb, "embeddings")
+        c = self.cfg
+        want = (c.W, c.E) if self.kind == "windowed" else (c.E,)
+        if tuple(emb.shape[1:]) != want:
+            raise ValueError(f"embeddings must be [B, {', '.join(map(str, want))}], got {tuple(emb.shape)}")
+        emb = emb.contiguous()
+        out = torch.empty(emb.shape[0], c.K, c.d, device=emb.device, dtype=out_dtype or emb.dtype)
+        with torch.cuda.device(emb.device):
+            _ffi.check(_ffi.lib().cc_mapper_forward(self._h, emb.data_ptr(), _ffi.torch_dtype_code(emb), emb.shape[0],
+                                                    out.data_ptr(), _ffi.torch_dtype_code(out),
+                                                    _ffi.current_stream_ptr()))
+        return out
+
+    @property
+    def last_launches(self) -> int:
+        return _ffi.lib().cc_mapper_last_launches(self._h)
+
+
+class Gpt2Engine(_Handle):
+    """cc_gpt2_* / cc_generate — GPT-2 forward, embedding lookup and the decode loops. Keys relative to
+    `language_model.` (HF GPT2LMHeadModel names)."""
+    _destroy_name = "cc_gpt2_destroy"
+
+    def __init__(self, weights: Dict[str, torch.Tensor], d=1024, L=24, H=16, V=50257, n_pos=1024, eps=1e-5,
+                 max_seqs=256, max_len=64, device="cuda"):
+        super().__init__()
+        self.device = torch.device(device)
+        self.cfg = _ffi.cc_gpt2_cfg(d, L, H, V, n_pos, eps)
+        self.max_seqs, self.max_len = max_seqs, max_len
+        with torch.cuda.device(self.device):
+            arr, keep = _ffi.make_tensor_table(_named(weights, self.device))
+            _ffi.check(_ffi.lib().cc_gpt2_create(C.byref(self._h), C.byref(self.cfg), arr, len(keep), max_seqs, max_len))
+            torch.cuda.synchronize()
+
+    def logits(self, embeds: torch.Tensor, all_positions: bool = False) -> torch.Tensor:
+        _require_cuda(embeds, "inputs_embeds")
+        if embeds.dim() != 3 or embeds.shape[2] != self.cfg.d:
+            raise ValueError(f"inputs_embeds must be [B, T, {self.cfg.d}], got {tuple(embeds.shape)}")
+        embeds = embeds.contiguous()
+        B, T, _ = embeds.shape
+        shape = (B, T, self.cfg.V) if all_positions else (B, self.cfg.V)
+        out = torch.empty(shape, device=embeds.device, dtype=torch.float32)
+        with torch.cuda.device(embeds.device):
+            _ffi.check(_ffi.lib().cc_gpt2_logits(self._h, embeds.data_ptr(), _ffi.torch_dtype_code(embeds), B, T,
+                                                 int(all_positions), out.data_ptr(), _ffi.current_stream_ptr()))
+        return out
+
+    def embed(self, ids: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        _require_cuda(ids, "token ids")
+        flat = ids.reshape(-1).to(torch.int32).contiguous()
+        out = torch.empty(flat.numel(), self.cfg.d, device=ids.device, dtype=dtype)
+        if flat.numel():
+            with torch.cuda.device(ids.device):
+                _ffi.check(_ffi.lib().cc_gpt2_embed(self._h, flat.data_ptr(), flat.numel(), out.data_ptr(),
+                                                    _ffi.torch_dtype_code(out), _ffi.current_stream_ptr()))
+        return out.view(*ids.shape, self.cfg.d)
+
+    def generate(self, prefix: torch.Tensor, mode: str = "greedy", beam: int = 1, entry_length: int = 67,
+                 temperature: float = 1.0, stop_token: int = 50256):
+        """-> (tokens int32 [B, entry_length], lengths int32 [B], scores fp32 [B]) on the device, no host sync."""
+        _require_cuda(prefix, "prefix embeddings")
+        if prefix.dim() != 3 or prefix.shape[2] != self.cfg.d:
+            raise ValueError(f"prefix must be [B, Tp, {self.cfg.d}], got {tuple(prefix.shape)}")
+        prefix = prefix.contiguous()
+        B, Tp, _ = prefix.shape
+        g = _ffi.cc_gen_cfg(_ffi.CC_GEN_BEAM if mode == "beam" else _ffi.CC_GEN_GREEDY, beam, entry_length,
+                            float(temperature), stop_token)
+        tokens = torch.empty(B, entry_length, device=prefix.device, dtype=torch.int32)
+        lengths = torch.empty(B, device=prefix.device, dtype=torch.int32)
+        scores = torch.empty(B, device=prefix.device, dtype=torch.float32)
+        with torch.cuda.device(prefix.device):
+            _ffi.check(_ffi.lib().cc_generate(self._h, prefix.data_ptr(), _ffi.torch_dtype_code(prefix), B, Tp,
+                                              C.byref(g), tokens.data_ptr(), lengths.data_ptr(), scores.data_ptr(),
+                                              _ffi.current_stream_ptr()))
+        return tokens, lengths, scores
+
+    @property
+    def last_launches(self) -> int:
+        return _ffi.lib().cc_gpt2_last_launches(self._h)

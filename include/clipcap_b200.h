@@ -78,6 +78,8 @@ int cc_vit_create(cc_vit** h, const cc_vit_cfg* cfg, const cc_tensor* weights, i
 /* pixels: [B,3,S,S] CLIP-normalised, dtype pix_dtype; out: [B,out_dim], dtype out_dtype. */
 int cc_vit_forward(cc_vit* h, const void* pixels, int pix_dtype, int B, int normalize, void* out, int out_dtype,
                    void* stream);
+/* number of kernel launches the last cc_vit_forward enqueued */
+int cc_vit_last_launches(cc_vit* h);
 void cc_vit_destroy(cc_vit* h);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -110,6 +112,8 @@ int cc_mapper_create(cc_mapper** h, const cc_mapper_cfg* cfg, const cc_tensor* w
 /* emb: [B,E] (or [B,W,E] windowed); prefix: [B,K,d]. */
 int cc_mapper_forward(cc_mapper* h, const void* emb, int emb_dtype, int B, void* prefix, int prefix_dtype,
                       void* stream);
+/* number of kernel launches the last cc_mapper_forward enqueued */
+int cc_mapper_last_launches(cc_mapper* h);
 void cc_mapper_destroy(cc_mapper* h);
 
 /* ------------------------------------------------------------------------------------------------------------------

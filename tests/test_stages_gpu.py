@@ -1,0 +1,152 @@
+"""Parity of the three stage engines (through the C ABI) against the CPU oracle on identical seeded inputs/weights.
+Tolerance: 1e-3 relative (max|a-b|/max|b|) for stage outputs — BASELINE.json north_star; fp16 operands, fp32 accumulate."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import restate as R
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.mark.parametrize("cfg,B", [
+    (R.MapperCfg(E=64, d=128, P=3, K=5, H=2, L=2), 4),       # hd 64
+    (R.MapperCfg(E=72, d=96, P=2, K=4, H=2, L=1), 3),        # hd 48
+    (R.MapperCfg(E=64, d=192, P=4, K=3, H=2, L=2), 2),       # hd 96
+    (R.MapperCfg(E=512, d=256, P=1, K=7, H=2, L=3), 5),      # hd 128
+    (R.MapperCfg(E=768, d=768, P=10, K=10, H=8, L=8), 2),    # config #1-like (GPT-2-small width)
+    (R.MapperCfg(kind="windowed", E=64, d=128, P=2, K=5, H=2, L=2, W=3, use_pos=True), 3),
+    (R.MapperCfg(kind="windowed", E=64, d=128, P=2, K=5, H=2, L=2, W=2, use_pos=False), 2),
+    (R.MapperCfg(kind="mlp", E=64, d=128, K=4), 3),
+])
+def test_mapper_matches_oracle(cuda_device, cfg, B):
+    from clipcap_b200.engine import MapperEngine
+    w = synth.mapper_weights(cfg)
+    emb = synth.embeddings(B * (cfg.W if cfg.kind == "windowed" else 1), cfg.E)
+    if cfg.kind == "windowed":
+        emb = emb.view(B, cfg.W, cfg.E)
+    ref = R.mapper_forward(w, emb, cfg)
+    eng = MapperEngine(w, kind=cfg.kind, E=cfg.E, d=cfg.d, P=cfg.P, K=cfg.K, H=cfg.H, L=cfg.L, W=cfg.W,
+                       use_pos=cfg.use_pos, max_batch=B + 1, device=cuda_device)
+    for dt in (torch.float32, torch.float16):
+        out = eng.forward(emb.to(cuda_device, dt))
+        assert out.dtype == dt and tuple(out.shape) == (B, cfg.K, cfg.d)
+        assert rel_err(out, ref) < (TOL if dt == torch.float32 else 2e-3)
+    assert eng.last_launches > 0
+
+
+@pytest.mark.parametrize("cfg,B", [
+    (R.VitCfg(image_size=28, patch=14, width=128, layers=2, heads=2, mlp_dim=256, out_dim=64), 3),
+    (R.VitCfg(image_size=56, patch=14, width=256, layers=3, heads=4, mlp_dim=512, out_dim=96), 2),
+])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_vit_matches_oracle(cuda_device, cfg, B, normalize):
+    from clipcap_b200.engine import VitEngine
+    w = synth.vit_weights(cfg)
+    px = synth.pixels(B, cfg.image_size)
+    ref = R.vit_encode(w, px, cfg, normalize)
+    eng = VitEngine(w, cfg.image_size, cfg.patch, cfg.width, cfg.layers, cfg.heads, cfg.mlp_dim, cfg.out_dim,
+                    max_batch=B, device=cuda_device)
+    out = eng.forward(px.to(cuda_device), normalize=normalize)
+    assert rel_err(out, ref) < TOL
+    out16 = eng.forward(px.to(cuda_device).half(), normalize=normalize)
+    assert out16.dtype == torch.float16 and rel_err(out16, ref) < 3e-3
+
+
+def test_vit_l14_one_image(cuda_device):
+    """Full-size ViT-L/14 on one image (the oracle needs ~1 s of CPU)."""
+    from clipcap_b200.engine import VitEngine
+    cfg = R.VitCfg()
+    w = synth.vit_weights(cfg)
+    px = synth.pixels(2, 224)
+    ref = R.vit_encode(w, px, cfg)
+    eng = VitEngine(w, max_batch=2, device=cuda_device)
+    out = eng.forward(px.to(cuda_device))
+    assert rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize("cfg,B,T", [
+    (R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64), 3, 7),
+    (R.Gpt2Cfg(d=192, L=3, H=3, V=517, n_pos=32), 2, 1),
+    (R.Gpt2Cfg(d=768, L=12, H=12, V=50257, n_pos=1024), 2, 12),  # GPT-2-small
+])
+def test_gpt2_logits_match_oracle(cuda_device, cfg, B, T):
+    from clipcap_b200.engine import Gpt2Engine
+    w = synth.gpt2_weights(cfg)
+    x = torch.randn(B, T, cfg.d, generator=torch.Generator().manual_seed(7))
+    ref = R.gpt2_logits(w, x, cfg)
+    eng = Gpt2Engine(w, cfg.d, cfg.L, cfg.H, cfg.V, cfg.n_pos, max_seqs=B, max_len=T + 2, device=cuda_device)
+    last = eng.logits(x.to(cuda_device))
+    assert rel_err(last, ref[:, -1]) < TOL
+    full = eng.logits(x.to(cuda_device), all_positions=True)
+    assert rel_err(full, ref) < TOL
+    ids = torch.tensor([[0, 5, cfg.V - 1], [1, 2, 3]], device=cuda_device)
+    assert torch.equal(eng.embed(ids).cpu(), w["transformer.wte.weight"][ids.cpu()])
+
+
+# ------------------------------------------------------------------------------------------------ decode loops
+from helpers import check_tokens_against_oracle  # noqa: E402
+
+
+def _lm_setup(cfg, B, Tp, seed=11, wte_std=0.1):
+    w = synth.gpt2_weights(cfg, wte_std=wte_std)
+    prefix = torch.randn(B, Tp, cfg.d, generator=torch.Generator().manual_seed(seed)) * 0.5
+    return w, prefix
+
+
+@pytest.mark.parametrize("cfg,B,Tp,EL", [
+    (R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64), 5, 5, 10),
+    (R.Gpt2Cfg(d=192, L=3, H=3, V=517, n_pos=48), 3, 1, 12),
+])
+def test_greedy_matches_oracle(cuda_device, cfg, B, Tp, EL):
+    from clipcap_b200.engine import Gpt2Engine
+    w, prefix = _lm_setup(cfg, B, Tp)
+    stop = cfg.V - 1
+    oracle = R.generate_greedy_batch(w, cfg, prefix, EL, stop)
+    eng = Gpt2Engine(w, cfg.d, cfg.L, cfg.H, cfg.V, cfg.n_pos, max_seqs=B, max_len=Tp + EL, device=cuda_device)
+    for _ in range(2):  # second call replays the captured CUDA graph
+        toks, lens, _ = eng.generate(prefix.to(cuda_device), "greedy", 1, EL, 1.0, stop)
+        exact, flips = check_tokens_against_oracle(toks, lens, oracle, margin_tol=5e-3)
+        assert exact >= B - 1
+    assert eng.last_launches > 0
+
+
+def test_greedy_stop_token(cuda_device):
+    """Stop-token bookkeeping of generate_beam(beam_size=1): tokens end with the stop token, length counts it."""
+    from clipcap_b200.engine import Gpt2Engine
+    cfg, B, Tp, EL = R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64), 4, 5, 10
+    w, prefix = _lm_setup(cfg, B, Tp)
+    free = R.generate_greedy_batch(w, cfg, prefix, EL, stop_token=cfg.V + 7)
+    stop = free[0][0][3]  # sample 0 will now stop at (or before) step 3
+    oracle = R.generate_greedy_batch(w, cfg, prefix, EL, stop)
+    assert len(oracle[0][0]) <= 4
+    eng = Gpt2Engine(w, cfg.d, cfg.L, cfg.H, cfg.V, cfg.n_pos, max_seqs=B, max_len=Tp + EL, device=cuda_device)
+    toks, lens, _ = eng.generate(prefix.to(cuda_device), "greedy", 1, EL, 1.0, stop)
+    exact, _ = check_tokens_against_oracle(toks, lens, oracle, margin_tol=5e-3)
+    assert exact >= B - 1
+    assert lens[0].item() == len(oracle[0][0])
+
+
+@pytest.mark.parametrize("beam", [1, 3, 5])
+@pytest.mark.parametrize("temperature", [1.0, 0.7])
+def test_beam_matches_oracle(cuda_device, beam, temperature):
+    from clipcap_b200.engine import Gpt2Engine
+    cfg, B, Tp, EL = R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64), 4, 5, 9
+    w, prefix = _lm_setup(cfg, B, Tp)
+    free = R.generate_beam(w, cfg, prefix[:1], beam, EL, temperature, cfg.V + 7)[0]
+    stop = free[4]  # make at least one beam of sample 0 terminate early
+    eng = Gpt2Engine(w, cfg.d, cfg.L, cfg.H, cfg.V, cfg.n_pos, max_seqs=B * beam, max_len=Tp + EL, device=cuda_device)
+    toks, lens, scores = eng.generate(prefix.to(cuda_device), "beam", beam, EL, temperature, stop)
+    toks, lens, scores = toks.cpu().tolist(), lens.cpu().tolist(), scores.cpu().tolist()
+    n_exact = 0
+    for i in range(B):
+        otoks, oscore, _ = R.generate_beam(w, cfg, prefix[i:i + 1], beam, EL, temperature, stop)
+        got = toks[i][:lens[i]]
+        if got == otoks:
+            n_exact += 1
+            assert abs(scores[i] - oscore) < 2e-3 * max(1.0, abs(oscore))
+        else:  # only a near-tie between beams may differ: the returned score must then match the oracle's best
+            assert abs(scores[i] - oscore) < 2e-3 * max(1.0, abs(oscore)), (i, got, otoks, scores[i], oscore)
+    assert n_exact >= B - 1
