@@ -76,6 +76,8 @@ PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {
     "cc_generate": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(cc_gen_cfg), _vp, _vp, _vp, _vp]),
     "cc_gpt2_last_launches": (_i, [_vp]),
     "cc_gpt2_destroy": (None, [_vp]),
+    "cc_prof_enable": (None, [_i]),
+    "cc_prof_read": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "cc_op_gemm": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "cc_op_layernorm": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _vp]),
     "cc_op_attention": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp]),

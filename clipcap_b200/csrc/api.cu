@@ -8,6 +8,13 @@ const char* cc_last_error(void) { return cc::get_error(); }
 
 const char* cc_version(void) { return "clipcap_b200 0.1.0 sm_100a"; }
 
+void cc_prof_enable(int on) { cc::gemm_prof_enable(on != 0); }
+
+void cc_prof_read(double* ms, double* flops, long long* n) {
+  if (ms == nullptr || flops == nullptr || n == nullptr) return;
+  cc::gemm_prof_read(ms, flops, n);
+}
+
 int cc_op_gemm(const void* a, int64_t lda, const void* w, const float* bias, void* out, int64_t ldc, int M, int N, int K,
                int epi, int bn, void* stream) {
   using namespace cc;

@@ -399,9 +399,67 @@ int gemm_plan(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __h
   return CC_OK;
 }
 
+// ------------------------------------------------------------------ live per-launch timing (bench.py roofline)
+namespace {
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  double flops;
+  int bn;
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+int gemm_dispatch(const GemmPlan& p, int bn, int M, cudaStream_t s);
+}  // namespace
+
+void gemm_prof_enable(bool on) {
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  g_prof_on = on;
+}
+
+// Sums duration / algorithmic FLOPs (2*M*N*K) over the recorded launches of the 128x256 tile (the dominant kernel).
+void gemm_prof_read(double* ms, double* flops, long long* n) {
+  *ms = 0;
+  *flops = 0;
+  *n = 0;
+  cudaDeviceSynchronize();
+  for (auto& r : g_prof) {
+    if (r.bn != 256) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) continue;
+    *ms += t;
+    *flops += r.flops;
+    *n += 1;
+  }
+}
+
 int gemm_run(const GemmPlan& p, int M, cudaStream_t s) {
   CC_REQUIRE(M > 0 && M <= p.max_rows, CC_ESHAPE, "gemm_run: M=%d outside plan (max %d)", M, p.max_rows);
   const int bn = p.force_bn ? p.force_bn : gemm_pick_bn(M, p.N);
+  if (g_prof_on) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cs);
+    if (cs == cudaStreamCaptureStatusNone) {
+      ProfRec r;
+      r.flops = 2.0 * M * p.N * p.K;
+      r.bn = bn;
+      CC_CUDA(cudaEventCreate(&r.e0));
+      CC_CUDA(cudaEventCreate(&r.e1));
+      CC_CUDA(cudaEventRecord(r.e0, s));
+      const int st = gemm_dispatch(p, bn, M, s);
+      CC_CUDA(cudaEventRecord(r.e1, s));
+      g_prof.push_back(r);
+      return st;
+    }
+  }
+  return gemm_dispatch(p, bn, M, s);
+}
+
+namespace {
+int gemm_dispatch(const GemmPlan& p, int bn, int M, cudaStream_t s) {
   switch (bn) {
     case 16: return launch_epi<16>(p, 0, M, s);
     case 32: return launch_epi<32>(p, 1, M, s);
@@ -412,5 +470,6 @@ int gemm_run(const GemmPlan& p, int M, cudaStream_t s) {
   set_error("gemm_run: unsupported BLOCK_N %d", bn);
   return CC_EINVAL;
 }
+}  // namespace
 
 }  // namespace cc

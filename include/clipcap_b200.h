@@ -179,6 +179,12 @@ int cc_op_attention(const void* q, const void* k, const void* v, int64_t ld, voi
 int cc_op_decode_attention(const void* qkv, void* kcache, void* vcache, const int32_t* anc, void* o, int nseq, int H,
                            int t_max, int pos, float scale, void* stream);
 
+/* Live per-launch timing of the dominant kernel (the 128x256-tile tcgen05 GEMM): while enabled, every such launch that
+ * is not inside a graph capture is bracketed by CUDA events on its own stream. cc_prof_read synchronises the device and
+ * returns the summed duration (ms), algorithmic FLOPs (2*M*N*K) and launch count since cc_prof_enable(1). */
+void cc_prof_enable(int on);
+void cc_prof_read(double* ms, double* flops, long long* n);
+
 #ifdef __cplusplus
 }
 #endif

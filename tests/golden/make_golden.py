@@ -1,0 +1,75 @@
+"""Freezes outputs of the REFERENCE (TheoCoombes/ClipCap imported unmodified from /root/reference, plus the third-party
+modules it calls: transformers GPT-2 / CLIP) on seeded inputs into tests/golden/*.npz. Run in the build container:
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden vectors of its own, so these are "outputs of the reference itself run here".
+Weights are regenerated from seeds at test time (oracle/synth.py); each fixture stores a checksum of them so RNG drift
+between torch builds is detected instead of silently comparing against different weights.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref_runner as RR  # noqa: E402
+from oracle import restate as R  # noqa: E402
+from oracle import synth  # noqa: E402
+
+CASES = {
+    # name: (lm spec, Gpt2Cfg, MapperCfg, beams)
+    "tiny_a": ("tiny:128:2:2:1003:64", R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64),
+               R.MapperCfg(E=64, d=128, P=3, K=5, H=2, L=2)),
+    "tiny_b": ("tiny:192:3:3:517:48", R.Gpt2Cfg(d=192, L=3, H=3, V=517, n_pos=48),
+               R.MapperCfg(E=72, d=192, P=2, K=4, H=2, L=1)),
+}
+VIT = R.VitCfg(image_size=28, patch=14, width=128, layers=2, heads=2, mlp_dim=512, out_dim=64)
+ENTRY = 9
+
+
+def main():
+    assert RR.available(), "needs /root/reference"
+    torch.manual_seed(0)
+    for name, (spec, gcfg, mcfg) in CASES.items():
+        map_w, lm_w = synth.mapper_weights(mcfg), synth.gpt2_weights(gcfg, wte_std=0.1)
+        model = RR.build_reference_model(spec, mcfg.E, mcfg.K, mcfg.P, mcfg.H, mcfg.L, map_w, lm_w)
+        B = 4
+        emb = synth.embeddings(B, mcfg.E)
+        out = {"emb": emb.numpy(), "w_checksum": np.float64(synth.checksum(map_w) + synth.checksum(lm_w))}
+        with torch.no_grad():
+            prefix = model.transformer_mapper(emb)                       # reference TransformerMapper
+            out["prefix"] = prefix.numpy()
+            out["logits"] = model.language_model(inputs_embeds=prefix).logits.numpy()  # HF GPT-2 via the reference model
+            free = RR.reference_generate_beam(model, prefix[:1], 1, ENTRY, 1.0, stop_token=gcfg.V + 7)
+            stop = free[4]
+            out["stop_token"] = np.int64(stop)
+            for beam in (1, 3, 5):
+                for temp in (1.0, 0.7):
+                    rows = [RR.reference_generate_beam(model, prefix[i:i + 1], beam, ENTRY, temp, stop) for i in range(B)]
+                    arr = np.full((B, ENTRY), -1, dtype=np.int64)
+                    for i, r in enumerate(rows):
+                        arr[i, :len(r)] = r
+                    out[f"beam{beam}_t{temp}"] = arr
+            # ClipCapModel.forward (teacher-forced logits, model.py:43-58)
+            tokens = torch.randint(0, gcfg.V, (B, 6), generator=torch.Generator().manual_seed(3))
+            mask = torch.ones(B, 6, dtype=torch.bool)
+            out["fwd_tokens"] = tokens.numpy()
+            out["fwd_logits"] = model(tokens, emb, mask).logits.numpy()
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+        print(name, {k: getattr(v, "shape", v) for k, v in out.items()})
+    # ViT (HF CLIP stand-in inside the reference's CLIPModel wrapper), with and without normalisation
+    vit_w = synth.vit_weights(VIT)
+    px = synth.pixels(3, VIT.image_size)
+    with torch.no_grad():
+        out = {"pixels": px.numpy(), "w_checksum": np.float64(synth.checksum(vit_w)),
+               "emb": RR.reference_clip_model(VIT, vit_w, False)(px).numpy(),
+               "emb_norm": RR.reference_clip_model(VIT, vit_w, True)(px.clone()).numpy()}
+    np.savez_compressed(os.path.join(HERE, "vit_tiny.npz"), **out)
+    print("vit_tiny", {k: getattr(v, "shape", v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,43 @@
+"""Loads the committed golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the reference)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate as R
+from oracle import synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+LM_CASES = {
+    "tiny_a": ("tiny:128:2:2:1003:64", R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64),
+               R.MapperCfg(E=64, d=128, P=3, K=5, H=2, L=2)),
+    "tiny_b": ("tiny:192:3:3:517:48", R.Gpt2Cfg(d=192, L=3, H=3, V=517, n_pos=48),
+               R.MapperCfg(E=72, d=192, P=2, K=4, H=2, L=1)),
+}
+VIT_CASE = R.VitCfg(image_size=28, patch=14, width=128, layers=2, heads=2, mlp_dim=512, out_dim=64)
+ENTRY = 9
+
+
+def load_lm_case(name):
+    spec, gcfg, mcfg = LM_CASES[name]
+    g = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"))
+    map_w, lm_w = synth.mapper_weights(mcfg), synth.gpt2_weights(gcfg, wte_std=0.1)
+    cs = synth.checksum(map_w) + synth.checksum(lm_w)
+    if abs(cs - float(g["w_checksum"])) > 1e-6 * abs(cs):
+        pytest.skip("seeded weights differ from the ones the fixture was made with (torch RNG drift): regenerate "
+                    "with tests/golden/make_golden.py")
+    return spec, gcfg, mcfg, map_w, lm_w, {k: g[k] for k in g.files}
+
+
+def load_vit_case():
+    g = np.load(os.path.join(GOLDEN_DIR, "vit_tiny.npz"))
+    w = synth.vit_weights(VIT_CASE)
+    if abs(synth.checksum(w) - float(g["w_checksum"])) > 1e-6 * synth.checksum(w):
+        pytest.skip("seeded weights differ from the fixture's (torch RNG drift)")
+    return VIT_CASE, w, {k: g[k] for k in g.files}
+
+
+def golden_rows(arr):
+    return [[int(t) for t in row if t >= 0] for row in arr]

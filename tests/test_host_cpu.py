@@ -1,0 +1,106 @@
+"""Host-side mirror of the reference interface: config dataclasses, state_dict key names, factories, error behaviour."""
+import dataclasses
+
+import pytest
+import torch
+
+from oracle import ref_runner as RR
+
+
+def _small_model():
+    from clipcap_b200.encoders import EncoderConfig
+    from clipcap_b200.model import ClipCapModelPrefixOnly, Config
+    return ClipCapModelPrefixOnly(Config(language_model="tiny:128:2:2:1003:64", prefix_length=5, projection_length=3,
+                                         transformer_layers=2, transformer_attention_heads=2,
+                                         encoder_config=EncoderConfig(encoder_embedding_size=64)))
+
+
+def test_top_level_surface():
+    import clipcap_b200
+    for name in ("get_encoder", "get_encoder_from_model", "load"):  # clipcap/__init__.py:1-2
+        assert callable(getattr(clipcap_b200, name))
+
+
+def test_config_defaults_match_reference_dataclasses():
+    from clipcap_b200.encoders import EncoderConfig
+    from clipcap_b200.model import Config, TrainingConfig
+    c = Config()
+    assert (c.language_model, c.prefix_length, c.projection_length, c.transformer_layers,
+            c.transformer_attention_heads, c.use_positional_embeddings) == ("gpt2-xl", 10, 10, 8, 16, True)
+    e = EncoderConfig()
+    assert (e.encoder_model_name, e.encoder_model_variant, e.window_size, e.normalize_embeddings) == \
+        ("clip", "ViT-L/14", 16, False)
+    assert set(Config(encoder_config=e).to_dict()["encoder_config"]) == {f.name for f in dataclasses.fields(EncoderConfig)}
+    if RR.available():
+        RR.import_reference()
+        from clipcap.encoders.config import EncoderConfig as RE
+        from clipcap.model.config import Config as RC, TrainingConfig as RT
+        assert Config().to_dict() == RC().to_dict()
+        assert EncoderConfig().to_dict() == RE().to_dict()
+        assert TrainingConfig().to_dict() == RT().to_dict()
+
+
+def test_state_dict_keys_match_reference():
+    m = _small_model()
+    keys = set(m.state_dict())
+    assert "transformer_mapper.prefix_const" in keys and "transformer_mapper.linear.weight" in keys
+    assert "transformer_mapper.transformer.layers.1.attn.to_keys_values.weight" in keys
+    assert "language_model.transformer.h.1.attn.c_attn.weight" in keys
+    assert m.state_dict()["language_model.transformer.h.0.attn.c_attn.weight"].shape == (128, 384)  # Conv1D [in, out]
+    if RR.available():
+        from oracle import restate as R, synth
+        ref = RR.build_reference_model("tiny:128:2:2:1003:64", 64, 5, 3, 2, 2,
+                                       synth.mapper_weights(R.MapperCfg(E=64, d=128, P=3, K=5, H=2, L=2)),
+                                       synth.gpt2_weights(R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64)))
+        ref_keys = {k for k in ref.state_dict() if not k.endswith("lm_head.weight")
+                    and not k.endswith(".attn.bias") and not k.endswith(".attn.masked_bias")}
+        assert keys == ref_keys
+        # a reference checkpoint loads as is
+        missing, unexpected = m.load_state_dict(ref.state_dict(), strict=False)
+        assert not missing, missing
+
+
+def test_mapper_default_init_is_rng_identical_to_reference():
+    if not RR.available():
+        pytest.skip("needs /root/reference")
+    RR.import_reference()
+    from clipcap.model.mapper import TransformerMapper as RefMapper
+    from clipcap_b200.model import TransformerMapper
+    torch.manual_seed(5)
+    a = RefMapper(64, 128, 5, 3, 2, 2).state_dict()
+    torch.manual_seed(5)
+    b = TransformerMapper(64, 128, 5, 3, 2, 2).state_dict()
+    assert list(a) == list(b)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_no_cpu_fallback():
+    m = _small_model()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.transformer_mapper(torch.randn(2, 64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.language_model(inputs_embeds=torch.randn(1, 3, 128))
+
+
+def test_factory_errors_match_reference():
+    import clipcap_b200 as clipcap
+    with pytest.raises(ValueError, match="invalid encoder name: 'x'"):  # encoders/base.py:25
+        clipcap.get_encoder("x", "y")
+    with pytest.raises(ValueError):
+        clipcap.get_encoder("clip", "RN50")
+    from clipcap_b200.model import GPT2LM, TransformerMapper
+    with pytest.raises(ValueError):
+        GPT2LM("llama-7b")
+    with pytest.raises(ValueError):
+        TransformerMapper(64, 100, 5, 3, num_heads=3)
+
+
+def test_product_package_never_imports_the_oracle():
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "clipcap_b200")
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
