@@ -88,7 +88,8 @@ enum Epi {
 
 struct GemmPlan {
   CUtensorMap map_a;     // A: [rows, K] fp16, row stride lda
-  CUtensorMap map_b[5];  // W: [N, K] fp16, one box height per BLOCK_N in {16, 32, 64, 128, 256}
+  CUtensorMap map_b[4];  // W: [N, K] fp16, one box height per BLOCK_N in {32, 64, 128, 256}
+  CUtensorMap map_c;     // out: [rows, N] fp16 / fp32 for the TMA store / reduce-add epilogues
   int max_rows = 0, N = 0, K = 0;
   int epi = EPI_F16_NONE;
   const float* bias = nullptr;

@@ -4,15 +4,18 @@
 // torch.nn.Linear keeps them (GPT-2's Conv1D [K,N] weights are transposed once at pack time). Accumulation is fp32 in
 // tensor memory.
 //
-// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes {64 x 128} of A and {64 x BN} of W into a ring of
 //               128B-swizzled shared-memory stages, completion counted on `full` mbarriers.
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::f16 (M=128, N=BN, K=16) x 4 per stage into one of two
 //               TMEM accumulator buffers; tcgen05.commit releases the smem stage (`empty`) and, after the last k-block,
 //               publishes the accumulator (`tmem_full`).
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp-instruction, thread == output row), bias /
-//               activation / residual / argmax, direct global stores; then `tmem_empty` lets the MMA warp reuse the
-//               buffer, so the epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 2..9  epilogue: two warps per TMEM lane quadrant, each owning half of the tile's columns. tcgen05.ld
+//               (thread == output row) -> bias / activation in registers -> 64-byte-swizzled per-warp staging buffer
+//               in shared memory -> one TMA store (fp16 outputs) or one TMA reduce-add (the fp32 residual update
+//               h += acc + bias happens in L2; h is never read by the SM) per 32-row x 64-byte chunk. fp32 logits
+//               and the fused argmax use direct stores / atomics. `tmem_empty` hands the accumulator back as soon as
+//               it has been read, so the epilogue of tile i overlaps the main loop of tile i+1.
 // Tiles are walked n-fastest so the A row-panel and the whole W stay L2 resident.
 #include "common.h"
 #include "ptx.cuh"
@@ -23,17 +26,21 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
+constexpr int STG_WARP_BYTES = 4096;  // per epilogue warp: two 32-row x 64-byte staging buffers
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kStageA = BM * BK * 2;
   static constexpr int kStageB = BN * BK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 6);
-  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);  // two accumulator buffers, power of two >= 32
+  static constexpr int kStages = BN >= 256 ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers (power of two >= 64)
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-  static constexpr int kSmem = kStages * kStage + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kStaging = EPI_WARPS * STG_WARP_BYTES;
+  static constexpr int kSplit = BN >= 64 ? 2 : 1;  // column halves handled by different epilogue warps
+  static constexpr int kSmem = kStages * kStage + kStaging + kBarBytes + 1024;  // + alignment slack
 };
 
 struct GemmArgs {
@@ -43,10 +50,22 @@ struct GemmArgs {
   long long ldc;
 };
 
-__device__ __forceinline__ float act_quickgelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
+// x * sigmoid(k x) with the two MUFU ops (ex2, rcp) at approximate precision: relative error ~2^-22, far below the
+// fp16 rounding of the result. k = 1.702 is CLIP's QuickGELU; gelu_new(x) = x * sigmoid(2u), u = sqrt(2/pi)(x + 0.044715 x^3),
+// because 0.5 (1 + tanh u) == sigmoid(2u); tanh(x) = 2 sigmoid(2x) - 1.
+__device__ __forceinline__ float fast_sigmoid_l2(float y_log2e) {  // sigmoid(y) given y * log2(e)
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-y_log2e));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
+__device__ __forceinline__ float act_quickgelu(float x) { return x * fast_sigmoid_l2(x * (1.702f * 1.4426950408889634f)); }
 __device__ __forceinline__ float act_gelu_new(float x) {
-  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  return 0.5f * x * (1.f + tanhf(u));
+  const float u2 = (2.f * 0.7978845608028654f * 1.4426950408889634f) * (x + 0.044715f * x * x * x);
+  return x * fast_sigmoid_l2(u2);
+}
+__device__ __forceinline__ float act_tanh(float x) {
+  return 2.f * fast_sigmoid_l2(x * (2.f * 1.4426950408889634f)) - 1.f;
 }
 
 template <int EPI>
@@ -54,7 +73,7 @@ __device__ __forceinline__ float apply_act(float x) {
   if constexpr (EPI == EPI_F16_RELU) return fmaxf(x, 0.f);
   if constexpr (EPI == EPI_F16_QUICKGELU) return act_quickgelu(x);
   if constexpr (EPI == EPI_F16_GELU_NEW) return act_gelu_new(x);
-  if constexpr (EPI == EPI_F16_TANH) return tanhf(x);
+  if constexpr (EPI == EPI_F16_TANH) return act_tanh(x);
   return x;
 }
 
@@ -63,13 +82,24 @@ __device__ __forceinline__ uint32_t float_order_key(float x) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+template <int EPI>
+struct EpiTraits {
+  static constexpr bool kTma = EPI <= EPI_F16_TANH || EPI == EPI_RESID_F32;
+};
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs args) {
+gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_c, GemmArgs args) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStage;
+  const uint32_t stg_base = smem_base + Cfg::kStages * Cfg::kStage;  // 1024-byte aligned
+  const uint32_t bar_base = stg_base + Cfg::kStaging;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
@@ -89,13 +119,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if constexpr (EpiTraits<EPI>::kTma) tma_prefetch_desc(&map_c);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), 4 * Cfg::kSplit);  // one arrive per active epilogue warp
     }
     fence_mbar_init();
   }
@@ -163,124 +194,177 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         umma_commit(tfull_bar(as));
       }
     }
-  } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+  } else if ((warp - 2) < 4 * Cfg::kSplit) {
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int ew = warp - 2;
+    const int quad = warp & 3;        // TMEM lane quadrant this warp may access
+    const int half_id = ew >> 2;      // which column half of the tile
+    constexpr int WCOLS = BN / Cfg::kSplit;  // accumulator columns this warp owns per tile
+    const int col_base = half_id * WCOLS;
     const int row_in_tile = quad * 32 + lane;
-    constexpr int CH = BN < 32 ? BN : 32;  // columns per tcgen05.ld
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const int m0 = (tile / tiles_n) * BM;
-      const int n0 = (tile % tiles_n) * BN;
-      const int m = m0 + row_in_tile;
-      const bool row_ok = m < args.M;
-      mbar_wait(tfull_bar(as), (it >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
 
-      float best = -INFINITY;
-      int best_n = 0x7fffffff;
+    if constexpr (EpiTraits<EPI>::kTma) {
+      // 64 bytes of output per row and chunk: 32 fp16 or 16 fp32 columns.
+      constexpr bool kF32 = (EPI == EPI_RESID_F32);
+      constexpr int CH = kF32 ? 16 : 32;
+      constexpr int NCH = WCOLS / CH;
+      const uint32_t stg = stg_base + ew * STG_WARP_BYTES;
+      // 64-byte swizzle: 16-byte chunk index ^= (row >> 1) & 3
+      const uint32_t row_off = lane * 64;
+      const uint32_t sw = (lane >> 1) & 3;
+      uint32_t chunk_no = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const int m0 = (tile / tiles_n) * BM;
+        const int n0 = (tile % tiles_n) * BN;
+        const bool rows_live = (m0 + quad * 32) < args.M;  // warp-uniform
+        mbar_wait(tfull_bar(as), (it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + col_base;
 
-#pragma unroll 1
-      for (int c = 0; c < BN / CH; ++c) {
-        const int nc = n0 + c * CH;
-        if (nc >= args.N) break;  // warp-uniform
-        uint32_t r[CH];
-        if constexpr (CH == 32) tmem_ld_x32(t_row + c * CH, r);
-        else tmem_ld_x16(t_row + c * CH, r);
-        tmem_ld_wait();
-        const bool full_chunk = nc + CH <= args.N;
-
-        if constexpr (EPI == EPI_ARGMAX) {
-          if (row_ok) {
+        uint32_t r[2][CH];
+        if constexpr (CH == 32) tmem_ld_x32(t_row, r[0]);
+        else tmem_ld_x16(t_row, r[0]);
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-              const float v = __uint_as_float(r[j]);
-              if (nc + j < args.N && v > best) {  // strict > keeps the lowest index on ties
-                best = v;
-                best_n = nc + j;
-              }
-            }
+        for (int c = 0; c < NCH; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < NCH) {
+            if constexpr (CH == 32) tmem_ld_x32(t_row + (c + 1) * CH, r[(c + 1) & 1]);
+            else tmem_ld_x16(t_row + (c + 1) * CH, r[(c + 1) & 1]);
+          } else {
+            // accumulator fully read (last load has landed): hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
           }
-        } else {
+          const int nc = n0 + col_base + c * CH;
+          if (nc >= args.N || !rows_live) continue;  // warp-uniform
+          const uint32_t(&rc)[CH] = r[c & 1];
           float v[CH];
           if (args.bias != nullptr) {
-            if (full_chunk) {
+            if (nc + CH <= args.N) {
 #pragma unroll
               for (int j = 0; j < CH; j += 4) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + nc + j));
-                v[j] = __uint_as_float(r[j]) + b4.x;
-                v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-                v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
-                v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+                v[j] = __uint_as_float(rc[j]) + b4.x;
+                v[j + 1] = __uint_as_float(rc[j + 1]) + b4.y;
+                v[j + 2] = __uint_as_float(rc[j + 2]) + b4.z;
+                v[j + 3] = __uint_as_float(rc[j + 3]) + b4.w;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < CH; ++j)
-                v[j] = __uint_as_float(r[j]) + (nc + j < args.N ? __ldg(args.bias + nc + j) : 0.f);
+                v[j] = __uint_as_float(rc[j]) + (nc + j < args.N ? __ldg(args.bias + nc + j) : 0.f);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(rc[j]);
           }
+          // staging buffer (chunk_no & 1) is free once the bulk store issued two chunks ago has read it
+          const uint32_t buf = stg + (chunk_no & 1u) * 2048u + row_off;
+          ++chunk_no;
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          if constexpr (kF32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(buf + ((q ^ sw) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+                           __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(buf + ((q ^ sw) << 4), pack_half2(apply_act<EPI>(v[8 * q]), apply_act<EPI>(v[8 * q + 1])),
+                           pack_half2(apply_act<EPI>(v[8 * q + 2]), apply_act<EPI>(v[8 * q + 3])),
+                           pack_half2(apply_act<EPI>(v[8 * q + 4]), apply_act<EPI>(v[8 * q + 5])),
+                           pack_half2(apply_act<EPI>(v[8 * q + 6]), apply_act<EPI>(v[8 * q + 7])));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kF32) tma_reduce_add_2d(&map_c, buf - row_off, nc, m0 + quad * 32);
+            else tma_store_2d(&map_c, buf - row_off, nc, m0 + quad * 32);
+            bulk_commit();
+          }
+        }
+      }
+      if (lane == 0) bulk_wait<0>();  // all global writes of this warp are complete before the CTA exits
+    } else {
+      // fp32 logits (arbitrary ldc) and fused argmax: direct global stores / atomics, thread == output row
+      constexpr int CH = WCOLS < 32 ? WCOLS : 32;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const int m0 = (tile / tiles_n) * BM;
+        const int n0 = (tile % tiles_n) * BN;
+        const int m = m0 + row_in_tile;
+        const bool row_ok = m < args.M;
+        mbar_wait(tfull_bar(as), (it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + col_base;
 
-          if (row_ok) {
-            if constexpr (EPI <= EPI_F16_TANH) {
-              __half* dst = reinterpret_cast<__half*>(args.out) + static_cast<long long>(m) * args.ldc + nc;
-              if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+        float best = -INFINITY;
+        int best_n = 0x7fffffff;
+
+#pragma unroll 1
+        for (int c = 0; c < WCOLS / CH; ++c) {
+          const int nc = n0 + col_base + c * CH;
+          if (nc >= args.N) break;  // warp-uniform
+          uint32_t r[CH];
+          if constexpr (CH == 32) tmem_ld_x32(t_row + c * CH, r);
+          else tmem_ld_x16(t_row + c * CH, r);
+          tmem_ld_wait();
+          const bool full_chunk = nc + CH <= args.N;
+
+          if constexpr (EPI == EPI_ARGMAX) {
+            if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < CH; j += 8) {
-                  uint4 q;
-                  q.x = pack_half2(apply_act<EPI>(v[j]), apply_act<EPI>(v[j + 1]));
-                  q.y = pack_half2(apply_act<EPI>(v[j + 2]), apply_act<EPI>(v[j + 3]));
-                  q.z = pack_half2(apply_act<EPI>(v[j + 4]), apply_act<EPI>(v[j + 5]));
-                  q.w = pack_half2(apply_act<EPI>(v[j + 6]), apply_act<EPI>(v[j + 7]));
-                  *reinterpret_cast<uint4*>(dst + j) = q;
+              for (int j = 0; j < CH; ++j) {
+                const float v = __uint_as_float(r[j]);
+                if (nc + j < args.N && v > best) {  // strict > keeps the lowest index on ties
+                  best = v;
+                  best_n = nc + j;
                 }
-              } else {
-#pragma unroll
-                for (int j = 0; j < CH; ++j)
-                  if (nc + j < args.N) dst[j] = __float2half_rn(apply_act<EPI>(v[j]));
               }
-            } else if constexpr (EPI == EPI_F32 || EPI == EPI_RESID_F32) {
+            }
+          } else {
+            static_assert(EPI == EPI_F32 || EPI == EPI_ARGMAX, "direct epilogue handles fp32 stores and argmax only");
+            if (row_ok) {
               float* dst = reinterpret_cast<float*>(args.out) + static_cast<long long>(m) * args.ldc + nc;
               if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
                 for (int j = 0; j < CH; j += 4) {
-                  float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                  if constexpr (EPI == EPI_RESID_F32) {
-                    const float4 h = *reinterpret_cast<const float4*>(dst + j);
-                    o.x += h.x;
-                    o.y += h.y;
-                    o.z += h.z;
-                    o.w += h.w;
+                  float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                         __uint_as_float(r[j + 3]));
+                  if (args.bias != nullptr) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + nc + j));
+                    o.x += b4.x;
+                    o.y += b4.y;
+                    o.z += b4.z;
+                    o.w += b4.w;
                   }
                   *reinterpret_cast<float4*>(dst + j) = o;
                 }
               } else {
 #pragma unroll
                 for (int j = 0; j < CH; ++j)
-                  if (nc + j < args.N) {
-                    if constexpr (EPI == EPI_RESID_F32) dst[j] += v[j];
-                    else dst[j] = v[j];
-                  }
+                  if (nc + j < args.N)
+                    dst[j] = __uint_as_float(r[j]) + (args.bias != nullptr ? __ldg(args.bias + nc + j) : 0.f);
               }
             }
           }
         }
-      }
 
-      // accumulator fully read: hand the TMEM buffer back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+        // accumulator fully read: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
 
-      if constexpr (EPI == EPI_ARGMAX) {
-        if (row_ok && best_n != 0x7fffffff) {
-          const unsigned long long key = (static_cast<unsigned long long>(float_order_key(best)) << 32) |
-                                         static_cast<unsigned long long>(~static_cast<uint32_t>(best_n));
-          atomicMax(reinterpret_cast<unsigned long long*>(args.out) + m, key);
+        if constexpr (EPI == EPI_ARGMAX) {
+          if (row_ok && best_n != 0x7fffffff) {
+            const unsigned long long key = (static_cast<unsigned long long>(float_order_key(best)) << 32) |
+                                           static_cast<unsigned long long>(~static_cast<uint32_t>(best_n));
+            atomicMax(reinterpret_cast<unsigned long long*>(args.out) + m, key);
+          }
         }
       }
     }
@@ -331,6 +415,27 @@ int encode_map(CUtensorMap* m, const __half* base, uint64_t rows, uint64_t cols,
   return CC_OK;
 }
 
+// Output map for the TMA epilogue: [rows, cols] of fp16 / fp32 with row stride ldc, box = {64 bytes of columns, 32
+// rows}, 64-byte swizzle (matches the per-warp staging layout in the kernel).
+int encode_out_map(CUtensorMap* m, void* base, bool f32, uint64_t rows, uint64_t cols, uint64_t ldc) {
+  EncodeTiledFn fn = get_encode_fn();
+  CC_REQUIRE(fn != nullptr, CC_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  const uint64_t es = f32 ? 4 : 2;
+  CC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, CC_EALIGN, "GEMM output base %p not 16-byte aligned", base);
+  CC_REQUIRE((ldc * es) % 16 == 0, CC_EALIGN, "GEMM output row stride %llu elements is not 16-byte aligned",
+             (unsigned long long)ldc);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ldc * es};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(64 / es), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CC_REQUIRE(r == CUDA_SUCCESS, CC_ECUDA, "cuTensorMapEncodeTiled (output) failed (%d) rows=%llu cols=%llu ldc=%llu",
+             (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ldc);
+  return CC_OK;
+}
+
 template <int BN, int EPI>
 int launch(const GemmPlan& p, int bn_idx, int M, cudaStream_t s) {
   using Cfg = GemmCfg<BN>;
@@ -343,7 +448,7 @@ int launch(const GemmPlan& p, int bn_idx, int M, cudaStream_t s) {
   const int tiles = ((M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   GemmArgs a{M, p.N, p.K, p.bias, p.out, static_cast<long long>(p.ldc)};
-  kern<<<grid, GEMM_THREADS, Cfg::kSmem, s>>>(p.map_a, p.map_b[bn_idx], a);
+  kern<<<grid, GEMM_THREADS, Cfg::kSmem, s>>>(p.map_a, p.map_b[bn_idx], p.map_c, a);
   CC_CUDA(cudaGetLastError());
   return CC_OK;
 }
@@ -371,14 +476,14 @@ int gemm_pick_bn(int M, int N) {
   // want many CTAs, large ones want the 128x256 tile.
   const int sms = num_sms();
   const int tiles_m = (M + BM - 1) / BM;
-  static const int cand[5] = {256, 128, 64, 32, 16};
-  for (int i = 0; i < 5; ++i) {
+  static const int cand[4] = {256, 128, 64, 32};
+  for (int i = 0; i < 4; ++i) {
     const int bn = cand[i];
-    if (bn > 16 && bn / 2 >= N) continue;  // do not use a tile mostly outside N
+    if (bn > 32 && bn / 2 >= N) continue;  // do not use a tile mostly outside N
     const int tiles = tiles_m * ((N + bn - 1) / bn);
     if (tiles >= sms) return bn;
   }
-  return 16;
+  return 32;
 }
 
 int gemm_plan(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __half* w, int N, int K, int epi,
@@ -394,8 +499,14 @@ int gemm_plan(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __h
   p->out = out;
   p->ldc = ldc;
   CC_TRY(encode_map(&p->map_a, a, max_rows, K, lda, BM));
-  static const int bns[5] = {16, 32, 64, 128, 256};
-  for (int i = 0; i < 5; ++i) CC_TRY(encode_map(&p->map_b[i], w, N, K, K, bns[i]));
+  static const int bns[4] = {32, 64, 128, 256};
+  for (int i = 0; i < 4; ++i) CC_TRY(encode_map(&p->map_b[i], w, N, K, K, bns[i]));
+  // fp16 outputs and the fp32 residual update leave through TMA (rows M..max_rows of `out` are scratch: whole 32-row
+  // groups are written); fp32 logits and argmax keys use direct stores and get a copy of map_a as a placeholder.
+  if (epi <= EPI_F16_TANH || epi == EPI_RESID_F32)
+    CC_TRY(encode_out_map(&p->map_c, out, epi == EPI_RESID_F32, max_rows, N, ldc));
+  else
+    p->map_c = p->map_a;
   return CC_OK;
 }
 
@@ -461,11 +572,10 @@ int gemm_run(const GemmPlan& p, int M, cudaStream_t s) {
 namespace {
 int gemm_dispatch(const GemmPlan& p, int bn, int M, cudaStream_t s) {
   switch (bn) {
-    case 16: return launch_epi<16>(p, 0, M, s);
-    case 32: return launch_epi<32>(p, 1, M, s);
-    case 64: return launch_epi<64>(p, 2, M, s);
-    case 128: return launch_epi<128>(p, 3, M, s);
-    case 256: return launch_epi<256>(p, 4, M, s);
+    case 32: return launch_epi<32>(p, 0, M, s);
+    case 64: return launch_epi<64>(p, 1, M, s);
+    case 128: return launch_epi<128>(p, 2, M, s);
+    case 256: return launch_epi<256>(p, 3, M, s);
   }
   set_error("gemm_run: unsupported BLOCK_N %d", bn);
   return CC_EINVAL;
