@@ -52,6 +52,8 @@ attn_fwd_kernel(const __half* __restrict__ q, const __half* __restrict__ k, cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int h = blockIdx.y, b = blockIdx.z;
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row_base = static_cast<long long>(b) * S;
   const __half* qh = q + row_base * ld + h * HD;
   const __half* kh = k + row_base * ld + h * HD;
@@ -231,98 +233,114 @@ int launch_attn(const __half* q, const __half* k, const __half* v, int64_t ld, _
   const int nblk = (tiles + 7) / 8;
   const int nw = (tiles + nblk - 1) / nblk;
   dim3 grid(nblk, H, B);
-  kern<<<grid, nw * 32, AttnSmem<HD>::kBytes, s>>>(q, k, v, ld, o, ldo, S, scale * 1.4426950408889634f);
+  CC_CUDA(launch_pdl(kern, grid, dim3(nw * 32), AttnSmem<HD>::kBytes, s, q, k, v, static_cast<long long>(ld), o,
+                     static_cast<long long>(ldo), S, scale * 1.4426950408889634f));
   CC_CUDA(cudaGetLastError());
   return CC_OK;
 }
 
 // ------------------------------------------------------------------ decode attention over the KV cache (hd = 64)
+// One warp per (sequence, head). A key/value row is 128 B = 8 lanes x 16 B, so a warp covers 4 keys per load
+// instruction; each pass of the loop issues 4 K loads + 4 V loads per lane (16 keys, 4 KB in flight per warp) before
+// any arithmetic, and keeps a single online-softmax state, so the dependent chain is ceil(T/16) memory round trips.
+// The step's own k,v come straight from the qkv row (and are appended to the cache for later steps).
 constexpr int DEC_WARPS = 4;
+constexpr int DEC_KEYS = 16;  // keys per loop pass
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(hp[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
 
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 decode_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, __half* __restrict__ vcache,
                    const int32_t* __restrict__ anc, __half* __restrict__ o, int nseq, int H, int t_max, int pos,
                    float scale_log2) {
-  extern __shared__ float sc_all[];  // [DEC_WARPS][t_max] scores
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * DEC_WARPS + warp;
+  pdl_launch_dependents();
+  pdl_wait();
   if (pair >= nseq * H) return;
   const int seq = pair / H, h = pair % H;
   const int d = H * 64;
-  float* sc = sc_all + warp * t_max;
-  const int kq = lane >> 3;  // key slot 0..3 within a pass
+  const int kq = lane >> 3;  // key slot 0..3 within a load
   const int c = lane & 7;    // 16-byte chunk (8 dims) of the head row
 
   const __half* qrow = qkv + static_cast<long long>(seq) * 3 * d + h * 64;
+  const __half* knew = qrow + d + c * 8;
+  const __half* vnew = qrow + 2 * d + c * 8;
   // append this step's k, v (lanes 0..7 copy k, 8..15 copy v)
   {
-    const long long dst = ((static_cast<long long>(seq) * H + h) * t_max + pos) * 64;
-    if (lane < 8) *reinterpret_cast<uint4*>(kcache + dst + lane * 8) = *reinterpret_cast<const uint4*>(qrow + d + lane * 8);
-    else if (lane < 16)
-      *reinterpret_cast<uint4*>(vcache + dst + (lane - 8) * 8) = *reinterpret_cast<const uint4*>(qrow + 2 * d + (lane - 8) * 8);
+    const long long dst = ((static_cast<long long>(seq) * H + h) * t_max + pos) * 64 + c * 8;
+    if (kq == 0) *reinterpret_cast<uint4*>(kcache + dst) = *reinterpret_cast<const uint4*>(knew);
+    else if (kq == 1) *reinterpret_cast<uint4*>(vcache + dst) = *reinterpret_cast<const uint4*>(vnew);
   }
-  __syncwarp();
-  __threadfence_block();
 
   float qf[8];
-  {
-    const uint4 qq = *reinterpret_cast<const uint4*>(qrow + c * 8);
-    const __half2* hp = reinterpret_cast<const __half2*>(&qq);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __half22float2(hp[i]);
-      qf[2 * i] = f.x;
-      qf[2 * i + 1] = f.y;
-    }
-  }
+  unpack8(*reinterpret_cast<const uint4*>(qrow + c * 8), qf);
   const int T = pos + 1;
   const int32_t* arow = anc ? anc + static_cast<long long>(seq) * t_max : nullptr;
-
-  float mx = -INFINITY;
-  for (int t0 = 0; t0 < T; t0 += 4) {
-    const int tt = t0 + kq;
-    float dot = 0.f;
-    if (tt < T) {
-      const int slot = (arow && tt != pos) ? arow[tt] : seq;
-      const uint4 kk = *reinterpret_cast<const uint4*>(kcache + ((static_cast<long long>(slot) * H + h) * t_max + tt) * 64 + c * 8);
-      const __half2* hp = reinterpret_cast<const __half2*>(&kk);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(hp[i]);
-        dot += qf[2 * i] * f.x + qf[2 * i + 1] * f.y;
-      }
-    }
-    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-    if (tt < T) {
-      if (c == 0) sc[tt] = dot;
-      mx = fmaxf(mx, dot);
-    }
-  }
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-  __syncwarp();
+  const long long own = (static_cast<long long>(seq) * H + h) * t_max;
 
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  float lsum = 0.f;
-  const float mxs = mx * scale_log2;
-  for (int t0 = 0; t0 < T; t0 += 4) {
-    const int tt = t0 + kq;
-    if (tt < T) {
-      const float p = exp2f(sc[tt] * scale_log2 - mxs);
-      lsum += p;
-      const int slot = (arow && tt != pos) ? arow[tt] : seq;
-      const uint4 vv = *reinterpret_cast<const uint4*>(vcache + ((static_cast<long long>(slot) * H + h) * t_max + tt) * 64 + c * 8);
-      const __half2* hp = reinterpret_cast<const __half2*>(&vv);
+  float mx = -INFINITY, lsum = 0.f;
+
+  for (int t0 = 0; t0 < T; t0 += DEC_KEYS) {
+    uint4 kk[4], vv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(hp[i]);
-        acc[2 * i] += p * f.x;
-        acc[2 * i + 1] += p * f.y;
+    for (int j = 0; j < 4; ++j) {
+      const int tt = t0 + 4 * j + kq;
+      if (tt < pos) {
+        const long long base = arow ? (static_cast<long long>(arow[tt]) * H + h) * t_max : own;
+        kk[j] = *reinterpret_cast<const uint4*>(kcache + (base + tt) * 64 + c * 8);
+        vv[j] = *reinterpret_cast<const uint4*>(vcache + (base + tt) * 64 + c * 8);
+      } else if (tt == pos) {
+        kk[j] = *reinterpret_cast<const uint4*>(knew);
+        vv[j] = *reinterpret_cast<const uint4*>(vnew);
+      } else {
+        kk[j] = make_uint4(0u, 0u, 0u, 0u);
+        vv[j] = make_uint4(0u, 0u, 0u, 0u);
       }
+    }
+    float dot[4];
+    float bm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float kf[8];
+      unpack8(kk[j], kf);
+      float dd = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dd += qf[i] * kf[i];
+      dd += __shfl_xor_sync(0xffffffffu, dd, 1);
+      dd += __shfl_xor_sync(0xffffffffu, dd, 2);
+      dd += __shfl_xor_sync(0xffffffffu, dd, 4);
+      dot[j] = (t0 + 4 * j + kq < T) ? dd : -INFINITY;
+      bm = fmaxf(bm, dot[j]);
+    }
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+    const float nm = fmaxf(mx, bm);  // finite: every pass holds at least one valid key
+    const float corr = exp2f((mx - nm) * scale_log2);
+    mx = nm;
+    lsum *= corr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= corr;
+    const float nms = nm * scale_log2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float p = exp2f(dot[j] * scale_log2 - nms);  // exp2(-inf) = 0 for masked keys
+      lsum += p;
+      float vf[8];
+      unpack8(vv[j], vf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += p * vf[i];
     }
   }
 #pragma unroll
@@ -347,6 +365,8 @@ __global__ void kv_scatter_kernel(const __half* __restrict__ qkv, __half* __rest
                                   __half* __restrict__ vcache, int nseq, int T, int H, int t_max, int pos0,
                                   int slot_stride) {
   // one thread per 16-byte chunk of one (seq, t, head) row, k and v
+  pdl_launch_dependents();
+  pdl_wait();
   const long long n = static_cast<long long>(nseq) * T * H * 8;
   const int d = H * 64;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -387,13 +407,10 @@ int attention_run(const __half* q, const __half* k, const __half* v, int64_t ld,
 int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, const int32_t* anc, __half* o, int nseq,
                          int H, int t_max, int pos, float scale, cudaStream_t s) {
   CC_REQUIRE(pos >= 0 && pos < t_max, CC_ESHAPE, "decode attention: position %d outside cache (t_max %d)", pos, t_max);
-  CC_REQUIRE(t_max <= 2048, CC_ESHAPE, "decode attention: t_max %d > 2048", t_max);
   const int pairs = nseq * H;
   const int grid = (pairs + DEC_WARPS - 1) / DEC_WARPS;
-  const size_t smem = static_cast<size_t>(DEC_WARPS) * t_max * sizeof(float);
-  decode_attn_kernel<<<grid, DEC_WARPS * 32, smem, s>>>(qkv, kcache, vcache, anc, o, nseq, H, t_max, pos,
-                                                        scale * 1.4426950408889634f);
-  CC_CUDA(cudaGetLastError());
+  CC_CUDA(launch_pdl(decode_attn_kernel, dim3(grid), dim3(DEC_WARPS * 32), 0, s, qkv, kcache, vcache, anc, o, nseq, H,
+                     t_max, pos, scale * 1.4426950408889634f));
   return CC_OK;
 }
 
@@ -402,8 +419,8 @@ int kv_scatter_run(const __half* qkv, __half* kcache, __half* vcache, int nseq, 
   CC_REQUIRE(pos0 + T <= t_max, CC_ESHAPE, "kv scatter: %d + %d positions exceed cache length %d", pos0, T, t_max);
   const long long n = static_cast<long long>(nseq) * T * H * 8;
   const int grid = static_cast<int>(std::min<long long>((n + 255) / 256, 148LL * 16));
-  kv_scatter_kernel<<<grid, 256, 0, s>>>(qkv, kcache, vcache, nseq, T, H, t_max, pos0, slot_stride);
-  CC_CUDA(cudaGetLastError());
+  CC_CUDA(launch_pdl(kv_scatter_kernel, dim3(grid), dim3(256), 0, s, qkv, kcache, vcache, nseq, T, H, t_max, pos0,
+                     slot_stride));
   return CC_OK;
 }
 

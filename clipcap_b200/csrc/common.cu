@@ -1,4 +1,6 @@
 // Host-side plumbing shared by the engines: thread-local error message, device arena, arch check, weight lookup.
+#include <cstdlib>
+
 #include "common.h"
 
 #include <cstdarg>
@@ -34,6 +36,14 @@ void DevBuf::release() {
   if (p) cudaFree(p);
   p = nullptr;
   bytes = 0;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CLIPCAP_B200_NO_PDL");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  return on;
 }
 
 int Arena::alloc(void** out, size_t bytes) {

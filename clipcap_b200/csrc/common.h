@@ -64,6 +64,24 @@ struct Arena {  // owns every allocation of one engine; freed in one go
   ~Arena() { release(); }
 };
 
+// Launch with programmatic dependent launch enabled (the kernel must call pdl_wait(), see ptx.cuh). Disabled with
+// CLIPCAP_B200_NO_PDL=1.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int check_device_sm100();  // CC_EARCH unless the current device is compute capability 10.x
 int num_sms();
 
@@ -83,6 +101,7 @@ enum Epi {
   EPI_F32,            // C32 = acc + bias
   EPI_RESID_F32,      // C32 += acc + bias       (in-place fp32 residual stream)
   EPI_ARGMAX,         // keys[m] = max over n of pack(acc, n)   (fused greedy LM head; no logits written)
+  EPI_PARTIAL_F32,    // split-K: partial[split][m][n] = acc over this split's k-range (summed by layernorm_reduce)
   EPI_COUNT
 };
 
@@ -96,13 +115,20 @@ struct GemmPlan {
   void* out = nullptr;  // half* / float* / unsigned long long* by epilogue
   int64_t ldc = 0;
   int force_bn = 0;  // 0 = heuristic
+  int splits = 1;      // EPI_PARTIAL_F32: split-K factor and the row pitch of one split inside `out`
+  int split_rows = 0;
 };
 
 // Encodes the tensor maps. `a` must stay at this address with >= max_rows rows readable.
 int gemm_plan(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __half* w, int N, int K, int epi,
               const float* bias, void* out, int64_t ldc);
+// Split-K plan for skinny problems (decode): partial[s][split_rows][N] fp32 holds split s of A W^T without bias; rows
+// M..split_rows of each split are scratch. The reduction over s happens, in order, inside layernorm_reduce_run.
+int gemm_plan_partial(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __half* w, int N, int K,
+                      float* partial, int split_rows, int splits, int bn);
+void gemm_pick_split(int M, int N, int K, int* bn_out, int* splits_out);
 int gemm_run(const GemmPlan& p, int M, cudaStream_t s);
-int gemm_pick_bn(int M, int N);
+int gemm_pick_bn(int M, int N, int K);
 // Live timing of GEMM launches with CUDA events on the launching stream (cc_prof_*; bench.py's roofline figure).
 void gemm_prof_enable(bool on);
 void gemm_prof_read(double* ms, double* flops, long long* n);
@@ -113,6 +139,12 @@ __host__ __device__ inline uint32_t argmax_key_index(unsigned long long key) { r
 // ------------------------------------------------------------------ LayerNorm (fp32 in, fp16 out), row-strided
 int layernorm_run(const float* x, int64_t x_ld, const float* gamma, const float* beta, __half* y, int64_t y_ld, int rows,
                   int d, float eps, cudaStream_t s);
+
+// h[r,:] += bias + sum_s partial[s][r,:] (s ascending, fixed order), written back, then LayerNorm(h[r,:]) -> y fp16.
+// partial == nullptr / splits == 0 degenerates to layernorm_run.
+int layernorm_reduce_run(float* h, int64_t h_ld, const float* partial, int splits, int64_t split_stride,
+                         const float* bias, const float* gamma, const float* beta, __half* y, int64_t y_ld, int rows,
+                         int d, float eps, cudaStream_t s);
 
 // ------------------------------------------------------------------ attention
 // Full / causal self-attention over packed projections. q,k,v point at the first element of their column block inside
@@ -186,7 +218,19 @@ struct Stack {
   std::vector<GemmPlan> p_qkv, p_o, p_1, p_2;
   int launches = 0;  // kernels enqueued since the counter was last reset
 
-  int init(Arena& arena, int d_, int dff_, int H_, int act_epi_, bool causal_, float eps_, int max_rows_);
+  // Decode path (GPT-2 only, dec_rows > 0): the two N = d projections run split-K into `part` and the LayerNorm that
+  // follows (LN2, the next layer's LN1, or ln_f) folds bias + partial sums into h in a fixed order (deterministic).
+  int dec_rows = 0, dec_rows_pad = 0;
+  Arena* arena_ = nullptr;  // the owning engine's arena (set by init)
+  float* part = nullptr;  // [max splits][dec_rows_pad][d] fp32
+  std::vector<GemmPlan> p_o_dec, p_2_dec;
+  int pend_splits = 0;  // partial sums waiting in `part` for the next LayerNorm (0 = none)
+  const float* pend_bias = nullptr;
+
+  int init(Arena& arena, int d_, int dff_, int H_, int act_epi_, bool causal_, float eps_, int max_rows_,
+           int dec_rows_ = 0);
+  // LayerNorm of the first nseq rows of h for the decode path, absorbing pending split-K partial sums first.
+  int ln_decode(const float* g, const float* b, __half* y, int nseq, cudaStream_t s);
   int plan();  // after `layers` is filled
   // Full-sequence pass of layer l over B sequences of S rows (rows b*S .. b*S+S-1 of h). If `kv` is given the layer's
   // K,V rows are also scattered into the cache at positions 0..S-1 of slot b*slot_stride.

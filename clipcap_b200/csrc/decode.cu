@@ -5,6 +5,7 @@
 // All state lives on the device; nothing here synchronises the host.
 #include "common.h"
 #include "decode.h"
+#include "ptx.cuh"
 
 namespace cc {
 namespace {
@@ -25,6 +26,8 @@ __global__ void gen_reset_kernel(int32_t* stopped, int32_t* lengths, unsigned lo
 __global__ void greedy_select_kernel(unsigned long long* keys, int32_t* tokens, int entry_len, int step, int32_t* stopped,
                                      int32_t* lengths, int stop_token, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (i >= n) return;
   const int tok = static_cast<int>(argmax_key_index(keys[i]));
   keys[i] = 0ull;  // re-armed for the next step's atomicMax
@@ -292,8 +295,8 @@ int gen_reset_run(int32_t* stopped, int32_t* lengths, unsigned long long* keys, 
 
 int greedy_select_run(unsigned long long* keys, int32_t* tokens, int entry_len, int step, int32_t* stopped,
                       int32_t* lengths, int stop_token, int n, cudaStream_t s) {
-  greedy_select_kernel<<<(n + 255) / 256, 256, 0, s>>>(keys, tokens, entry_len, step, stopped, lengths, stop_token, n);
-  CC_CUDA(cudaGetLastError());
+  CC_CUDA(launch_pdl(greedy_select_kernel, dim3((n + 255) / 256), dim3(256), 0, s, keys, tokens, entry_len, step, stopped,
+                     lengths, stop_token, n));
   return CC_OK;
 }
 

@@ -186,6 +186,8 @@ __global__ void gpt2_embed_prefix_kernel(const SRC* __restrict__ e, const float*
 __global__ void gpt2_embed_tokens_kernel(const int32_t* __restrict__ tokens, long long tok_stride,
                                          const float* __restrict__ wte, const float* __restrict__ wpe,
                                          float* __restrict__ h, int n, int d, int pos, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(n) * (d / 4);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const float4* wpe4 = reinterpret_cast<const float4*>(wpe + static_cast<long long>(pos) * d);
@@ -327,8 +329,8 @@ int gpt2_embed_prefix_run(const void* embeds, int dtype, const float* wpe, float
 int gpt2_embed_tokens_run(const int32_t* tokens, int64_t tok_stride, const float* wte, const float* wpe, float* h, int n,
                           int d, int pos, int V, cudaStream_t s) {
   const long long total = static_cast<long long>(n) * (d / 4);
-  gpt2_embed_tokens_kernel<<<grid_for(total, 256), 256, 0, s>>>(tokens, tok_stride, wte, wpe, h, n, d, pos, V);
-  CC_CUDA(cudaGetLastError());
+  CC_CUDA(launch_pdl(gpt2_embed_tokens_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, tokens,
+                     static_cast<long long>(tok_stride), wte, wpe, h, n, d, pos, V));
   return CC_OK;
 }
 

@@ -48,6 +48,9 @@ struct GemmArgs {
   const float* bias;
   void* out;
   long long ldc;
+  int splits;        // split-K factor (EPI_PARTIAL_F32 only, else 1)
+  int kb_per_split;  // k-blocks per split
+  int split_rows;    // row offset of split s inside the partial-sum matrix: s * split_rows
 };
 
 // x * sigmoid(k x) with the two MUFU ops (ex2, rcp) at approximate precision: relative error ~2^-22, far below the
@@ -84,7 +87,8 @@ __device__ __forceinline__ uint32_t float_order_key(float x) {
 
 template <int EPI>
 struct EpiTraits {
-  static constexpr bool kTma = EPI <= EPI_F16_TANH || EPI == EPI_RESID_F32;
+  static constexpr bool kTma = EPI <= EPI_F16_TANH || EPI == EPI_RESID_F32 || EPI == EPI_PARTIAL_F32;
+  static constexpr bool kF32 = EPI == EPI_RESID_F32 || EPI == EPI_PARTIAL_F32;
 };
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -113,7 +117,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int tiles_m = (args.M + BM - 1) / BM;
   const int tiles_n = (args.N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
+  const int num_work = tiles_m * tiles_n * args.splits;  // work item = (tile, k-split), split fastest
   const int num_kb = (args.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -138,16 +142,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Everything above touched only this CTA's shared / tensor memory; from here on we read what earlier kernels wrote.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int tile = w / args.splits, split = w - tile * args.splits;
         const int m0 = (tile / tiles_n) * BM;
         const int n0 = (tile % tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = split * args.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + args.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStage;
           const uint32_t sb = sa + Cfg::kStageA;
@@ -168,12 +178,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
         const int as = it & 1;
+        const int split = w % args.splits;
+        const int nkb = min(num_kb, (split + 1) * args.kb_per_split) - split * args.kb_per_split;
         mbar_wait(tempty_bar(as), ((it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStage;
@@ -206,7 +218,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if constexpr (EpiTraits<EPI>::kTma) {
       // 64 bytes of output per row and chunk: 32 fp16 or 16 fp32 columns.
-      constexpr bool kF32 = (EPI == EPI_RESID_F32);
+      constexpr bool kF32 = EpiTraits<EPI>::kF32;
       constexpr int CH = kF32 ? 16 : 32;
       constexpr int NCH = WCOLS / CH;
       const uint32_t stg = stg_base + ew * STG_WARP_BYTES;
@@ -214,11 +226,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t row_off = lane * 64;
       const uint32_t sw = (lane >> 1) & 3;
       uint32_t chunk_no = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
         const int as = it & 1;
+        const int tile = w / args.splits, split = w - tile * args.splits;
         const int m0 = (tile / tiles_n) * BM;
         const int n0 = (tile % tiles_n) * BN;
         const bool rows_live = (m0 + quad * 32) < args.M;  // warp-uniform
+        const int out_row = split * args.split_rows + m0 + quad * 32;
         mbar_wait(tfull_bar(as), (it >> 1) & 1u);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + col_base;
@@ -282,8 +296,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if constexpr (kF32) tma_reduce_add_2d(&map_c, buf - row_off, nc, m0 + quad * 32);
-            else tma_store_2d(&map_c, buf - row_off, nc, m0 + quad * 32);
+            if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(&map_c, buf - row_off, nc, out_row);
+            else tma_store_2d(&map_c, buf - row_off, nc, out_row);
             bulk_commit();
           }
         }
@@ -292,7 +306,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else {
       // fp32 logits (arbitrary ldc) and fused argmax: direct global stores / atomics, thread == output row
       constexpr int CH = WCOLS < 32 ? WCOLS : 32;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < num_work; tile += gridDim.x, ++it) {  // splits == 1 here
         const int as = it & 1;
         const int m0 = (tile / tiles_n) * BM;
         const int n0 = (tile % tiles_n) * BN;
@@ -445,11 +459,13 @@ int launch(const GemmPlan& p, int bn_idx, int M, cudaStream_t s) {
     CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     configured = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int tiles = ((M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * ((EPI == EPI_PARTIAL_F32) ? p.splits : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  GemmArgs a{M, p.N, p.K, p.bias, p.out, static_cast<long long>(p.ldc)};
-  kern<<<grid, GEMM_THREADS, Cfg::kSmem, s>>>(p.map_a, p.map_b[bn_idx], p.map_c, a);
-  CC_CUDA(cudaGetLastError());
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int splits = (EPI == EPI_PARTIAL_F32) ? p.splits : 1;
+  const int kb_per = (num_kb + splits - 1) / splits;
+  GemmArgs a{M, p.N, p.K, p.bias, p.out, static_cast<long long>(p.ldc), splits, kb_per, p.split_rows};
+  CC_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmem, s, p.map_a, p.map_b[bn_idx], p.map_c, a));
   return CC_OK;
 }
 
@@ -464,6 +480,7 @@ int launch_epi(const GemmPlan& p, int bn_idx, int M, cudaStream_t s) {
     case EPI_F32: return launch<BN, EPI_F32>(p, bn_idx, M, s);
     case EPI_RESID_F32: return launch<BN, EPI_RESID_F32>(p, bn_idx, M, s);
     case EPI_ARGMAX: return launch<BN, EPI_ARGMAX>(p, bn_idx, M, s);
+    case EPI_PARTIAL_F32: return launch<BN, EPI_PARTIAL_F32>(p, bn_idx, M, s);
   }
   set_error("unknown GEMM epilogue %d", p.epi);
   return CC_EINVAL;
@@ -471,19 +488,62 @@ int launch_epi(const GemmPlan& p, int bn_idx, int M, cudaStream_t s) {
 
 }  // namespace
 
-int gemm_pick_bn(int M, int N) {
-  // Largest BLOCK_N that still yields at least one CTA per SM; small problems (decode, M <= 256) stream weights and
-  // want many CTAs, large ones want the 128x256 tile.
+namespace {
+// Rough cycle estimate of one persistent CTA's share of the problem: per work item the slower of operand ingest
+// (~40 B/clk/SM from L2) and the tensor pipe (128 x BN x 16 MMA = BN/8... 8192 FLOP/clk/SM), plus a fixed fill/drain
+// cost; split-K adds the partial-sum store and the consumer's re-read.
+double gemm_cost(int M, int N, int K, int bn, int splits, int sms) {
+  const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn) * splits;
+  const int waves = (tiles + sms - 1) / sms;
+  const double ks = static_cast<double>(K) / splits;
+  const double mem = (BM + bn) * ks * 2.0 / 40.0;
+  const double mma = 2.0 * BM * bn * ks / 8192.0;
+  double c = waves * ((mem > mma ? mem : mma) + 2000.0);
+  if (splits > 1) c += waves * (BM * bn * 4.0 / 40.0) + splits * (static_cast<double>(M) * N * 4.0 / (sms * 40.0));
+  return c;
+}
+}  // namespace
+
+int gemm_pick_bn(int M, int N, int K) {
+  // Large problems (>= one tile per SM at 128x256): the biggest tile. Small ones (decode, M <= a few hundred rows):
+  // whatever keeps the work in the fewest, best balanced waves.
   const int sms = num_sms();
   const int tiles_m = (M + BM - 1) / BM;
+  if (tiles_m * ((N + 255) / 256) >= sms) return 256;
   static const int cand[4] = {256, 128, 64, 32};
+  int best = 32;
+  double best_c = 1e30;
   for (int i = 0; i < 4; ++i) {
     const int bn = cand[i];
     if (bn > 32 && bn / 2 >= N) continue;  // do not use a tile mostly outside N
-    const int tiles = tiles_m * ((N + bn - 1) / bn);
-    if (tiles >= sms) return bn;
+    const double c = gemm_cost(M, N, K, bn, 1, sms);
+    if (c < best_c) {
+      best_c = c;
+      best = bn;
+    }
   }
-  return 32;
+  return best;
+}
+
+void gemm_pick_split(int M, int N, int K, int* bn_out, int* splits_out) {
+  const int sms = num_sms();
+  const int num_kb = (K + BK - 1) / BK;
+  static const int cand[4] = {256, 128, 64, 32};
+  double best_c = 1e30;
+  *bn_out = 32;
+  *splits_out = 1;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cand[i];
+    if (bn > 32 && bn / 2 >= N) continue;
+    for (int sp = 1; sp <= 16 && sp * 2 <= num_kb; sp *= 2) {
+      const double c = gemm_cost(M, N, K, bn, sp, sms);
+      if (c < best_c) {
+        best_c = c;
+        *bn_out = bn;
+        *splits_out = sp;
+      }
+    }
+  }
 }
 
 int gemm_plan(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __half* w, int N, int K, int epi,
@@ -503,10 +563,39 @@ int gemm_plan(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __h
   for (int i = 0; i < 4; ++i) CC_TRY(encode_map(&p->map_b[i], w, N, K, K, bns[i]));
   // fp16 outputs and the fp32 residual update leave through TMA (rows M..max_rows of `out` are scratch: whole 32-row
   // groups are written); fp32 logits and argmax keys use direct stores and get a copy of map_a as a placeholder.
+  CC_REQUIRE(epi != EPI_PARTIAL_F32, CC_EINVAL, "gemm_plan: split-K plans are built with gemm_plan_partial");
   if (epi <= EPI_F16_TANH || epi == EPI_RESID_F32)
     CC_TRY(encode_out_map(&p->map_c, out, epi == EPI_RESID_F32, max_rows, N, ldc));
   else
     p->map_c = p->map_a;
+  return CC_OK;
+}
+
+int gemm_plan_partial(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __half* w, int N, int K,
+                      float* partial, int split_rows, int splits, int bn) {
+  CC_REQUIRE(max_rows > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 4 == 0, CC_ESHAPE,
+             "gemm_plan_partial: bad shape M=%d N=%d K=%d", max_rows, N, K);
+  const int num_kb = (K + BK - 1) / BK;
+  CC_REQUIRE(splits >= 1 && splits <= num_kb, CC_EINVAL, "gemm_plan_partial: %d splits over %d k-blocks", splits, num_kb);
+  CC_REQUIRE(split_rows % 32 == 0 && split_rows >= max_rows, CC_EINVAL,
+             "gemm_plan_partial: split_rows %d must be a multiple of 32 and >= %d", split_rows, max_rows);
+  // no empty split: splits = ceil(num_kb / kb_per)
+  const int kb_per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kb_per - 1) / kb_per;
+  p->max_rows = max_rows;
+  p->N = N;
+  p->K = K;
+  p->epi = EPI_PARTIAL_F32;
+  p->bias = nullptr;
+  p->out = partial;
+  p->ldc = N;
+  p->splits = splits;
+  p->split_rows = split_rows;
+  p->force_bn = bn;
+  CC_TRY(encode_map(&p->map_a, a, max_rows, K, lda, BM));
+  static const int bns[4] = {32, 64, 128, 256};
+  for (int i = 0; i < 4; ++i) CC_TRY(encode_map(&p->map_b[i], w, N, K, K, bns[i]));
+  CC_TRY(encode_out_map(&p->map_c, partial, true, static_cast<uint64_t>(splits) * split_rows, N, N));
   return CC_OK;
 }
 
@@ -549,7 +638,7 @@ void gemm_prof_read(double* ms, double* flops, long long* n) {
 
 int gemm_run(const GemmPlan& p, int M, cudaStream_t s) {
   CC_REQUIRE(M > 0 && M <= p.max_rows, CC_ESHAPE, "gemm_run: M=%d outside plan (max %d)", M, p.max_rows);
-  const int bn = p.force_bn ? p.force_bn : gemm_pick_bn(M, p.N);
+  const int bn = p.force_bn ? p.force_bn : gemm_pick_bn(M, p.N, p.K);
   if (g_prof_on) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(s, &cs);

@@ -59,7 +59,7 @@ int gpt2_build(cc_gpt2* m, const cc_tensor* w, int nw) {
   m->max_rows = m->max_seqs * m->max_len;
   m->v_ld = (c.V + 7) / 8 * 8;
   m->max_entry = kMaxEntry;
-  CC_TRY(m->st.init(m->arena, d, 4 * d, c.H, EPI_F16_GELU_NEW, true, c.eps, m->max_rows));
+  CC_TRY(m->st.init(m->arena, d, 4 * d, c.H, EPI_F16_GELU_NEW, true, c.eps, m->max_rows, m->max_seqs));
   CC_REQUIRE(m->st.hd == 64, CC_ESHAPE, "gpt2: head dim %d (n_embd %d / n_head %d) must be 64", m->st.hd, d, c.H);
 
   const float *wte, *wpe, *g, *b;
@@ -182,8 +182,8 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
     CC_TRY(gpt2_embed_tokens_run(toks + (step - 1), EL, m->wte32, m->wpe32, st.h, nseq, d, pos, c.V, s));
     for (int l = 0; l < c.L; ++l)
       CC_TRY(st.layer_decode(l, nseq, &m->kv, is_beam ? m->beam.anc[cur] : nullptr, pos, s));
-    CC_TRY(layernorm_run(st.h, d, m->lnf_g, m->lnf_b, m->lnf16, d, nseq, d, c.eps, s));
-    extra += 2;
+    CC_TRY(st.ln_decode(m->lnf_g, m->lnf_b, m->lnf16, nseq, s));  // absorbs the last layer's fc2 partial sums
+    extra += 1;
     if (!is_beam) {
       CC_TRY(gemm_run(m->p_head_keys, nseq, s));
       CC_TRY(greedy_select_run(m->keys, m->g_tokens, EL, step, m->g_stopped, m->g_lengths, g.stop_token, nseq, s));

@@ -21,7 +21,8 @@ int pack_f16(Arena& arena, const float* src_dev, int rows, int cols, bool transp
   return CC_OK;
 }
 
-int Stack::init(Arena& arena, int d_, int dff_, int H_, int act_epi_, bool causal_, float eps_, int max_rows_) {
+int Stack::init(Arena& arena, int d_, int dff_, int H_, int act_epi_, bool causal_, float eps_, int max_rows_,
+                int dec_rows_) {
   CC_REQUIRE(d_ > 0 && H_ > 0 && d_ % H_ == 0, CC_ESHAPE, "stack: width %d not divisible by %d heads", d_, H_);
   CC_REQUIRE(d_ % 8 == 0 && dff_ % 8 == 0, CC_ESHAPE, "stack: widths must be multiples of 8 (d=%d dff=%d)", d_, dff_);
   d = d_;
@@ -41,6 +42,9 @@ int Stack::init(Arena& arena, int d_, int dff_, int H_, int act_epi_, bool causa
   CC_TRY(arena.alloc_t(&qkv16, r * 3 * d));
   CC_TRY(arena.alloc_t(&att16, r * d));
   CC_TRY(arena.alloc_t(&mlp16, r * dff));
+  arena_ = &arena;
+  dec_rows = dec_rows_;
+  dec_rows_pad = (dec_rows_ + 127) / 128 * 128;
   return CC_OK;
 }
 
@@ -57,7 +61,32 @@ int Stack::plan() {
     CC_TRY(gemm_plan(&p_1[l], ln16, d, max_rows, w.w1, dff, d, act_epi, w.b1, mlp16, dff));
     CC_TRY(gemm_plan(&p_2[l], mlp16, dff, max_rows, w.w2, d, dff, EPI_RESID_F32, w.b2, h, d));
   }
+  if (dec_rows > 0) {
+    int bn_o, sp_o, bn_2, sp_2;
+    gemm_pick_split(dec_rows, d, d, &bn_o, &sp_o);
+    gemm_pick_split(dec_rows, d, dff, &bn_2, &sp_2);
+    const int sp_max = sp_o > sp_2 ? sp_o : sp_2;
+    // `part` is allocated once per stack; plan() runs once after the layers are filled
+    if (part == nullptr) CC_TRY(arena_->alloc_t(&part, static_cast<size_t>(sp_max) * dec_rows_pad * d));
+    p_o_dec.resize(L);
+    p_2_dec.resize(L);
+    for (size_t l = 0; l < L; ++l) {
+      const LayerW& w = layers[l];
+      CC_TRY(gemm_plan_partial(&p_o_dec[l], att16, d, dec_rows, w.wo, d, d, part, dec_rows_pad, sp_o, bn_o));
+      CC_TRY(gemm_plan_partial(&p_2_dec[l], mlp16, dff, dec_rows, w.w2, d, dff, part, dec_rows_pad, sp_2, bn_2));
+    }
+  }
   return CC_OK;
+}
+
+int Stack::ln_decode(const float* g, const float* b, __half* y, int nseq, cudaStream_t s) {
+  const int sp = pend_splits;
+  const float* bias = pend_bias;
+  pend_splits = 0;
+  pend_bias = nullptr;
+  launches += 1;
+  return layernorm_reduce_run(h, d, sp > 0 ? part : nullptr, sp, static_cast<int64_t>(dec_rows_pad) * d, bias, g, b, y, d,
+                              nseq, d, eps, s);
 }
 
 int Stack::layer_full(int l, int B, int S, KvCache* kv, int slot_stride, cudaStream_t s) {
@@ -84,16 +113,21 @@ int Stack::layer_full(int l, int B, int S, KvCache* kv, int slot_stride, cudaStr
 int Stack::layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int pos, cudaStream_t s) {
   CC_REQUIRE(nseq <= max_rows && nseq <= kv->slots, CC_ESHAPE, "stack: %d sequences exceed handle capacity", nseq);
   CC_REQUIRE(hd == 64, CC_ESHAPE, "decode attention needs head dim 64 (got %d)", hd);
+  CC_REQUIRE(nseq <= dec_rows, CC_ESHAPE, "stack: %d sequences exceed the %d decode rows planned", nseq, dec_rows);
   const LayerW& w = layers[l];
-  CC_TRY(layernorm_run(h, d, w.ln1_g, w.ln1_b, ln16, d, nseq, d, eps, s));
+  CC_TRY(ln_decode(w.ln1_g, w.ln1_b, ln16, nseq, s));  // absorbs the previous layer's fc2 partial sums
   CC_TRY(gemm_run(p_qkv[l], nseq, s));
   CC_TRY(decode_attention_run(qkv16, kv->k + l * kv->layer_elems, kv->v + l * kv->layer_elems, anc, att16, nseq, H,
                               kv->t_max, pos, scale, s));
-  CC_TRY(gemm_run(p_o[l], nseq, s));
-  CC_TRY(layernorm_run(h, d, w.ln2_g, w.ln2_b, ln16, d, nseq, d, eps, s));
+  CC_TRY(gemm_run(p_o_dec[l], nseq, s));
+  pend_splits = p_o_dec[l].splits;
+  pend_bias = w.bo;
+  CC_TRY(ln_decode(w.ln2_g, w.ln2_b, ln16, nseq, s));
   CC_TRY(gemm_run(p_1[l], nseq, s));
-  CC_TRY(gemm_run(p_2[l], nseq, s));
-  launches += 7;
+  CC_TRY(gemm_run(p_2_dec[l], nseq, s));
+  pend_splits = p_2_dec[l].splits;
+  pend_bias = w.b2;
+  launches += 5;
   return CC_OK;
 }
 
