@@ -142,13 +142,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  // Everything above touched only this CTA's shared / tensor memory; from here on we read what earlier kernels wrote.
+  // Everything above touched only this CTA's shared / tensor memory. Weights (operand B) are never written by a kernel
+  // of the stream, so the producer puts the first stages' weight tiles in flight before waiting for the predecessor
+  // grid; activations (operand A) and all outputs are only touched after pdl_wait().
   pdl_launch_dependents();
-  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      int pre = 0;  // k-blocks of the first work item whose B tile is already in flight
+      if (static_cast<int>(blockIdx.x) < num_work) {
+        const int w = blockIdx.x;
+        const int tile = w / args.splits, split = w - tile * args.splits;
+        const int n0 = (tile % tiles_n) * BN;
+        const int kb0 = split * args.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + args.kb_per_split);
+        pre = min(Cfg::kStages, kb1 - kb0);
+        for (int i = 0; i < pre; ++i) {
+          mbar_arrive_expect_tx(full_bar(i), Cfg::kStage);
+          tma_load_2d(&map_b, full_bar(i), smem_base + i * Cfg::kStage + Cfg::kStageA, (kb0 + i) * BK, n0);
+        }
+      }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -158,21 +173,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(num_kb, kb0 + args.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStage;
           const uint32_t sb = sa + Cfg::kStageA;
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStage);
-          tma_load_2d(&map_a, full_bar(stage), sa, kb * BK, m0);
-          tma_load_2d(&map_b, full_bar(stage), sb, kb * BK, n0);
+          if (pre > 0) {  // stage is fresh and its B tile + expect_tx were issued above
+            --pre;
+            tma_load_2d(&map_a, full_bar(stage), sa, kb * BK, m0);
+          } else {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStage);
+            tma_load_2d(&map_a, full_bar(stage), sa, kb * BK, m0);
+            tma_load_2d(&map_b, full_bar(stage), sb, kb * BK, n0);
+          }
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
       }
+    } else {
+      pdl_wait();
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
+    pdl_wait();
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
       int stage = 0;
@@ -208,6 +231,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if ((warp - 2) < 4 * Cfg::kSplit) {
     // ------------------------------------------------------------ epilogue (warps 2..9)
+    pdl_wait();
     const int ew = warp - 2;
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access
     const int half_id = ew >> 2;      // which column half of the tile
@@ -384,6 +408,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   }
 
+  if ((warp - 2) >= 4 * Cfg::kSplit) pdl_wait();  // idle epilogue warps (narrow tiles)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
