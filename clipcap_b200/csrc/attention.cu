@@ -11,6 +11,7 @@
 //     K and V rows (128 B each) with 8 lanes per key, plus the in-place cache append of the step's own k,v.
 // (3) kv_scatter_kernel: prefill K,V rows -> cache.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -391,6 +392,13 @@ int attention_run(const __half* q, const __half* k, const __half* v, int64_t ld,
   CC_REQUIRE(B > 0 && S > 0 && H > 0, CC_ESHAPE, "attention: bad shape B=%d S=%d H=%d", B, S, H);
   CC_REQUIRE(ld % 8 == 0 && ldo % 2 == 0, CC_EALIGN, "attention: ld must be a multiple of 8 elements");
   CC_REQUIRE(H <= 65535 && B <= 65535, CC_ESHAPE, "attention: grid too large (H=%d B=%d)", H, B);
+  {
+    static const bool no_tc = [] {
+      const char* e = getenv("CLIPCAP_B200_NO_TC_ATTN");
+      return e != nullptr && e[0] == '1';
+    }();
+    if (!no_tc && vit_attention_fits(S, hd, causal, ld, ldo, q, k, v)) return vit_attention_run(q, k, v, ld, o, ldo, B, S, H, scale, s);
+  }
 #define CC_ATTN_CASE(HD)                                                                         \
   if (hd == HD)                                                                                  \
     return causal ? launch_attn<HD, true>(q, k, v, ld, o, ldo, B, S, H, scale, s)                \

@@ -119,6 +119,10 @@ struct GemmPlan {
   int split_rows = 0;
 };
 
+// TMA descriptor of a 2-D fp16 row-major [rows, cols] matrix (row stride ld elements), box {64 columns, box_rows rows},
+// 128-byte swizzle: the layout tcgen05 K-major operands (and MN-major operands of 64 columns) expect.
+int tma_map_f16_sw128(CUtensorMap* m, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
 // Encodes the tensor maps. `a` must stay at this address with >= max_rows rows readable.
 int gemm_plan(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __half* w, int N, int K, int epi,
               const float* bias, void* out, int64_t ldc);
@@ -151,6 +155,13 @@ int layernorm_reduce_run(float* h, int64_t h_ld, const float* partial, int split
 // one [B*S, ld] fp16 matrix (head h at column h*hd); o is [B*S, ldo] fp16. hd in {48, 64, 96, 128}.
 int attention_run(const __half* q, const __half* k, const __half* v, int64_t ld, __half* o, int64_t ldo, int B, int S,
                   int H, int hd, bool causal, float scale, cudaStream_t s);
+
+// tcgen05 attention for the ViT-L/14 shape (S = 257 = CLS + 256 patches, head dim 64, non-causal). Returns CC_ESHAPE
+// without launching if the shape does not fit; attention_run tries it first.
+bool vit_attention_fits(int S, int hd, bool causal, int64_t ld, int64_t ldo, const __half* q, const __half* k,
+                        const __half* v);
+int vit_attention_run(const __half* q, const __half* k, const __half* v, int64_t ld, __half* o, int64_t ldo, int B, int S,
+                      int H, float scale, cudaStream_t s);
 
 // KV cache: [layer][k|v][slot][head][t_max][64] fp16. Decode step: append this step's k,v (from qkv[nseq,3d]) at position
 // `pos` of slot `seq`, then attend over positions 0..pos, position t being read from slot anc[seq*t_max + t]

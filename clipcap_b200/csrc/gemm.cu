@@ -434,8 +434,10 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+}  // namespace
+
 // 2-D fp16 row-major [rows, cols] with row stride ld (elements); box = {64 cols, box_rows}, 128B swizzle.
-int encode_map(CUtensorMap* m, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+int tma_map_f16_sw128(CUtensorMap* m, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   CC_REQUIRE(fn != nullptr, CC_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   CC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, CC_EALIGN, "GEMM operand base %p not 16-byte aligned",
@@ -452,6 +454,11 @@ int encode_map(CUtensorMap* m, const __half* base, uint64_t rows, uint64_t cols,
   CC_REQUIRE(r == CUDA_SUCCESS, CC_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%u",
              (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
   return CC_OK;
+}
+
+namespace {
+int encode_map(CUtensorMap* m, const __half* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return tma_map_f16_sw128(m, base, rows, cols, ld, box_rows);
 }
 
 // Output map for the TMA epilogue: [rows, cols] of fp16 / fp32 with row stride ldc, box = {64 bytes of columns, 32

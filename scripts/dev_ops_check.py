@@ -66,6 +66,20 @@ for (B, Sq, H, hd, causal) in [(2, 257, 16, 64, 0), (3, 50, 8, 128, 0), (2, 20, 
     e = rel(o, r); ok = e < 3e-3; bad += (not ok)
     print(f"attention B={B} S={Sq} H={H} hd={hd} causal={causal} rel={e:.2e} {'ok' if ok else 'FAIL'}")
 
+if os.environ.get("ATTN_TIME", "1") == "1":
+    B, Sq, H, hd = 256, 257, 16, 64
+    d = H * hd
+    qkv = torch.randn(B * Sq, 3 * d, device=dev).half(); o = torch.zeros(B * Sq, d, device=dev, dtype=torch.half)
+    def run(): ck(h.cc_op_attention(qkv.data_ptr(), qkv.data_ptr() + d * 2, qkv.data_ptr() + 4 * d, 3 * d, o.data_ptr(), d, B, Sq, H, hd, 0, hd ** -0.5, S()))
+    for _ in range(3): run()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True); torch.cuda.synchronize(); e0.record()
+    for _ in range(10): run()
+    e1.record(); torch.cuda.synchronize(); ms = e0.elapsed_time(e1) / 10
+    q, k, v = [t.view(B, Sq, H, hd).transpose(1, 2)[:4].float() for t in qkv.split(d, dim=1)]
+    r = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(4 * Sq, d)
+    e = rel(o[:4 * Sq], r); ok = e < 3e-3; bad += (not ok)
+    print(f"time attention ViT B=256 S=257 H=16: {ms*1000:.1f} us  {4*Sq*Sq*hd*B*H/ms/1e9:.1f} TFLOP/s rel={e:.2e} {'ok' if ok else 'FAIL'}")
+
 # ---- decode attention
 nseq, H, t_max = 5, 4, 32
 d = H * 64
