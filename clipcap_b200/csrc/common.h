@@ -102,6 +102,7 @@ enum Epi {
   EPI_RESID_F32,      // C32 += acc + bias       (in-place fp32 residual stream)
   EPI_ARGMAX,         // keys[m] = max over n of pack(acc, n)   (fused greedy LM head; no logits written)
   EPI_PARTIAL_F32,    // split-K: partial[split][m][n] = acc over this split's k-range (summed by layernorm_reduce)
+  EPI_F16_HEADS,      // packed QKV projection written head-major: out[((b*3 + which)*H + h)*S + tok][64] = acc + bias
   EPI_COUNT
 };
 
@@ -117,6 +118,7 @@ struct GemmPlan {
   int force_bn = 0;  // 0 = heuristic
   int splits = 1;      // EPI_PARTIAL_F32: split-K factor and the row pitch of one split inside `out`
   int split_rows = 0;
+  int heads_S = 0, heads_H = 0;  // EPI_F16_HEADS: tokens per image, heads (N = 3 * H * 64)
 };
 
 // TMA descriptor of a 2-D fp16 row-major [rows, cols] matrix (row stride ld elements), box {64 columns, box_rows rows},
@@ -128,6 +130,11 @@ int gemm_plan(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __h
               const float* bias, void* out, int64_t ldc);
 // Split-K plan for skinny problems (decode): partial[s][split_rows][N] fp32 holds split s of A W^T without bias; rows
 // M..split_rows of each split are scratch. The reduction over s happens, in order, inside layernorm_reduce_run.
+// QKV projection of a [images * S, d] activation into the head-major layout the tcgen05 attention kernel reads:
+// out is [images * 3 * H][S][64] fp16 (plane = (image * 3 + {q,k,v}) * H + head), so every (image, head) operand is one
+// contiguous S x 64 block. N must be 3 * H * 64.
+int gemm_plan_heads(GemmPlan* p, const __half* a, int64_t lda, int max_images, int S, int H, const __half* w, int K,
+                    const float* bias, __half* out);
 int gemm_plan_partial(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __half* w, int N, int K,
                       float* partial, int split_rows, int splits, int bn);
 void gemm_pick_split(int M, int N, int K, int* bn_out, int* splits_out);
@@ -162,6 +169,10 @@ bool vit_attention_fits(int S, int hd, bool causal, int64_t ld, int64_t ldo, con
                         const __half* v);
 int vit_attention_run(const __half* q, const __half* k, const __half* v, int64_t ld, __half* o, int64_t ldo, int B, int S,
                       int H, float scale, cudaStream_t s);
+// Same kernel on the head-major QKV layout gemm_plan_heads writes ([B*3*H][S][64]): every operand tile is one contiguous
+// block, which is what lets the loads run at HBM speed.
+int vit_attention_heads_run(const __half* qkvh, __half* o, int64_t ldo, int B, int S, int H, float scale, cudaStream_t s);
+constexpr int kVitAttnTokens = 257;
 
 // KV cache: [layer][k|v][slot][head][t_max][64] fp16. Decode step: append this step's k,v (from qkv[nseq,3d]) at position
 // `pos` of slot `seq`, then attend over positions 0..pos, position t being read from slot anc[seq*t_max + t]
@@ -237,6 +248,10 @@ struct Stack {
   std::vector<GemmPlan> p_o_dec, p_2_dec;
   int pend_splits = 0;  // partial sums waiting in `part` for the next LayerNorm (0 = none)
   const float* pend_bias = nullptr;
+
+  // ViT-L/14 shape only (tokens per image == kVitAttnTokens, head dim 64): QKV is written head-major and attention
+  // runs on the tcgen05 kernel. Set before plan().
+  int heads_S = 0;
 
   int init(Arena& arena, int d_, int dff_, int H_, int act_epi_, bool causal_, float eps_, int max_rows_,
            int dec_rows_ = 0);

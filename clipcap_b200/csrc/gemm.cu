@@ -51,6 +51,7 @@ struct GemmArgs {
   int splits;        // split-K factor (EPI_PARTIAL_F32 only, else 1)
   int kb_per_split;  // k-blocks per split
   int split_rows;    // row offset of split s inside the partial-sum matrix: s * split_rows
+  int heads_S, heads_H;  // EPI_F16_HEADS: tokens per image, heads
 };
 
 // x * sigmoid(k x) with the two MUFU ops (ex2, rcp) at approximate precision: relative error ~2^-22, far below the
@@ -87,7 +88,8 @@ __device__ __forceinline__ uint32_t float_order_key(float x) {
 
 template <int EPI>
 struct EpiTraits {
-  static constexpr bool kTma = EPI <= EPI_F16_TANH || EPI == EPI_RESID_F32 || EPI == EPI_PARTIAL_F32;
+  static constexpr bool kTma =
+      EPI <= EPI_F16_TANH || EPI == EPI_RESID_F32 || EPI == EPI_PARTIAL_F32 || EPI == EPI_F16_HEADS;
   static constexpr bool kF32 = EPI == EPI_RESID_F32 || EPI == EPI_PARTIAL_F32;
 };
 
@@ -310,18 +312,44 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               st_shared_v4(buf + ((q ^ sw) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
                            __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
           } else {
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = pack_half2(apply_act<EPI>(v[2 * j]), apply_act<EPI>(v[2 * j + 1]));
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              st_shared_v4(buf + ((q ^ sw) << 4), pack_half2(apply_act<EPI>(v[8 * q]), apply_act<EPI>(v[8 * q + 1])),
-                           pack_half2(apply_act<EPI>(v[8 * q + 2]), apply_act<EPI>(v[8 * q + 3])),
-                           pack_half2(apply_act<EPI>(v[8 * q + 4]), apply_act<EPI>(v[8 * q + 5])),
-                           pack_half2(apply_act<EPI>(v[8 * q + 6]), apply_act<EPI>(v[8 * q + 7])));
+              st_shared_v4(buf + ((q ^ sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            if constexpr (EPI == EPI_F16_HEADS) {
+              // Rows of this 32-token group that run past the end of the image belong to the next image's plane: the
+              // TMA store below clips them, and their lanes write their 64 bytes directly (1 group in 8 straddles).
+              const int img = out_row / args.heads_S, tok = out_row - img * args.heads_S + lane;
+              if (tok >= args.heads_S && out_row + lane < args.M) {
+                const int d_model = args.heads_H * 64;
+                const int which = nc / d_model, rem = nc - which * d_model;
+                const long long plane = (static_cast<long long>(img + 1) * 3 + which) * args.heads_H + (rem >> 6);
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(args.out) +
+                                                      (plane * args.heads_S + (tok - args.heads_S)) * 64 + (rem & 63));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              }
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(&map_c, buf - row_off, nc, out_row);
-            else tma_store_2d(&map_c, buf - row_off, nc, out_row);
+            if constexpr (EPI == EPI_RESID_F32) {
+              tma_reduce_add_2d(&map_c, buf - row_off, nc, out_row);
+            } else if constexpr (EPI == EPI_F16_HEADS) {
+              // 32 rows x 32 columns = half a head of {q,k,v} for 32 consecutive tokens; rows past the end of the image
+              // are clipped by TMA (their lanes stored them directly above).
+              const int d_model = args.heads_H * 64;
+              const int which = nc / d_model, rem = nc - which * d_model;
+              const int hh = rem >> 6, dim0 = rem & 63;
+              const int img = out_row / args.heads_S, tok0 = out_row - img * args.heads_S;
+              const int plane = (img * 3 + which) * args.heads_H + hh;
+              tma_store_3d(&map_c, buf - row_off, dim0, tok0, plane);
+            } else {
+              tma_store_2d(&map_c, buf - row_off, nc, out_row);
+            }
             bulk_commit();
           }
         }
@@ -496,7 +524,8 @@ int launch(const GemmPlan& p, int bn_idx, int M, cudaStream_t s) {
   const int num_kb = (p.K + BK - 1) / BK;
   const int splits = (EPI == EPI_PARTIAL_F32) ? p.splits : 1;
   const int kb_per = (num_kb + splits - 1) / splits;
-  GemmArgs a{M, p.N, p.K, p.bias, p.out, static_cast<long long>(p.ldc), splits, kb_per, p.split_rows};
+  GemmArgs a{M,      p.N,    p.K,          p.bias,    p.out, static_cast<long long>(p.ldc),
+             splits, kb_per, p.split_rows, p.heads_S, p.heads_H};
   CC_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmem, s, p.map_a, p.map_b[bn_idx], p.map_c, a));
   return CC_OK;
 }
@@ -513,6 +542,7 @@ int launch_epi(const GemmPlan& p, int bn_idx, int M, cudaStream_t s) {
     case EPI_RESID_F32: return launch<BN, EPI_RESID_F32>(p, bn_idx, M, s);
     case EPI_ARGMAX: return launch<BN, EPI_ARGMAX>(p, bn_idx, M, s);
     case EPI_PARTIAL_F32: return launch<BN, EPI_PARTIAL_F32>(p, bn_idx, M, s);
+    case EPI_F16_HEADS: return launch<BN, EPI_F16_HEADS>(p, bn_idx, M, s);
   }
   set_error("unknown GEMM epilogue %d", p.epi);
   return CC_EINVAL;
@@ -595,11 +625,44 @@ int gemm_plan(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __h
   for (int i = 0; i < 4; ++i) CC_TRY(encode_map(&p->map_b[i], w, N, K, K, bns[i]));
   // fp16 outputs and the fp32 residual update leave through TMA (rows M..max_rows of `out` are scratch: whole 32-row
   // groups are written); fp32 logits and argmax keys use direct stores and get a copy of map_a as a placeholder.
-  CC_REQUIRE(epi != EPI_PARTIAL_F32, CC_EINVAL, "gemm_plan: split-K plans are built with gemm_plan_partial");
+  CC_REQUIRE(epi != EPI_PARTIAL_F32 && epi != EPI_F16_HEADS, CC_EINVAL,
+             "gemm_plan: split-K / head-major plans are built with gemm_plan_partial / gemm_plan_heads");
   if (epi <= EPI_F16_TANH || epi == EPI_RESID_F32)
     CC_TRY(encode_out_map(&p->map_c, out, epi == EPI_RESID_F32, max_rows, N, ldc));
   else
     p->map_c = p->map_a;
+  return CC_OK;
+}
+
+int gemm_plan_heads(GemmPlan* p, const __half* a, int64_t lda, int max_images, int S, int H, const __half* w, int K,
+                    const float* bias, __half* out) {
+  CC_REQUIRE(max_images > 0 && S > 0 && H > 0 && K > 0 && K % 8 == 0, CC_ESHAPE,
+             "gemm_plan_heads: bad shape images=%d S=%d H=%d K=%d", max_images, S, H, K);
+  const int N = 3 * H * 64;
+  p->max_rows = max_images * S;
+  p->N = N;
+  p->K = K;
+  p->epi = EPI_F16_HEADS;
+  p->bias = bias;
+  p->out = out;
+  p->ldc = 64;
+  p->heads_S = S;
+  p->heads_H = H;
+  CC_TRY(encode_map(&p->map_a, a, p->max_rows, K, lda, BM));
+  static const int bns[4] = {32, 64, 128, 256};
+  for (int i = 0; i < 4; ++i) CC_TRY(encode_map(&p->map_b[i], w, N, K, K, bns[i]));
+  // 3-D output map: {64 dims, S tokens, planes}, box {32, 32, 1}, 64-byte swizzle (the staging layout of the epilogue)
+  EncodeTiledFn fn = get_encode_fn();
+  CC_REQUIRE(fn != nullptr, CC_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  CC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, CC_EALIGN, "gemm_plan_heads: output not 16-byte aligned");
+  cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(max_images) * 3 * H};
+  cuuint64_t strides[2] = {64 * 2, static_cast<cuuint64_t>(S) * 64 * 2};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(&p->map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, out, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CC_REQUIRE(r == CUDA_SUCCESS, CC_ECUDA, "cuTensorMapEncodeTiled (head-major output) failed (%d)", (int)r);
   return CC_OK;
 }
 

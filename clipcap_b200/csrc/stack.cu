@@ -56,7 +56,10 @@ int Stack::plan() {
   p_2.resize(L);
   for (size_t l = 0; l < L; ++l) {
     const LayerW& w = layers[l];
-    CC_TRY(gemm_plan(&p_qkv[l], ln16, d, max_rows, w.wqkv, 3 * d, d, EPI_F16_NONE, w.bqkv, qkv16, 3 * d));
+    if (heads_S > 0)
+      CC_TRY(gemm_plan_heads(&p_qkv[l], ln16, d, max_rows / heads_S, heads_S, H, w.wqkv, d, w.bqkv, qkv16));
+    else
+      CC_TRY(gemm_plan(&p_qkv[l], ln16, d, max_rows, w.wqkv, 3 * d, d, EPI_F16_NONE, w.bqkv, qkv16, 3 * d));
     CC_TRY(gemm_plan(&p_o[l], att16, d, max_rows, w.wo, d, d, EPI_RESID_F32, w.bo, h, d));
     CC_TRY(gemm_plan(&p_1[l], ln16, d, max_rows, w.w1, dff, d, act_epi, w.b1, mlp16, dff));
     CC_TRY(gemm_plan(&p_2[l], mlp16, dff, max_rows, w.w2, d, dff, EPI_RESID_F32, w.b2, h, d));
@@ -95,7 +98,12 @@ int Stack::layer_full(int l, int B, int S, KvCache* kv, int slot_stride, cudaStr
   const LayerW& w = layers[l];
   CC_TRY(layernorm_run(h, d, w.ln1_g, w.ln1_b, ln16, d, rows, d, eps, s));
   CC_TRY(gemm_run(p_qkv[l], rows, s));
-  CC_TRY(attention_run(qkv16, qkv16 + d, qkv16 + 2 * d, 3 * d, att16, d, B, S, H, hd, causal, scale, s));
+  if (heads_S > 0) {
+    CC_REQUIRE(S == heads_S, CC_ESHAPE, "stack: head-major QKV planned for %d tokens per image, got %d", heads_S, S);
+    CC_TRY(vit_attention_heads_run(qkv16, att16, d, B, S, H, scale, s));
+  } else {
+    CC_TRY(attention_run(qkv16, qkv16 + d, qkv16 + 2 * d, 3 * d, att16, d, B, S, H, hd, causal, scale, s));
+  }
   launches += 3;
   if (kv != nullptr) {
     CC_TRY(kv_scatter_run(qkv16, kv->k + l * kv->layer_elems, kv->v + l * kv->layer_elems, B, S, H, kv->t_max, 0,

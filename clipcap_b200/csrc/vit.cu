@@ -5,6 +5,8 @@
 //   e = LN_post(h[:,0]) @ proj;  optional e /= ||e||  (clip.py:122-123)
 #include <string>
 
+#include <cstdlib>
+
 #include "common.h"
 
 struct cc_vit {
@@ -95,6 +97,13 @@ int vit_build(cc_vit* m, const cc_tensor* w, int nw) {
     CC_TRY(pack_f16(m->arena, w2, wd, c.mlp_dim, false, c.mlp_dim, &L.w2));
     CC_TRY(keep_f32(m->arena, b2, wd, &L.b2));
     stage.release();
+  }
+  {
+    // ViT-L/14 @ 224 (257 tokens, head dim 64): head-major QKV + tcgen05 attention. CLIPCAP_B200_NO_TC_ATTN=1 keeps the
+    // generic path (A/B measurements).
+    const char* e = getenv("CLIPCAP_B200_NO_TC_ATTN");
+    const bool no_tc = e != nullptr && e[0] == '1';
+    if (!no_tc && m->T == kVitAttnTokens && m->st.hd == 64) m->st.heads_S = m->T;
   }
   CC_TRY(m->st.plan());
   return CC_OK;
