@@ -82,6 +82,12 @@ __device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* m, uint32_t b
       : "memory");
 }
 
+// Plain (non-tensor) bulk copy global -> shared of `bytes` (multiple of 16, both addresses 16-byte aligned).
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 // 2-D tiled store shared -> global (bulk async-group completion). Out-of-bounds parts of the box are clipped.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

@@ -35,9 +35,10 @@ constexpr int VA_S = 257;
 constexpr int VA_Q_BYTES = 256 * 64 * 2;  // both 128-query tiles
 constexpr int VA_K_BYTES = 256 * 64 * 2;
 constexpr int VA_V_BYTES = 256 * 64 * 2;
+constexpr int VA_C_BYTES = 512;  // CLS token rows of q, k, v (3 x 128 B, padded)
 constexpr int VA_STAGE = VA_Q_BYTES + VA_K_BYTES + VA_V_BYTES;
 constexpr int VA_SCRATCH = 2048;  // CLS-query probabilities (256 floats)
-constexpr int VA_SMEM = 2 * VA_STAGE + VA_SCRATCH + 256 + 1024;
+constexpr int VA_SMEM = 2 * VA_STAGE + 2 * VA_C_BYTES + VA_SCRATCH + 256 + 1024;
 constexpr int VA_TMEM_COLS = 512;  // 256 per stream: S [0,256) -> P [0,128) + O [128,192)
 constexpr int VA_EMPTY_ARRIVALS = 2 + 8 + 1;  // both MMA streams (commit), 8 softmax warps, CLS warp
 
@@ -73,6 +74,9 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t r;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
@@ -82,13 +86,15 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
 __global__ void __launch_bounds__(VA_THREADS, 1)
-vit_attn_kernel(const __grid_constant__ CUtensorMap map, VaArgs a, int H, int n_items) {
+vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_o, VaArgs a, int H,
+                int n_items) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   auto sQ = [&](int s) { return base + s * VA_STAGE; };
   auto sK = [&](int s) { return base + s * VA_STAGE + VA_Q_BYTES; };
   auto sV = [&](int s) { return base + s * VA_STAGE + VA_Q_BYTES + VA_K_BYTES; };
-  const uint32_t sP = base + 2 * VA_STAGE;
+  auto sC = [&](int s, int which) { return base + 2 * VA_STAGE + s * VA_C_BYTES + which * 128; };  // CLS q/k/v rows
+  const uint32_t sP = base + 2 * VA_STAGE + 2 * VA_C_BYTES;
   const uint32_t bars = sP + VA_SCRATCH;
   auto full_qk = [&](int s) { return bars + 8u * s; };
   auto full_v = [&](int s) { return bars + 16u + 8u * s; };
@@ -105,6 +111,7 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, VaArgs a, int H, int n_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map);
+    tma_prefetch_desc(&map_o);
     for (int i = 0; i < 2; ++i) {
       mbar_init(full_qk(i), 1);
       mbar_init(full_v(i), 1);
@@ -138,12 +145,15 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, VaArgs a, int H, int n_
         const int rq = va_row(a, b, h, 0) + 1, rk = va_row(a, b, h, 1) + 1, rv = va_row(a, b, h, 2) + 1;
         const int cq = va_col(a, h, 0), ck = va_col(a, h, 1), cv = va_col(a, h, 2);
         mbar_wait(empty(s), ((it >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(full_qk(s), VA_Q_BYTES + VA_K_BYTES);
+        mbar_arrive_expect_tx(full_qk(s), VA_Q_BYTES + VA_K_BYTES + 256);
+        bulk_load(sC(s, 0), a.base + static_cast<long long>(rq - 1) * a.ld + cq, 128, full_qk(s));
+        bulk_load(sC(s, 1), a.base + static_cast<long long>(rk - 1) * a.ld + ck, 128, full_qk(s));
         tma_load_2d(&map, full_qk(s), sQ(s), cq, rq);
         tma_load_2d(&map, full_qk(s), sQ(s) + 128 * 128, cq, rq + 128);
         tma_load_2d(&map, full_qk(s), sK(s), ck, rk);
         tma_load_2d(&map, full_qk(s), sK(s) + 128 * 128, ck, rk + 128);
-        mbar_arrive_expect_tx(full_v(s), VA_V_BYTES);
+        mbar_arrive_expect_tx(full_v(s), VA_V_BYTES + 128);
+        bulk_load(sC(s, 2), a.base + static_cast<long long>(rv - 1) * a.ld + cv, 128, full_v(s));
         tma_load_2d(&map, full_v(s), sV(s), cv, rv);
         tma_load_2d(&map, full_v(s), sV(s) + 128 * 128, cv, rv + 128);
       }
@@ -188,14 +198,12 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, VaArgs a, int H, int n_
       const uint32_t ph_s = (it >> 1) & 1u;
       const int b = w / H, h = w - b * H;
       const long long row0 = static_cast<long long>(b) * VA_S;  // CLS row of this image in the output
-      const __half* q0 = a.base + va_row(a, b, h, 0) * a.ld + va_col(a, h, 0);
-      const __half* k0 = a.base + va_row(a, b, h, 1) * a.ld + va_col(a, h, 1);
-      const __half* v0 = a.base + va_row(a, b, h, 2) * a.ld + va_col(a, h, 2);
+      mbar_wait(full_qk(s), ph_s);
       float qf[64];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float tmp[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(q0) + c), tmp);
+        unpack8(lds128(sC(s, 0) + 16 * c), tmp);
 #pragma unroll
         for (int i = 0; i < 8; ++i) qf[8 * c + i] = tmp[i];
       }
@@ -203,12 +211,10 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, VaArgs a, int H, int n_
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float kf[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(k0) + c), kf);
+        unpack8(lds128(sC(s, 1) + 16 * c), kf);
 #pragma unroll
         for (int e = 0; e < 8; ++e) sc0 += qf[8 * c + e] * kf[e];
       }
-      const float2 v0f = __half22float2(*reinterpret_cast<const __half2*>(v0 + 2 * lane));
-      mbar_wait(full_qk(s), ph_s);
       // scores: lane handles patch keys lane, lane + 32, ... (8 each)
       float sc[8];
       float mx = sc0;
@@ -244,6 +250,8 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, VaArgs a, int H, int n_
       __syncwarp();
       // O: lane owns head dims 2*lane, 2*lane + 1
       mbar_wait(full_v(s), ph_s);
+      const uint32_t v0u = lds32(sC(s, 2) + 4 * lane);
+      const float2 v0f = __half22float2(*reinterpret_cast<const __half2*>(&v0u));
       float o0 = pc * v0f.x, o1 = pc * v0f.y;
       const int c16 = lane >> 2;
       const uint32_t within = (lane & 3) * 4;
@@ -267,31 +275,31 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, VaArgs a, int H, int n_
     const int quad = warp & 3;
     const int r = quad * 32 + lane;  // row inside the 128-query tile == TMEM lane
     const uint32_t t_row = tmem_base + 256u * t + (static_cast<uint32_t>(quad * 32) << 16);
-    int it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      const int s = it & 1;
-      const uint32_t ph_s = (it >> 1) & 1u, ph = it & 1u;
-      const int b = w / H, h = w - b * H;
-      const long long row0 = static_cast<long long>(b) * VA_S;
-      const __half* k0 = a.base + va_row(a, b, h, 1) * a.ld + va_col(a, h, 1);  // CLS key / value rows
-      const __half* v0 = a.base + va_row(a, b, h, 2) * a.ld + va_col(a, h, 2);
-
-      // score against the CLS key while the S MMA runs
-      uint4 k0r[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) k0r[c] = __ldg(reinterpret_cast<const uint4*>(k0) + c);
-      mbar_wait(full_qk(s), ph_s);
+    // score of this thread's query row against the CLS key of the item in stage s (needs Q and the CLS key row)
+    auto cls_score = [&](int s) {
       float s0 = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float qf[8], kf[8];
         unpack8(lds128(sQ(s) + t * 128 * 128 + sw128_off(r, c)), qf);
-        unpack8(k0r[c], kf);
+        unpack8(lds128(sC(s, 1) + 16 * c), kf);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s0 += qf[i] * kf[i];
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty(s));  // this warp no longer reads the stage
+      return s0;
+    };
+    if (t == 1) __nanosleep(1500);  // start the two streams half a period apart so their exp2 phases interleave
+    int it = 0;
+    float s0 = 0.f;
+    if (static_cast<int>(blockIdx.x) < n_items) {
+      mbar_wait(full_qk(0), 0);
+      s0 = cls_score(0);
+    }
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph_s = (it >> 1) & 1u, ph = it & 1u;
+      const int b = w / H, h = w - b * H;
+      const long long row0 = static_cast<long long>(b) * VA_S;
 
       mbar_wait(s_full(t), ph);
       tc_fence_after();
@@ -336,8 +344,12 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, VaArgs a, int H, int n_
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(t));
 
+      // While the P V MMA runs: the next item's CLS-key score (its stage has been loading all along)
+      if (w + static_cast<int>(gridDim.x) < n_items) {
+        mbar_wait(full_qk(s ^ 1), ((it + 1) >> 1) & 1u);
+        s0 = cls_score(s ^ 1);
+      }
       const float inv = 1.f / sum;
-      __half* orow = a.o + (row0 + 1 + 128 * t + r) * a.ldo + h * 64;
 
       mbar_wait(o_full(t), ph);
       tc_fence_after();
@@ -348,24 +360,39 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, VaArgs a, int H, int n_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_free(t));  // the stream's TMEM columns may take the next S
+      uint4 v0r[8];  // CLS value row (o_full implies full_v of this stage)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v0r[c] = lds128(sC(s, 2) + 16 * c);
+      // The output rows leave through shared memory and one TMA store per warp (32 rows x 128 B): a thread-per-row
+      // global store would touch 32 cache lines per instruction. The staging area is this tile's Q buffer, dead since the
+      // S MMA and the CLS-key scores; the stage is released once the bulk store has read it.
+      const uint32_t stg = sQ(s) + t * 128 * 128 + quad * 32 * 128;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float vf[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(v0) + half * 4 + c), vf);
-          uint4 out;
-          uint32_t* op = reinterpret_cast<uint32_t*>(&out);
+          unpack8(v0r[half * 4 + c], vf);
+          uint32_t op[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             op[i] = pack_half2((__uint_as_float(orr[half][8 * c + 2 * i]) + pc * vf[2 * i]) * inv,
                                (__uint_as_float(orr[half][8 * c + 2 * i + 1]) + pc * vf[2 * i + 1]) * inv);
-          *reinterpret_cast<uint4*>(orow + half * 32 + c * 8) = out;
+          st_shared_v4(stg + sw128_off(lane, half * 4 + c), op[0], op[1], op[2], op[3]);
         }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&map_o, stg, h * 64, static_cast<int>(row0) + 1 + 128 * t + 32 * quad);
+        bulk_commit();
+        bulk_wait_read<0>();
+        mbar_arrive(empty(s));  // this warp no longer touches the stage
       }
     }
   }
 
+  if (warp >= 4 && lane == 0) bulk_wait<0>();  // output stores complete before the CTA exits
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -378,6 +405,7 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, VaArgs a, int H, int n_
 
 namespace {
 int va_launch(const __half* base, uint64_t rows, uint64_t cols, int64_t ld, VaArgs a, int B, int H, cudaStream_t s) {
+  CC_REQUIRE((reinterpret_cast<uintptr_t>(a.o) & 15) == 0, CC_EALIGN, "vit attention: output not 16-byte aligned");
   CC_REQUIRE(H <= 65535 && B <= 65535, CC_ESHAPE, "vit attention: grid too large (H=%d B=%d)", H, B);
   static bool configured = false;
   if (!configured) {
@@ -389,9 +417,19 @@ int va_launch(const __half* base, uint64_t rows, uint64_t cols, int64_t ld, VaAr
     const __half* base = nullptr;
     int64_t ld = 0;
     uint64_t rows = 0, cols = 0;
-    CUtensorMap map;
+    const __half* o = nullptr;
+    int64_t ldo = 0;
+    int B = 0, H = 0;
+    CUtensorMap map, map_o;
   };
   static thread_local Cached cache;
+  if (cache.o != a.o || cache.ldo != a.ldo || cache.B != B || cache.H != H) {
+    CC_TRY(tma_map_f16_sw128(&cache.map_o, a.o, static_cast<uint64_t>(B) * VA_S, static_cast<uint64_t>(H) * 64, a.ldo, 32));
+    cache.o = a.o;
+    cache.ldo = a.ldo;
+    cache.B = B;
+    cache.H = H;
+  }
   if (cache.base != base || cache.ld != ld || cache.rows != rows || cache.cols != cols) {
     CC_TRY(tma_map_f16_sw128(&cache.map, base, rows, cols, ld, 128));
     cache.base = base;
@@ -401,7 +439,7 @@ int va_launch(const __half* base, uint64_t rows, uint64_t cols, int64_t ld, VaAr
   }
   const int n_items = B * H;
   const int grid = n_items < num_sms() ? n_items : num_sms();
-  CC_CUDA(launch_pdl(vit_attn_kernel, dim3(grid), dim3(VA_THREADS), VA_SMEM, s, cache.map, a, H, n_items));
+  CC_CUDA(launch_pdl(vit_attn_kernel, dim3(grid), dim3(VA_THREADS), VA_SMEM, s, cache.map, cache.map_o, a, H, n_items));
   return CC_OK;
 }
 }  // namespace
