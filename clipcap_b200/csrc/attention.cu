@@ -258,7 +258,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   }
 }
 
-__global__ void __launch_bounds__(DEC_WARPS * 32)
+__global__ void __launch_bounds__(DEC_WARPS * 32, 8)
 decode_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, __half* __restrict__ vcache,
                    const int32_t* __restrict__ anc, __half* __restrict__ o, int nseq, int H, int t_max, int pos,
                    float scale_log2) {
@@ -362,6 +362,127 @@ decode_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, 
   }
 }
 
+// Greedy decode (no ancestry table): the keys and values of one (sequence, head) are contiguous in the cache, so each
+// warp pulls them into shared memory with two bulk copies (all bytes in flight at once, completion on the warp's own
+// mbarrier) instead of walking them 16 keys per round trip. Same arithmetic and lane layout as decode_attn_kernel.
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+decode_attn_bulk_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, __half* __restrict__ vcache,
+                        __half* __restrict__ o, int nseq, int H, int t_max, int pos, float scale_log2) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __shared__ __align__(8) unsigned long long bars[DEC_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * DEC_WARPS + warp;
+  const uint32_t bar = smem_u32(&bars[warp]);
+  const uint32_t row_bytes = 128;
+  const uint32_t kbuf = smem_u32(dsm) + warp * 2 * pos * row_bytes;  // [pos] K rows, then [pos] V rows
+  const uint32_t vbuf = kbuf + pos * row_bytes;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  pdl_launch_dependents();
+  pdl_wait();
+  if (pair >= nseq * H) return;
+  const int seq = pair / H, h = pair % H;
+  const int d = H * 64;
+  const int kq = lane >> 3;
+  const int c = lane & 7;
+  const long long own = (static_cast<long long>(seq) * H + h) * t_max;
+  if (lane == 0 && pos > 0) {
+    mbar_arrive_expect_tx(bar, 2u * pos * row_bytes);
+    bulk_load(kbuf, kcache + own * 64, pos * row_bytes, bar);
+    bulk_load(vbuf, vcache + own * 64, pos * row_bytes, bar);
+  }
+  const __half* qrow = qkv + static_cast<long long>(seq) * 3 * d + h * 64;
+  const uint4 knew = *reinterpret_cast<const uint4*>(qrow + d + c * 8);
+  const uint4 vnew = *reinterpret_cast<const uint4*>(qrow + 2 * d + c * 8);
+  {  // append this step's k, v for later steps
+    const long long dst = (own + pos) * 64 + c * 8;
+    if (kq == 0) *reinterpret_cast<uint4*>(kcache + dst) = knew;
+    else if (kq == 1) *reinterpret_cast<uint4*>(vcache + dst) = vnew;
+  }
+  float qf[8];
+  unpack8(*reinterpret_cast<const uint4*>(qrow + c * 8), qf);
+  const int T = pos + 1;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  float mx = -INFINITY, lsum = 0.f;
+  if (pos > 0) mbar_wait(bar, 0);
+
+  for (int t0 = 0; t0 < T; t0 += DEC_KEYS) {
+    uint4 kk[4], vv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tt = t0 + 4 * j + kq;
+      if (tt < pos) {
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(kk[j].x), "=r"(kk[j].y), "=r"(kk[j].z), "=r"(kk[j].w)
+                     : "r"(kbuf + tt * row_bytes + c * 16));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(vv[j].x), "=r"(vv[j].y), "=r"(vv[j].z), "=r"(vv[j].w)
+                     : "r"(vbuf + tt * row_bytes + c * 16));
+      } else if (tt == pos) {
+        kk[j] = knew;
+        vv[j] = vnew;
+      } else {
+        kk[j] = make_uint4(0u, 0u, 0u, 0u);
+        vv[j] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    float dot[4];
+    float bm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float kf[8];
+      unpack8(kk[j], kf);
+      float dd = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dd += qf[i] * kf[i];
+      dd += __shfl_xor_sync(0xffffffffu, dd, 1);
+      dd += __shfl_xor_sync(0xffffffffu, dd, 2);
+      dd += __shfl_xor_sync(0xffffffffu, dd, 4);
+      dot[j] = (t0 + 4 * j + kq < T) ? dd : -INFINITY;
+      bm = fmaxf(bm, dot[j]);
+    }
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+    const float nm = fmaxf(mx, bm);
+    const float corr = exp2f((mx - nm) * scale_log2);
+    mx = nm;
+    lsum *= corr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= corr;
+    const float nms = nm * scale_log2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float p = exp2f(dot[j] * scale_log2 - nms);
+      lsum += p;
+      float vf[8];
+      unpack8(vv[j], vf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += p * vf[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+  lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+  if (kq == 0) {
+    const float inv = 1.f / lsum;
+    uint4 out;
+    out.x = pack_half2(acc[0] * inv, acc[1] * inv);
+    out.y = pack_half2(acc[2] * inv, acc[3] * inv);
+    out.z = pack_half2(acc[4] * inv, acc[5] * inv);
+    out.w = pack_half2(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(o + static_cast<long long>(seq) * d + h * 64 + c * 8) = out;
+  }
+}
+
 __global__ void kv_scatter_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache,
                                   __half* __restrict__ vcache, int nseq, int T, int H, int t_max, int pos0,
                                   int slot_stride) {
@@ -417,6 +538,18 @@ int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, cons
   CC_REQUIRE(pos >= 0 && pos < t_max, CC_ESHAPE, "decode attention: position %d outside cache (t_max %d)", pos, t_max);
   const int pairs = nseq * H;
   const int grid = (pairs + DEC_WARPS - 1) / DEC_WARPS;
+  // bulk-copy variant: no ancestry indirection, cache rows 16-byte aligned, staging fits beside two other CTAs
+  const size_t bulk_smem = static_cast<size_t>(DEC_WARPS) * 2 * pos * 128;  // the pos cached rows of K and V per warp
+  if (anc == nullptr && bulk_smem <= 72 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      CC_CUDA(cudaFuncSetAttribute(decode_attn_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+      configured = true;
+    }
+    CC_CUDA(launch_pdl(decode_attn_bulk_kernel, dim3(grid), dim3(DEC_WARPS * 32), bulk_smem, s, qkv, kcache, vcache, o,
+                       nseq, H, t_max, pos, scale * 1.4426950408889634f));
+    return CC_OK;
+  }
   CC_CUDA(launch_pdl(decode_attn_kernel, dim3(grid), dim3(DEC_WARPS * 32), 0, s, qkv, kcache, vcache, anc, o, nseq, H,
                      t_max, pos, scale * 1.4426950408889634f));
   return CC_OK;

@@ -288,13 +288,14 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
       }
       return s0;
     };
-    if (t == 1) __nanosleep(1500);  // start the two streams half a period apart so their exp2 phases interleave
     int it = 0;
     float s0 = 0.f;
     if (static_cast<int>(blockIdx.x) < n_items) {
       mbar_wait(full_qk(0), 0);
       s0 = cls_score(0);
     }
+    bool stagger = (t == 1);  // start the two streams half a period apart so their exp2 phases interleave
+    int release_stage = -1;   // stage whose Q buffer holds this warp's in-flight output rows
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       const int s = it & 1;
       const uint32_t ph_s = (it >> 1) & 1u, ph = it & 1u;
@@ -302,6 +303,10 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
       const long long row0 = static_cast<long long>(b) * VA_S;
 
       mbar_wait(s_full(t), ph);
+      if (stagger) {
+        __nanosleep(2000);
+        stagger = false;
+      }
       tc_fence_after();
       // pass 1: row max (TMEM loads double-buffered in registers)
       float mx = s0;
@@ -317,6 +322,13 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
         }
       }
       const float ms = mx * a.scale_log2;
+      if (release_stage >= 0) {
+        if (lane == 0) {
+          bulk_wait_read<0>();
+          mbar_arrive(empty(release_stage));  // this warp no longer touches that stage
+        }
+        release_stage = -1;
+      }
       // pass 2: p = exp2((s - max) * scale * log2 e), row sum, P -> TMEM as fp16 pairs
       float sum = 0.f;
       {
@@ -386,13 +398,13 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
       if (lane == 0) {
         tma_store_2d(&map_o, stg, h * 64, static_cast<int>(row0) + 1 + 128 * t + 32 * quad);
         bulk_commit();
-        bulk_wait_read<0>();
-        mbar_arrive(empty(s));  // this warp no longer touches the stage
       }
+      release_stage = s;  // released (below / next iteration) once the bulk store has read the staging rows
     }
   }
 
-  if (warp >= 4 && lane == 0) bulk_wait<0>();  // output stores complete before the CTA exits
+  if (warp >= 4 && lane == 0) bulk_wait<0>();  // output stores complete before the CTA exits (no stage left to release:
+                                               // the producer is done)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
