@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-captions", type=int, default=3, help="captions timed for the cpu_baseline sample")
+    ap.add_argument("--cpu-captions", type=int, default=12, help="captions timed for the cpu_baseline sample")
     return ap.parse_args()
 
 
