@@ -138,7 +138,8 @@ int gemm_plan_heads(GemmPlan* p, const __half* a, int64_t lda, int max_images, i
 int gemm_plan_partial(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __half* w, int N, int K,
                       float* partial, int split_rows, int splits, int bn);
 void gemm_pick_split(int M, int N, int K, int* bn_out, int* splits_out);
-int gemm_run(const GemmPlan& p, int M, cudaStream_t s);
+// row0: first row of A / out covered (a multiple of 32); lets independent row groups of one plan run on different streams.
+int gemm_run(const GemmPlan& p, int M, cudaStream_t s, int row0 = 0);
 int gemm_pick_bn(int M, int N, int K);
 // Live timing of GEMM launches with CUDA events on the launching stream (cc_prof_*; bench.py's roofline figure).
 void gemm_prof_enable(bool on);
@@ -256,13 +257,14 @@ struct Stack {
   int init(Arena& arena, int d_, int dff_, int H_, int act_epi_, bool causal_, float eps_, int max_rows_,
            int dec_rows_ = 0);
   // LayerNorm of the first nseq rows of h for the decode path, absorbing pending split-K partial sums first.
-  int ln_decode(const float* g, const float* b, __half* y, int nseq, cudaStream_t s);
+  int ln_decode(const float* g, const float* b, __half* y, int nseq, cudaStream_t s, int row0 = 0);
   int plan();  // after `layers` is filled
   // Full-sequence pass of layer l over B sequences of S rows (rows b*S .. b*S+S-1 of h). If `kv` is given the layer's
   // K,V rows are also scattered into the cache at positions 0..S-1 of slot b*slot_stride.
   int layer_full(int l, int B, int S, KvCache* kv, int slot_stride, cudaStream_t s);
   // One decode step of layer l for nseq single-row sequences at cache position pos.
-  int layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int pos, cudaStream_t s);
+  // row0 > 0 (greedy only, anc == nullptr): the rows row0 .. row0 + nseq - 1, an independent group on its own stream.
+  int layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int pos, cudaStream_t s, int row0 = 0);
 };
 
 }  // namespace cc

@@ -52,6 +52,7 @@ struct GemmArgs {
   int kb_per_split;  // k-blocks per split
   int split_rows;    // row offset of split s inside the partial-sum matrix: s * split_rows
   int heads_S, heads_H;  // EPI_F16_HEADS: tokens per image, heads
+  int row_base;          // first row of A / out this launch covers (decode row groups); rows row_base .. row_base + M - 1
 };
 
 // x * sigmoid(k x) with the two MUFU ops (ex2, rcp) at approximate precision: relative error ~2^-22, far below the
@@ -170,7 +171,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int tile = w / args.splits, split = w - tile * args.splits;
-        const int m0 = (tile / tiles_n) * BM;
+        const int m0 = args.row_base + (tile / tiles_n) * BM;
         const int n0 = (tile % tiles_n) * BN;
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(num_kb, kb0 + args.kb_per_split);
@@ -255,9 +256,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
         const int as = it & 1;
         const int tile = w / args.splits, split = w - tile * args.splits;
-        const int m0 = (tile / tiles_n) * BM;
+        const int m0 = args.row_base + (tile / tiles_n) * BM;
         const int n0 = (tile % tiles_n) * BN;
-        const bool rows_live = (m0 + quad * 32) < args.M;  // warp-uniform
+        const bool rows_live = (m0 + quad * 32) < args.row_base + args.M;  // warp-uniform
         const int out_row = split * args.split_rows + m0 + quad * 32;
         mbar_wait(tfull_bar(as), (it >> 1) & 1u);
         tc_fence_after();
@@ -322,7 +323,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               // Rows of this 32-token group that run past the end of the image belong to the next image's plane: the
               // TMA store below clips them, and their lanes write their 64 bytes directly (1 group in 8 straddles).
               const int img = out_row / args.heads_S, tok = out_row - img * args.heads_S + lane;
-              if (tok >= args.heads_S && out_row + lane < args.M) {
+              if (tok >= args.heads_S && out_row + lane < args.row_base + args.M) {
                 const int d_model = args.heads_H * 64;
                 const int which = nc / d_model, rem = nc - which * d_model;
                 const long long plane = (static_cast<long long>(img + 1) * 3 + which) * args.heads_H + (rem >> 6);
@@ -360,10 +361,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       constexpr int CH = WCOLS < 32 ? WCOLS : 32;
       for (int tile = blockIdx.x; tile < num_work; tile += gridDim.x, ++it) {  // splits == 1 here
         const int as = it & 1;
-        const int m0 = (tile / tiles_n) * BM;
+        const int m0 = args.row_base + (tile / tiles_n) * BM;
         const int n0 = (tile % tiles_n) * BN;
         const int m = m0 + row_in_tile;
-        const bool row_ok = m < args.M;
+        const bool row_ok = m < args.row_base + args.M;
         mbar_wait(tfull_bar(as), (it >> 1) & 1u);
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + col_base;
@@ -511,7 +512,7 @@ int encode_out_map(CUtensorMap* m, void* base, bool f32, uint64_t rows, uint64_t
 }
 
 template <int BN, int EPI>
-int launch(const GemmPlan& p, int bn_idx, int M, cudaStream_t s) {
+int launch(const GemmPlan& p, int bn_idx, int M, cudaStream_t s, int row0) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   auto kern = gemm_tn_kernel<BN, EPI>;
@@ -525,24 +526,24 @@ int launch(const GemmPlan& p, int bn_idx, int M, cudaStream_t s) {
   const int splits = (EPI == EPI_PARTIAL_F32) ? p.splits : 1;
   const int kb_per = (num_kb + splits - 1) / splits;
   GemmArgs a{M,      p.N,    p.K,          p.bias,    p.out, static_cast<long long>(p.ldc),
-             splits, kb_per, p.split_rows, p.heads_S, p.heads_H};
+             splits, kb_per, p.split_rows, p.heads_S, p.heads_H, row0};
   CC_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmem, s, p.map_a, p.map_b[bn_idx], p.map_c, a));
   return CC_OK;
 }
 
 template <int BN>
-int launch_epi(const GemmPlan& p, int bn_idx, int M, cudaStream_t s) {
+int launch_epi(const GemmPlan& p, int bn_idx, int M, cudaStream_t s, int row0) {
   switch (p.epi) {
-    case EPI_F16_NONE: return launch<BN, EPI_F16_NONE>(p, bn_idx, M, s);
-    case EPI_F16_RELU: return launch<BN, EPI_F16_RELU>(p, bn_idx, M, s);
-    case EPI_F16_QUICKGELU: return launch<BN, EPI_F16_QUICKGELU>(p, bn_idx, M, s);
-    case EPI_F16_GELU_NEW: return launch<BN, EPI_F16_GELU_NEW>(p, bn_idx, M, s);
-    case EPI_F16_TANH: return launch<BN, EPI_F16_TANH>(p, bn_idx, M, s);
-    case EPI_F32: return launch<BN, EPI_F32>(p, bn_idx, M, s);
-    case EPI_RESID_F32: return launch<BN, EPI_RESID_F32>(p, bn_idx, M, s);
-    case EPI_ARGMAX: return launch<BN, EPI_ARGMAX>(p, bn_idx, M, s);
-    case EPI_PARTIAL_F32: return launch<BN, EPI_PARTIAL_F32>(p, bn_idx, M, s);
-    case EPI_F16_HEADS: return launch<BN, EPI_F16_HEADS>(p, bn_idx, M, s);
+    case EPI_F16_NONE: return launch<BN, EPI_F16_NONE>(p, bn_idx, M, s, row0);
+    case EPI_F16_RELU: return launch<BN, EPI_F16_RELU>(p, bn_idx, M, s, row0);
+    case EPI_F16_QUICKGELU: return launch<BN, EPI_F16_QUICKGELU>(p, bn_idx, M, s, row0);
+    case EPI_F16_GELU_NEW: return launch<BN, EPI_F16_GELU_NEW>(p, bn_idx, M, s, row0);
+    case EPI_F16_TANH: return launch<BN, EPI_F16_TANH>(p, bn_idx, M, s, row0);
+    case EPI_F32: return launch<BN, EPI_F32>(p, bn_idx, M, s, row0);
+    case EPI_RESID_F32: return launch<BN, EPI_RESID_F32>(p, bn_idx, M, s, row0);
+    case EPI_ARGMAX: return launch<BN, EPI_ARGMAX>(p, bn_idx, M, s, row0);
+    case EPI_PARTIAL_F32: return launch<BN, EPI_PARTIAL_F32>(p, bn_idx, M, s, row0);
+    case EPI_F16_HEADS: return launch<BN, EPI_F16_HEADS>(p, bn_idx, M, s, row0);
   }
   set_error("unknown GEMM epilogue %d", p.epi);
   return CC_EINVAL;
@@ -703,7 +704,7 @@ struct ProfRec {
 };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
-int gemm_dispatch(const GemmPlan& p, int bn, int M, cudaStream_t s);
+int gemm_dispatch(const GemmPlan& p, int bn, int M, cudaStream_t s, int row0);
 }  // namespace
 
 void gemm_prof_enable(bool on) {
@@ -731,8 +732,10 @@ void gemm_prof_read(double* ms, double* flops, long long* n) {
   }
 }
 
-int gemm_run(const GemmPlan& p, int M, cudaStream_t s) {
-  CC_REQUIRE(M > 0 && M <= p.max_rows, CC_ESHAPE, "gemm_run: M=%d outside plan (max %d)", M, p.max_rows);
+int gemm_run(const GemmPlan& p, int M, cudaStream_t s, int row0) {
+  CC_REQUIRE(M > 0 && row0 >= 0 && row0 + M <= p.max_rows, CC_ESHAPE, "gemm_run: rows %d..%d outside plan (max %d)", row0,
+             row0 + M, p.max_rows);
+  CC_REQUIRE(row0 % 32 == 0, CC_ESHAPE, "gemm_run: row group must start at a multiple of 32 (got %d)", row0);
   const int bn = p.force_bn ? p.force_bn : gemm_pick_bn(M, p.N, p.K);
   if (g_prof_on) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -744,22 +747,22 @@ int gemm_run(const GemmPlan& p, int M, cudaStream_t s) {
       CC_CUDA(cudaEventCreate(&r.e0));
       CC_CUDA(cudaEventCreate(&r.e1));
       CC_CUDA(cudaEventRecord(r.e0, s));
-      const int st = gemm_dispatch(p, bn, M, s);
+      const int st = gemm_dispatch(p, bn, M, s, row0);
       CC_CUDA(cudaEventRecord(r.e1, s));
       g_prof.push_back(r);
       return st;
     }
   }
-  return gemm_dispatch(p, bn, M, s);
+  return gemm_dispatch(p, bn, M, s, row0);
 }
 
 namespace {
-int gemm_dispatch(const GemmPlan& p, int bn, int M, cudaStream_t s) {
+int gemm_dispatch(const GemmPlan& p, int bn, int M, cudaStream_t s, int row0) {
   switch (bn) {
-    case 32: return launch_epi<32>(p, 0, M, s);
-    case 64: return launch_epi<64>(p, 1, M, s);
-    case 128: return launch_epi<128>(p, 2, M, s);
-    case 256: return launch_epi<256>(p, 3, M, s);
+    case 32: return launch_epi<32>(p, 0, M, s, row0);
+    case 64: return launch_epi<64>(p, 1, M, s, row0);
+    case 128: return launch_epi<128>(p, 2, M, s, row0);
+    case 256: return launch_epi<256>(p, 3, M, s, row0);
   }
   set_error("gemm_run: unsupported BLOCK_N %d", bn);
   return CC_EINVAL;

@@ -35,6 +35,14 @@ struct cc_gpt2 {
   int max_entry = 0;
   cc::GemmPlan p_head_keys, p_head_logits;
   cudaStream_t cap_stream = nullptr;
+  // Greedy decode can run as independent row groups on parallel streams (parallel branches of the captured graph).
+  // Measured on B200 at B=256 it loses (1 group 31.9 ms, 2 groups 36.2 ms, 4 groups 45.5 ms per generate call: the
+  // branches' GEMM CTAs compete for whole SMs and every group re-streams the weights), so the default is one group;
+  // CLIPCAP_B200_DECODE_GROUPS=n keeps the experiment reproducible.
+  static constexpr int kMaxGroups = 4;
+  int decode_groups = 1;
+  cudaStream_t grp_stream[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
   using Key = std::tuple<int, int, int, int, int, int, uint32_t>;
   std::map<Key, cudaGraphExec_t> graphs;
   bool use_graphs = true;
@@ -43,6 +51,11 @@ struct cc_gpt2 {
   ~cc_gpt2() {
     for (auto& kv_ : graphs) cudaGraphExecDestroy(kv_.second);
     if (cap_stream) cudaStreamDestroy(cap_stream);
+    for (int i = 0; i < kMaxGroups; ++i) {
+      if (grp_stream[i]) cudaStreamDestroy(grp_stream[i]);
+      if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+    }
+    if (ev_fork) cudaEventDestroy(ev_fork);
   }
 };
 
@@ -141,6 +154,17 @@ int gpt2_build(cc_gpt2* m, const cc_tensor* w, int nw) {
   CC_TRY(gemm_plan(&m->p_head_keys, m->lnf16, d, m->max_seqs, m->wte16, c.V, d, EPI_ARGMAX, nullptr, m->keys, 1));
   CC_TRY(gemm_plan(&m->p_head_logits, m->lnf16, d, m->max_seqs, m->wte16, c.V, d, EPI_F32, nullptr, m->logits, m->v_ld));
   CC_CUDA(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+  {
+    const char* e = getenv("CLIPCAP_B200_DECODE_GROUPS");
+    if (e != nullptr) m->decode_groups = atoi(e);
+    if (m->decode_groups < 1) m->decode_groups = 1;
+    if (m->decode_groups > cc_gpt2::kMaxGroups) m->decode_groups = cc_gpt2::kMaxGroups;
+    CC_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    for (int i = 1; i < m->decode_groups; ++i) {
+      CC_CUDA(cudaStreamCreateWithFlags(&m->grp_stream[i], cudaStreamNonBlocking));
+      CC_CUDA(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
+    }
+  }
   const char* ng = getenv("CLIPCAP_B200_NO_GRAPH");
   m->use_graphs = !(ng != nullptr && ng[0] == '1');
   return CC_OK;
@@ -176,25 +200,50 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
     extra += 3;
   }
   int cur = 0;  // ping-pong index of the beam token / ancestry tables
-  for (int step = 1; step < EL; ++step) {
-    const int pos = Tp + step - 1;  // position of the token fed this step
-    const int32_t* toks = is_beam ? m->beam.tokens[cur] : m->g_tokens;
-    CC_TRY(gpt2_embed_tokens_run(toks + (step - 1), EL, m->wte32, m->wpe32, st.h, nseq, d, pos, c.V, s));
-    for (int l = 0; l < c.L; ++l)
-      CC_TRY(st.layer_decode(l, nseq, &m->kv, is_beam ? m->beam.anc[cur] : nullptr, pos, s));
-    CC_TRY(st.ln_decode(m->lnf_g, m->lnf_b, m->lnf16, nseq, s));  // absorbs the last layer's fc2 partial sums
-    extra += 1;
-    if (!is_beam) {
-      CC_TRY(gemm_run(m->p_head_keys, nseq, s));
-      CC_TRY(greedy_select_run(m->keys, m->g_tokens, EL, step, m->g_stopped, m->g_lengths, g.stop_token, nseq, s));
-      extra += 2;
-    } else {
+  if (!is_beam) {
+    // Row groups: boundaries are multiples of 32 rows (the GEMM epilogue stores whole 32-row groups), group 0 stays on
+    // the caller's stream, the others fork from it after the first token and join before the results are read.
+    int G = m->decode_groups;
+    int rows_per = ((nseq + G - 1) / G + 31) / 32 * 32;
+    if (nseq < 64 || EL < 2) {
+      G = 1;
+      rows_per = nseq;
+    }
+    G = (nseq + rows_per - 1) / rows_per;
+    if (G > 1) CC_CUDA(cudaEventRecord(m->ev_fork, s));
+    for (int gi = 0; gi < G; ++gi) {
+      const int row0 = gi * rows_per;
+      const int n = nseq - row0 < rows_per ? nseq - row0 : rows_per;
+      cudaStream_t gs = gi == 0 ? s : m->grp_stream[gi];
+      if (gi > 0) CC_CUDA(cudaStreamWaitEvent(gs, m->ev_fork, 0));
+      for (int step = 1; step < EL; ++step) {
+        const int pos = Tp + step - 1;  // position of the token fed this step
+        CC_TRY(gpt2_embed_tokens_run(m->g_tokens + static_cast<size_t>(row0) * EL + (step - 1), EL, m->wte32, m->wpe32,
+                                     st.h + static_cast<size_t>(row0) * d, n, d, pos, c.V, gs));
+        for (int l = 0; l < c.L; ++l) CC_TRY(st.layer_decode(l, n, &m->kv, nullptr, pos, gs, row0));
+        CC_TRY(st.ln_decode(m->lnf_g, m->lnf_b, m->lnf16, n, gs, row0));  // absorbs the last layer's fc2 partial sums
+        CC_TRY(gemm_run(m->p_head_keys, n, gs, row0));
+        CC_TRY(greedy_select_run(m->keys + row0, m->g_tokens + static_cast<size_t>(row0) * EL, EL, step,
+                                 m->g_stopped + row0, m->g_lengths + row0, g.stop_token, n, gs));
+        extra += 3;
+      }
+      if (gi > 0) {
+        CC_CUDA(cudaEventRecord(m->ev_join[gi], gs));
+        CC_CUDA(cudaStreamWaitEvent(s, m->ev_join[gi], 0));
+      }
+    }
+  } else {
+    for (int step = 1; step < EL; ++step) {
+      const int pos = Tp + step - 1;  // position of the token fed this step
+      CC_TRY(gpt2_embed_tokens_run(m->beam.tokens[cur] + (step - 1), EL, m->wte32, m->wpe32, st.h, nseq, d, pos, c.V, s));
+      for (int l = 0; l < c.L; ++l) CC_TRY(st.layer_decode(l, nseq, &m->kv, m->beam.anc[cur], pos, s));
+      CC_TRY(st.ln_decode(m->lnf_g, m->lnf_b, m->lnf16, nseq, s));  // absorbs the last layer's fc2 partial sums
       CC_TRY(gemm_run(m->p_head_logits, nseq, s));
       CC_TRY(row_topk_run(m->logits, m->v_ld, c.V, inv_temp, beam, m->beam.stopped, m->cand_val, m->cand_idx, nseq, s));
       CC_TRY(beam_step_run(m->cand_val, m->cand_idx, m->beam, cur, beam, c.V, EL, m->t_max, step, pos, g.stop_token, B,
                            s));
       cur ^= 1;
-      extra += 3;
+      extra += 4;
     }
   }
   if (is_beam) {

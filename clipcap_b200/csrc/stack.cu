@@ -82,14 +82,15 @@ int Stack::plan() {
   return CC_OK;
 }
 
-int Stack::ln_decode(const float* g, const float* b, __half* y, int nseq, cudaStream_t s) {
+int Stack::ln_decode(const float* g, const float* b, __half* y, int nseq, cudaStream_t s, int row0) {
   const int sp = pend_splits;
   const float* bias = pend_bias;
   pend_splits = 0;
   pend_bias = nullptr;
   launches += 1;
-  return layernorm_reduce_run(h, d, sp > 0 ? part : nullptr, sp, static_cast<int64_t>(dec_rows_pad) * d, bias, g, b, y, d,
-                              nseq, d, eps, s);
+  const size_t off = static_cast<size_t>(row0) * d;
+  return layernorm_reduce_run(h + off, d, sp > 0 ? part + off : nullptr, sp, static_cast<int64_t>(dec_rows_pad) * d, bias, g,
+                              b, y + off, d, nseq, d, eps, s);
 }
 
 int Stack::layer_full(int l, int B, int S, KvCache* kv, int slot_stride, cudaStream_t s) {
@@ -118,21 +119,25 @@ int Stack::layer_full(int l, int B, int S, KvCache* kv, int slot_stride, cudaStr
   return CC_OK;
 }
 
-int Stack::layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int pos, cudaStream_t s) {
-  CC_REQUIRE(nseq <= max_rows && nseq <= kv->slots, CC_ESHAPE, "stack: %d sequences exceed handle capacity", nseq);
+int Stack::layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int pos, cudaStream_t s, int row0) {
+  CC_REQUIRE(row0 + nseq <= max_rows && row0 + nseq <= kv->slots, CC_ESHAPE, "stack: %d sequences exceed handle capacity",
+             row0 + nseq);
+  CC_REQUIRE(row0 == 0 || anc == nullptr, CC_EINVAL, "stack: row groups need the ancestry-free (greedy) cache layout");
   CC_REQUIRE(hd == 64, CC_ESHAPE, "decode attention needs head dim 64 (got %d)", hd);
-  CC_REQUIRE(nseq <= dec_rows, CC_ESHAPE, "stack: %d sequences exceed the %d decode rows planned", nseq, dec_rows);
+  CC_REQUIRE(row0 + nseq <= dec_rows, CC_ESHAPE, "stack: %d sequences exceed the %d decode rows planned", row0 + nseq,
+             dec_rows);
   const LayerW& w = layers[l];
-  CC_TRY(ln_decode(w.ln1_g, w.ln1_b, ln16, nseq, s));  // absorbs the previous layer's fc2 partial sums
-  CC_TRY(gemm_run(p_qkv[l], nseq, s));
-  CC_TRY(decode_attention_run(qkv16, kv->k + l * kv->layer_elems, kv->v + l * kv->layer_elems, anc, att16, nseq, H,
-                              kv->t_max, pos, scale, s));
-  CC_TRY(gemm_run(p_o_dec[l], nseq, s));
+  const size_t cache_off = l * kv->layer_elems + static_cast<size_t>(row0) * H * kv->t_max * 64;  // slot == row
+  CC_TRY(ln_decode(w.ln1_g, w.ln1_b, ln16, nseq, s, row0));  // absorbs the previous layer's fc2 partial sums
+  CC_TRY(gemm_run(p_qkv[l], nseq, s, row0));
+  CC_TRY(decode_attention_run(qkv16 + static_cast<size_t>(row0) * 3 * d, kv->k + cache_off, kv->v + cache_off, anc,
+                              att16 + static_cast<size_t>(row0) * d, nseq, H, kv->t_max, pos, scale, s));
+  CC_TRY(gemm_run(p_o_dec[l], nseq, s, row0));
   pend_splits = p_o_dec[l].splits;
   pend_bias = w.bo;
-  CC_TRY(ln_decode(w.ln2_g, w.ln2_b, ln16, nseq, s));
-  CC_TRY(gemm_run(p_1[l], nseq, s));
-  CC_TRY(gemm_run(p_2_dec[l], nseq, s));
+  CC_TRY(ln_decode(w.ln2_g, w.ln2_b, ln16, nseq, s, row0));
+  CC_TRY(gemm_run(p_1[l], nseq, s, row0));
+  CC_TRY(gemm_run(p_2_dec[l], nseq, s, row0));
   pend_splits = p_2_dec[l].splits;
   pend_bias = w.b2;
   launches += 5;
