@@ -21,7 +21,7 @@ STATUS_NAMES = {0: "CC_OK", -1: "CC_EINVAL", -2: "CC_ESHAPE", -3: "CC_EALIGN", -
 EPI_F16_NONE, EPI_F16_RELU, EPI_F16_QUICKGELU, EPI_F16_GELU_NEW, EPI_F16_TANH, EPI_F32, EPI_RESID_F32, EPI_ARGMAX = range(8)
 
 CC_MAPPER_TRANSFORMER, CC_MAPPER_WINDOWED, CC_MAPPER_MLP = 0, 1, 2
-CC_GEN_GREEDY, CC_GEN_BEAM = 0, 1
+CC_GEN_GREEDY, CC_GEN_BEAM, CC_GEN_NUCLEUS, CC_GEN_SAMPLE = 0, 1, 2, 3
 
 
 class CCError(RuntimeError):
@@ -52,7 +52,9 @@ class cc_gpt2_cfg(C.Structure):
 
 class cc_gen_cfg(C.Structure):
     _fields_ = [("mode", C.c_int32), ("beam", C.c_int32), ("entry_length", C.c_int32), ("temperature", C.c_float),
-                ("stop_token", C.c_int32)]
+                ("stop_token", C.c_int32), ("top_p", C.c_float), ("top_k", C.c_int32), ("repetition_penalty", C.c_float),
+                ("desired_sentence_length", C.c_int32), ("sentence_length_factor", C.c_float), ("n_history", C.c_int32),
+                ("history", C.c_void_p), ("seed", C.c_uint64)]
 
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -82,6 +84,7 @@ PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {
     "cc_op_layernorm": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _vp]),
     "cc_op_attention": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "cc_op_decode_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "cc_op_sample": (_i, [_vp, _i, _i, C.POINTER(cc_gen_cfg), _i, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

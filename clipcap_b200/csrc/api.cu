@@ -1,6 +1,7 @@
 // C-ABI odds and ends: error/version strings and the kernel-level test hooks declared at the bottom of
 // include/clipcap_b200.h.  The hooks launch exactly the kernels the engines launch (same plans, same heuristics).
 #include "common.h"
+#include "decode.h"
 
 extern "C" {
 
@@ -56,6 +57,28 @@ int cc_op_decode_attention(const void* qkv, void* kcache, void* vcache, const in
   return decode_attention_run(static_cast<const __half*>(qkv), static_cast<__half*>(kcache),
                               static_cast<__half*>(vcache), anc, static_cast<__half*>(o), nseq, H, t_max, pos, scale,
                               static_cast<cudaStream_t>(stream));
+}
+
+int cc_op_sample(const float* logits, int rows, int V, const cc_gen_cfg* g, int step, int32_t* tokens, int32_t* stopped,
+                 int32_t* lengths, void* stream) {
+  using namespace cc;
+  CC_REQUIRE(logits != nullptr && g != nullptr && tokens != nullptr && stopped != nullptr && lengths != nullptr, CC_EINVAL,
+             "cc_op_sample: null argument");
+  CC_TRY(check_device_sm100());
+  CC_REQUIRE(step >= 0 && step < g->entry_length, CC_EINVAL, "cc_op_sample: step %d outside entry_length %d", step,
+             g->entry_length);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static unsigned long long* d_seed = nullptr;  // test hook: one scratch scalar per process
+  if (d_seed == nullptr) CC_CUDA(cudaMalloc(&d_seed, sizeof(unsigned long long)));
+  const unsigned long long seed = g->seed;
+  CC_CUDA(cudaMemcpyAsync(d_seed, &seed, sizeof(seed), cudaMemcpyHostToDevice, s));
+  const float inv_temp = 1.0f / (g->temperature > 0.f ? g->temperature : 1.0f);
+  const float lps = g->desired_sentence_length != 0
+                        ? g->sentence_length_factor / static_cast<float>(g->desired_sentence_length)
+                        : 0.f;
+  return sample_run(logits, V, V, g->mode, inv_temp, g->top_p, g->top_k, g->repetition_penalty, lps, g->stop_token,
+                    g->history, g->mode == CC_GEN_SAMPLE ? g->n_history : 0, tokens, g->entry_length, step, stopped, lengths,
+                    d_seed, rows, s);
 }
 
 }  // extern "C"

@@ -26,6 +26,11 @@ int beam_init_run(const float* cand_val, const int32_t* cand_idx, const BeamStat
                   int t_max, int Tp, int stop_token, int n_img, cudaStream_t s);
 int beam_step_run(const float* cand_val, const int32_t* cand_idx, const BeamState& st, int in, int beam, int V,
                   int entry_len, int t_max, int step, int pos, int stop_token, int n_img, cudaStream_t s);
+// One sampling step for `rows` sequences (sample.cu): NUCLEUS / SAMPLE token selection on fp32 logits.
+int sample_run(const float* logits, int64_t ldl, int V, int mode, float inv_temp, float top_p, int top_k,
+               float rep_penalty, float len_penalty_scale, int stop_token, const int32_t* prefix_hist, int n_prefix,
+               int32_t* tokens, int entry_len, int step, int32_t* stopped, int32_t* lengths,
+               const unsigned long long* seed, int rows, cudaStream_t s);
 int beam_final_run(const BeamState& st, int cur, int beam, int entry_len, int32_t* tokens, int32_t* lengths,
                    float* scores, int n_img, cudaStream_t s);
 

@@ -29,6 +29,8 @@ struct cc_gpt2 {
   unsigned long long* keys = nullptr;
   int32_t *g_tokens = nullptr, *g_lengths = nullptr, *g_stopped = nullptr;  // greedy state / final outputs
   float* g_scores = nullptr;
+  unsigned long long* d_seed = nullptr;  // sampling modes: Philox seed of the current call
+  int32_t* d_history = nullptr;          // sampling modes: text-prefix tokens (device copy), kMaxHistory entries
   float* cand_val = nullptr;
   int32_t* cand_idx = nullptr;
   cc::BeamState beam{};
@@ -62,7 +64,8 @@ struct cc_gpt2 {
 namespace cc {
 namespace {
 
-constexpr int kMaxEntry = 128;  // generated tokens per call the state buffers are sized for
+constexpr int kMaxEntry = 128;   // generated tokens per call the state buffers are sized for
+constexpr int kMaxHistory = 512;  // text-prefix tokens a sampling call may carry
 
 int gpt2_build(cc_gpt2* m, const cc_tensor* w, int nw) {
   const cc_gpt2_cfg& c = m->cfg;
@@ -138,6 +141,8 @@ int gpt2_build(cc_gpt2* m, const cc_tensor* w, int nw) {
   CC_TRY(m->arena.alloc_t(&m->g_lengths, ns));
   CC_TRY(m->arena.alloc_t(&m->g_stopped, ns));
   CC_TRY(m->arena.alloc_t(&m->g_scores, ns));
+  CC_TRY(m->arena.alloc_t(&m->d_seed, 1));
+  CC_TRY(m->arena.alloc_t(&m->d_history, kMaxHistory));
   CC_TRY(m->arena.alloc_t(&m->cand_val, ns * kMaxBeam));
   CC_TRY(m->arena.alloc_t(&m->cand_idx, ns * kMaxBeam));
   CC_TRY(m->arena.alloc_t(&m->beam.scores, ns));
@@ -170,13 +175,26 @@ int gpt2_build(cc_gpt2* m, const cc_tensor* w, int nw) {
   return CC_OK;
 }
 
+inline float inv_temp_of(const cc_gen_cfg& g) { return 1.0f / (g.temperature > 0.f ? g.temperature : 1.0f); }
+inline int nseq_of(int B, int beam) { return B * beam; }
+
 // Everything of one generate call after the prefix rows have been written into st.h; results land in g_tokens /
 // g_lengths / g_scores. Safe to capture into a graph: touches only handle-owned memory.
 int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_t s) {
   const cc_gpt2_cfg& c = m->cfg;
   const int d = c.d, EL = g.entry_length;
   const bool is_beam = g.mode == CC_GEN_BEAM;
+  const bool is_sample = g.mode == CC_GEN_NUCLEUS || g.mode == CC_GEN_SAMPLE;
   const int beam = is_beam ? g.beam : 1;
+  // one sampling step on the logits of the rows' last position (sample.cu)
+  auto sample_step = [&](int step) -> int {
+    const float lps = g.desired_sentence_length != 0
+                          ? g.sentence_length_factor / static_cast<float>(g.desired_sentence_length)
+                          : 0.f;
+    return sample_run(m->logits, m->v_ld, c.V, g.mode, inv_temp_of(g), g.top_p, g.top_k, g.repetition_penalty, lps,
+                      g.stop_token, m->d_history, g.mode == CC_GEN_SAMPLE ? g.n_history : 0, m->g_tokens, EL, step,
+                      m->g_stopped, m->g_lengths, m->d_seed, nseq_of(B, beam), s);
+  };
   const int nseq = B * beam;
   const float inv_temp = 1.0f / (g.temperature > 0.f ? g.temperature : 1.0f);
   Stack& st = m->st;
@@ -188,7 +206,12 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
   CC_TRY(layernorm_run(st.h + static_cast<size_t>(Tp - 1) * d, static_cast<int64_t>(Tp) * d, m->lnf_g, m->lnf_b,
                        m->lnf16, d, B, d, c.eps, s));
   extra += 1;
-  if (!is_beam) {
+  if (is_sample) {
+    CC_TRY(gen_reset_run(m->g_stopped, m->g_lengths, m->keys, B, s));
+    CC_TRY(gemm_run(m->p_head_logits, B, s));
+    CC_TRY(sample_step(0));
+    extra += 3;
+  } else if (!is_beam) {
     CC_TRY(gen_reset_run(m->g_stopped, m->g_lengths, m->keys, B, s));
     CC_TRY(gemm_run(m->p_head_keys, B, s));
     CC_TRY(greedy_select_run(m->keys, m->g_tokens, EL, 0, m->g_stopped, m->g_lengths, g.stop_token, B, s));
@@ -200,7 +223,17 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
     extra += 3;
   }
   int cur = 0;  // ping-pong index of the beam token / ancestry tables
-  if (!is_beam) {
+  if (is_sample) {
+    for (int step = 1; step < EL; ++step) {
+      const int pos = Tp + step - 1;
+      CC_TRY(gpt2_embed_tokens_run(m->g_tokens + (step - 1), EL, m->wte32, m->wpe32, st.h, nseq, d, pos, c.V, s));
+      for (int l = 0; l < c.L; ++l) CC_TRY(st.layer_decode(l, nseq, &m->kv, nullptr, pos, s));
+      CC_TRY(st.ln_decode(m->lnf_g, m->lnf_b, m->lnf16, nseq, s));
+      CC_TRY(gemm_run(m->p_head_logits, nseq, s));
+      CC_TRY(sample_step(step));
+      extra += 4;
+    }
+  } else if (!is_beam) {
     // Row groups: boundaries are multiples of 32 rows (the GEMM epilogue stores whole 32-row groups), group 0 stays on
     // the caller's stream, the others fork from it after the first token and join before the results are read.
     int G = m->decode_groups;
@@ -320,7 +353,13 @@ int cc_generate(cc_gpt2* m, const void* prefix, int dtype, int B, int Tp, const 
   using namespace cc;
   CC_REQUIRE(m != nullptr && prefix != nullptr && g != nullptr && tokens != nullptr && lengths != nullptr, CC_EINVAL,
              "cc_generate: null argument");
-  CC_REQUIRE(g->mode == CC_GEN_GREEDY || g->mode == CC_GEN_BEAM, CC_EINVAL, "cc_generate: mode %d", g->mode);
+  CC_REQUIRE(g->mode >= CC_GEN_GREEDY && g->mode <= CC_GEN_SAMPLE, CC_EINVAL, "cc_generate: mode %d", g->mode);
+  const bool sampling = g->mode == CC_GEN_NUCLEUS || g->mode == CC_GEN_SAMPLE;
+  if (sampling) {
+    CC_REQUIRE(g->n_history >= 0 && g->n_history <= kMaxHistory && (g->n_history == 0 || g->history != nullptr), CC_EINVAL,
+               "cc_generate: %d history tokens (max %d)", g->n_history, kMaxHistory);
+    CC_REQUIRE(g->top_k >= 0, CC_EINVAL, "cc_generate: top_k %d", g->top_k);
+  }
   const int beam = g->mode == CC_GEN_BEAM ? g->beam : 1;
   CC_REQUIRE(beam >= 1 && beam <= kMaxBeam, CC_ESHAPE, "cc_generate: beam size %d outside 1..%d", beam, kMaxBeam);
   CC_REQUIRE(g->entry_length >= 1 && g->entry_length <= m->max_entry, CC_ESHAPE,
@@ -336,7 +375,14 @@ int cc_generate(cc_gpt2* m, const void* prefix, int dtype, int B, int Tp, const 
   // h = inputs_embeds + wpe[0..Tp-1]   (modeling_gpt2.py:579-585); reads the caller's buffer, so it stays outside the graph
   CC_TRY(gpt2_embed_prefix_run(prefix, dtype, m->wpe32, m->st.h, B, Tp, d, 0, s));
 
-  if (!m->use_graphs) {
+  if (sampling) {
+    // per-call inputs of the sampling kernel live in handle-owned device memory
+    const unsigned long long seed = g->seed;
+    CC_CUDA(cudaMemcpyAsync(m->d_seed, &seed, sizeof(seed), cudaMemcpyHostToDevice, s));
+    if (g->n_history > 0)
+      CC_CUDA(cudaMemcpyAsync(m->d_history, g->history, sizeof(int32_t) * g->n_history, cudaMemcpyHostToDevice, s));
+  }
+  if (!m->use_graphs || sampling) {  // sampling calls carry many free parameters: enqueued directly, not cached as graphs
     CC_TRY(enqueue_generate(m, B, Tp, *g, s));
   } else {
     uint32_t tbits;

@@ -145,16 +145,31 @@ class Gpt2Engine(_Handle):
                                                     _ffi.torch_dtype_code(out), _ffi.current_stream_ptr()))
         return out.view(*ids.shape, self.cfg.d)
 
+    _MODES = {"greedy": _ffi.CC_GEN_GREEDY, "beam": _ffi.CC_GEN_BEAM, "nucleus": _ffi.CC_GEN_NUCLEUS,
+              "sample": _ffi.CC_GEN_SAMPLE}
+
     def generate(self, prefix: torch.Tensor, mode: str = "greedy", beam: int = 1, entry_length: int = 67,
-                 temperature: float = 1.0, stop_token: int = 50256):
-        """-> (tokens int32 [B, entry_length], lengths int32 [B], scores fp32 [B]) on the device, no host sync."""
+                 temperature: float = 1.0, stop_token: int = 50256, top_p: float = 1.0, top_k: int = 0,
+                 repetition_penalty: float = 1.0, desired_sentence_length: int = 50,
+                 sentence_length_factor: float = 1.0, history=None, seed: int = 0):
+        """-> (tokens int32 [B, entry_length], lengths int32 [B], scores fp32 [B]) on the device, no host sync.
+        mode: "greedy" | "beam" (generate_beam), "nucleus" (generate_nucleus_sampling), "sample" (generate_no_beam);
+        `history` = text-prefix token ids that start every row's repetition-penalty history ("sample" only)."""
+        if mode not in self._MODES:
+            raise ValueError(f"unknown decode mode '{mode}'")
         _require_cuda(prefix, "prefix embeddings")
         if prefix.dim() != 3 or prefix.shape[2] != self.cfg.d:
             raise ValueError(f"prefix must be [B, Tp, {self.cfg.d}], got {tuple(prefix.shape)}")
         prefix = prefix.contiguous()
         B, Tp, _ = prefix.shape
-        g = _ffi.cc_gen_cfg(_ffi.CC_GEN_BEAM if mode == "beam" else _ffi.CC_GEN_GREEDY, beam, entry_length,
-                            float(temperature), stop_token)
+        hist = None
+        if history is not None and len(history) > 0:
+            hist = (C.c_int32 * len(history))(*[int(t) for t in history])
+        g = _ffi.cc_gen_cfg(self._MODES[mode], beam, entry_length, float(temperature), stop_token,
+                            float(1.0 if top_p is None else top_p), int(top_k), float(repetition_penalty),
+                            int(desired_sentence_length), float(sentence_length_factor),
+                            0 if hist is None else len(hist), None if hist is None else C.addressof(hist),
+                            int(seed) & 0xFFFFFFFFFFFFFFFF)
         tokens = torch.empty(B, entry_length, device=prefix.device, dtype=torch.int32)
         lengths = torch.empty(B, device=prefix.device, dtype=torch.int32)
         scores = torch.empty(B, device=prefix.device, dtype=torch.float32)

@@ -150,7 +150,7 @@ class GPT2LM(EngineModule):
 
     @torch.no_grad()
     def generate_tokens(self, prefix: torch.Tensor, mode="greedy", beam=1, entry_length=67, temperature=1.0,
-                        stop_token=50256):
+                        stop_token=50256, **sampling):
         B, Tp, _ = prefix.shape
         eng = self._engine_for(B * (beam if mode == "beam" else 1), Tp + entry_length)
-        return eng.generate(prefix, mode, beam, entry_length, temperature, stop_token)
+        return eng.generate(prefix, mode, beam, entry_length, temperature, stop_token, **sampling)

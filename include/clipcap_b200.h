@@ -145,13 +145,30 @@ int cc_gpt2_logits(cc_gpt2* h, const void* embeds, int dtype, int B, int T, int 
 /* out[i,:] = wte[ids[i],:] (get_input_embeddings(), base.py:76,117) */
 int cc_gpt2_embed(cc_gpt2* h, const int32_t* ids, int n, void* out, int out_dtype, void* stream);
 
-enum cc_gen_mode { CC_GEN_GREEDY = 0, CC_GEN_BEAM = 1 };
+/* GREEDY / BEAM: generate_beam (clipcap/inference/base.py:55-132).
+ * NUCLEUS: generate_nucleus_sampling (clipcap/inference/nucleus_sampling.py:9-75) — top-k / top-p over softmax(logits/T),
+ *          the stop token is part of the returned tokens.
+ * SAMPLE:  generate_no_beam (clipcap/inference/no_beam.py:10-82) with clipcap/inference/utils.py:5-49 — repetition
+ *          penalty, temperature, top_k_top_p_filtering, "sentence length penalty", multinomial; the stop token ends the
+ *          caption without being returned.
+ * The two sampling modes draw from the same distribution as the reference with a Philox stream keyed by (seed, row,
+ * step); results are reproducible for a given seed but not bit-identical to torch.multinomial's generator. */
+enum cc_gen_mode { CC_GEN_GREEDY = 0, CC_GEN_BEAM = 1, CC_GEN_NUCLEUS = 2, CC_GEN_SAMPLE = 3 };
 typedef struct cc_gen_cfg {
   int32_t mode;
   int32_t beam;         /* beam_size (BEAM) */
   int32_t entry_length; /* tokens to generate (base.py:62) */
   float temperature;    /* <= 0 treated as 1 (base.py:83) */
-  int32_t stop_token;   /* tokenizer.encode(eos)[0] (base.py:66) */
+  int32_t stop_token;   /* tokenizer.encode(eos)[0] (base.py:66) / tokenizer.encode(".")[0] (nucleus_sampling.py:21) */
+  /* sampling modes only */
+  float top_p;                     /* nucleus_sampling.py:16 / no_beam.py:16 (no_beam: <= 0 disables) */
+  int32_t top_k;                   /* 0 = whole vocabulary */
+  float repetition_penalty;        /* SAMPLE: no_beam.py:20 (1.0 disables) */
+  int32_t desired_sentence_length; /* SAMPLE: no_beam.py:21 */
+  float sentence_length_factor;    /* SAMPLE: no_beam.py:22 */
+  int32_t n_history;               /* SAMPLE: number of text-prefix tokens that start every row's token history */
+  const int32_t* history;          /* SAMPLE: those tokens (HOST pointer, may be NULL when n_history == 0) */
+  uint64_t seed;
 } cc_gen_cfg;
 /* prefix: [B,Tp,d] input embeddings (mapper prefix, optionally followed by text-prefix embeddings, base.py:75-77).
  * tokens: [B,entry_length] int32 — best beam per row (base.py:126-128); lengths: [B] int32 = number of valid tokens
@@ -178,6 +195,11 @@ int cc_op_attention(const void* q, const void* k, const void* v, int64_t ld, voi
                     int hd, int causal, float scale, void* stream);
 int cc_op_decode_attention(const void* qkv, void* kcache, void* vcache, const int32_t* anc, void* o, int nseq, int H,
                            int t_max, int pos, float scale, void* stream);
+/* One sampling step (the token-selection kernel of the NUCLEUS / SAMPLE modes) on given logits [rows, V] fp32:
+ * tokens[row * entry_length + step] receives the draw; stopped / lengths [rows] int32 are updated; cfg->history is a
+ * DEVICE pointer here. Used by the distribution tests. */
+int cc_op_sample(const float* logits, int rows, int V, const cc_gen_cfg* cfg, int step, int32_t* tokens,
+                 int32_t* stopped, int32_t* lengths, void* stream);
 
 /* Live per-launch timing of the dominant kernel (the 128x256-tile tcgen05 GEMM): while enabled, every such launch that
  * is not inside a graph capture is bracketed by CUDA events on its own stream. cc_prof_read synchronises the device and

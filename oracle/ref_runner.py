@@ -123,6 +123,46 @@ def reference_generate_beam(model, embeds: torch.Tensor, beam_size: int, entry_l
     return [int(t) for t in out[0].split()] if out[0] else []
 
 
+def rank_cycle_pick(p: torch.Tensor, step: int) -> int:
+    """Deterministic stand-in for torch.multinomial used on both sides of the sampling parity tests: the token of rank
+    (step mod 3) among the kept (non-zero) probabilities, so the sequences are not just the arg-max path."""
+    p = p.reshape(-1)
+    nz = int((p > 0).sum())
+    r = step % max(1, min(3, nz))
+    return int(p.topk(r + 1).indices[r])
+
+
+def reference_generate_sampling(model, embeds: torch.Tensor, mode: str, entry_length: int, text_prefix_tokens=None,
+                                deterministic: bool = True, **kw):
+    """clipcap.inference.nucleus_sampling.generate_nucleus_sampling (mode='nucleus') or
+    clipcap.inference.no_beam.generate_no_beam (mode='sample') on one image, number_to_generate=1. The random draw
+    (torch.multinomial) is replaced by rank_cycle_pick when `deterministic`, and the distribution of every step is
+    captured. Returns (token ids as the reference returns them, i.e. text prefix first; per-step distributions [V])."""
+    import_reference()
+    import clipcap.inference.no_beam as NB
+    import clipcap.inference.nucleus_sampling as NS
+    captured = []
+    real = torch.multinomial
+
+    def fake_multinomial(p, num_samples=1, *a, **k):
+        captured.append(p.detach().reshape(-1).clone())
+        if deterministic:
+            return torch.tensor([rank_cycle_pick(p, len(captured) - 1)]).reshape(*p.shape[:-1], 1)
+        return real(p, num_samples, *a, **k)
+
+    torch.multinomial = fake_multinomial
+    try:
+        if mode == "nucleus":
+            out = NS.generate_nucleus_sampling(model, FakeTokenizer(), embeds, number_to_generate=1,
+                                               text_prefix_tokens=text_prefix_tokens, entry_length=entry_length, **kw)
+        else:
+            out = NB.generate_no_beam(model, FakeTokenizer(), embeds, number_to_generate=1,
+                                      text_prefix_tokens=text_prefix_tokens, entry_length=entry_length, **kw)
+    finally:
+        torch.multinomial = real
+    return ([int(t) for t in out[0].split()] if out[0] else []), captured
+
+
 def hf_clip_vision(vcfg, vit_w: Dict[str, torch.Tensor]):
     """transformers.CLIPVisionModelWithProjection(quick_gelu) loaded with OpenAI-named weights — the stand-in for the
     un-installed `clip` package. Exposes encode_image so the reference CLIPModel wrapper can hold it."""

@@ -238,6 +238,89 @@ def teacher_forced_logits(w: Weights, cfg: Gpt2Cfg, prefix: torch.Tensor, tokens
     return full[:, Tp - 1:]
 
 
+# ------------------------------------------------------------------------------------------------ sampling decode
+def nucleus_distribution(logits: torch.Tensor, top_p: Optional[float] = 0.8, top_k: int = 0,
+                         temperature: float = 1.0) -> torch.Tensor:
+    """The distribution generate_nucleus_sampling draws from (clipcap/inference/nucleus_sampling.py:37-54) for last
+    logits [B, V]: softmax(logits / T) -> topk(top_k or V) -> cumsum -> searchsorted(top_p) clipped to top_k - 1 ->
+    keep cumulative <= cutoff -> renormalise -> scatter back."""
+    logits = logits.float() / (temperature if temperature > 0 else 1.0)
+    if top_k == 0:
+        top_k = logits.shape[-1]
+    if top_p is None:
+        top_p = 1.0
+    p, idx_sorted = logits.softmax(-1).topk(top_k, dim=-1)
+    cum = p.cumsum(-1)
+    idx = torch.searchsorted(cum, top_p + torch.zeros(len(p), 1)).clip(max=top_k - 1).reshape(-1)
+    cutoffs = cum[torch.arange(len(cum)), idx]
+    censored = (cum <= cutoffs[:, None]) * p
+    renorm = censored / censored.sum(-1, keepdim=True)
+    final = torch.zeros_like(logits)
+    final[torch.arange(len(p)).unsqueeze(1).repeat(1, top_k), idx_sorted] = renorm
+    return final
+
+
+def no_beam_distribution(logits: torch.Tensor, history: Optional[torch.Tensor], top_p: float = 0.9, top_k: float = 0.0,
+                         temperature: float = 1.0, repetition_penalty: float = 1.2, stop_token: int = 13,
+                         desired_sentence_length: int = 50, sentence_length_factor: float = 1.0) -> torch.Tensor:
+    """The distribution generate_no_beam draws from (clipcap/inference/no_beam.py:37-62 with utils.py:5-49) for ONE
+    row of last logits [V]; `history` = the 1-D `tokens` seen so far (text prefix + generated) or None."""
+    logits = logits.float().clone()
+    if repetition_penalty != 1.0 and history is not None:            # no_beam.py:41-44, utils.py:34-38
+        tok = logits.gather(-1, history)
+        tok = torch.where(tok < 0, tok * repetition_penalty, tok / repetition_penalty)
+        logits.scatter_(-1, history, tok)
+    logits = logits / (temperature if temperature > 0 else 1.0)      # no_beam.py:47
+    k = min(int(top_k), logits.size(-1))                             # utils.py:15-20
+    if k > 0:
+        logits[logits < torch.topk(logits, k)[0][..., -1, None]] = -float("inf")
+    if top_p > 0.0:                                                  # utils.py:22-31
+        sl, si = torch.sort(logits, descending=True)
+        cum = torch.cumsum(sl.softmax(-1), dim=-1)
+        rm = cum > top_p
+        rm[..., 1:] = rm[..., :-1].clone()
+        rm[..., 0] = 0
+        logits[si[rm]] = -float("inf")
+    if history is not None:                                          # no_beam.py:51-56, utils.py:40-49
+        penalty = (history.shape[0] / desired_sentence_length) * sentence_length_factor
+        tok = logits.gather(-1, history)
+        tok = torch.where(tok == stop_token, tok * penalty, tok)
+        logits.scatter_(-1, history, tok)
+    return logits.softmax(-1)
+
+
+def generate_sampling(w: Weights, cfg: Gpt2Cfg, embeds: torch.Tensor, mode: str, pick, entry_length: int = 67,
+                      text_prefix_tokens: Optional[torch.Tensor] = None, stop_token: int = 13, **kw) -> List[int]:
+    """The loops of generate_nucleus_sampling (mode='nucleus', nucleus_sampling.py:26-73) and generate_no_beam
+    (mode='sample', no_beam.py:26-80) for one image and number_to_generate=1, with the random draw abstracted as
+    `pick(probabilities [V]) -> token` (torch.multinomial in the reference; argmax in the deterministic tests).
+    Returns the generated tokens WITHOUT the text prefix the reference prepends."""
+    assert embeds.shape[0] == 1
+    wte = w["transformer.wte.weight"]
+    hist = None if text_prefix_tokens is None else text_prefix_tokens.reshape(-1).clone()
+    if text_prefix_tokens is not None:
+        embeds = torch.cat((embeds, wte[text_prefix_tokens.reshape(1, -1)]), dim=1)
+    out: List[int] = []
+    for _ in range(entry_length):
+        raw = gpt2_logits(w, embeds, cfg, last_only=True)[:, -1, :]
+        if mode == "nucleus":
+            probs = nucleus_distribution(raw, kw.get("top_p", 0.8), kw.get("top_k", 0), kw.get("temperature", 1.0))[0]
+        else:
+            probs = no_beam_distribution(raw[0], hist, kw.get("top_p", 0.9), kw.get("top_k", 0.0),
+                                         kw.get("temperature", 1.0), kw.get("repetition_penalty", 1.2), stop_token,
+                                         kw.get("desired_sentence_length", 50), kw.get("sentence_length_factor", 1.0))
+        tok = int(pick(probs))
+        if mode == "sample" and tok == stop_token:                    # no_beam.py:67-68: stop token not appended
+            break
+        out.append(tok)
+        t = torch.tensor([tok])
+        hist = t if hist is None else torch.cat((hist, t))
+        embeds = torch.cat((embeds, wte[t].view(1, 1, -1)), dim=1)
+        if mode == "nucleus" and tok == stop_token:                   # nucleus_sampling.py:67-68: appended, then stop
+            break
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ whole path
 def caption_greedy(vit_w: Weights, map_w: Weights, lm_w: Weights, vcfg: VitCfg, mcfg: MapperCfg, gcfg: Gpt2Cfg,
                    pixels: torch.Tensor, entry_length: int, stop_token: int, normalize: bool = False):

@@ -26,6 +26,14 @@ CASES = {
     "tiny_b": ("tiny:192:3:3:517:48", R.Gpt2Cfg(d=192, L=3, H=3, V=517, n_pos=48),
                R.MapperCfg(E=72, d=192, P=2, K=4, H=2, L=1)),
 }
+SAMPLING_CASES = [  # (mode, kwargs of the reference function)
+    ("nucleus", dict(top_p=0.8, top_k=0, temperature=0.9)),
+    ("nucleus", dict(top_p=0.5, top_k=7, temperature=1.0)),
+    ("nucleus", dict(top_p=0.3, top_k=1, temperature=1.0)),
+    ("sample", dict(top_p=0.9, top_k=0.0, temperature=1.0, repetition_penalty=1.2)),
+    ("sample", dict(top_p=0.0, top_k=5, temperature=0.7, repetition_penalty=1.5)),
+    ("sample", dict(top_p=0.6, top_k=1, temperature=1.0, repetition_penalty=5.0)),
+]
 VIT = R.VitCfg(image_size=28, patch=14, width=128, layers=2, heads=2, mlp_dim=512, out_dim=64)
 ENTRY = 9
 
@@ -53,6 +61,14 @@ def main():
                     for i, r in enumerate(rows):
                         arr[i, :len(r)] = r
                     out[f"beam{beam}_t{temp}"] = arr
+            # sampling loops (nucleus_sampling.py / no_beam.py) with torch.multinomial replaced by RR.rank_cycle_pick
+            tp = torch.tensor([[5, 17, 5]])
+            for ci, (mode, kw) in enumerate(SAMPLING_CASES):
+                for ti, tpt in enumerate((None, tp)):
+                    toks, dists = RR.reference_generate_sampling(model, prefix[:1], mode, ENTRY, text_prefix_tokens=tpt, **kw)
+                    out[f"samp{ci}_tp{ti}_tokens"] = np.asarray(toks, dtype=np.int64)
+                    out[f"samp{ci}_tp{ti}_nkept"] = np.asarray([int((d > 0).sum()) for d in dists], dtype=np.int64)
+                    out[f"samp{ci}_tp{ti}_pmax"] = np.asarray([float(d.max()) for d in dists], dtype=np.float64)
             # ClipCapModel.forward (teacher-forced logits, model.py:43-58)
             tokens = torch.randint(0, gcfg.V, (B, 6), generator=torch.Generator().manual_seed(3))
             mask = torch.ones(B, 6, dtype=torch.bool)

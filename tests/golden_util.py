@@ -16,6 +16,14 @@ LM_CASES = {
     "tiny_b": ("tiny:192:3:3:517:48", R.Gpt2Cfg(d=192, L=3, H=3, V=517, n_pos=48),
                R.MapperCfg(E=72, d=192, P=2, K=4, H=2, L=1)),
 }
+SAMPLING_CASES = [  # must match tests/golden/make_golden.py
+    ("nucleus", dict(top_p=0.8, top_k=0, temperature=0.9)),
+    ("nucleus", dict(top_p=0.5, top_k=7, temperature=1.0)),
+    ("nucleus", dict(top_p=0.3, top_k=1, temperature=1.0)),
+    ("sample", dict(top_p=0.9, top_k=0.0, temperature=1.0, repetition_penalty=1.2)),
+    ("sample", dict(top_p=0.0, top_k=5, temperature=0.7, repetition_penalty=1.5)),
+    ("sample", dict(top_p=0.6, top_k=1, temperature=1.0, repetition_penalty=5.0)),
+]
 VIT_CASE = R.VitCfg(image_size=28, patch=14, width=128, layers=2, heads=2, mlp_dim=512, out_dim=64)
 ENTRY = 9
 

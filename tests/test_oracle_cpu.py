@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from conftest import rel_err
-from golden_util import ENTRY, LM_CASES, golden_rows, load_lm_case, load_vit_case
+from golden_util import ENTRY, LM_CASES, SAMPLING_CASES, golden_rows, load_lm_case, load_vit_case
 from oracle import ref_runner as RR
 from oracle import restate as R
 from oracle import synth
@@ -44,6 +44,30 @@ def test_model_forward_matches_golden(name):
     prefix = R.mapper_forward(map_w, emb, mcfg)
     x = torch.cat((prefix, lm_w["transformer.wte.weight"][tokens]), dim=1)
     assert rel_err(R.gpt2_logits(lm_w, x, gcfg), torch.from_numpy(g["fwd_logits"])) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", list(LM_CASES))
+@pytest.mark.parametrize("ci", range(len(SAMPLING_CASES)))
+@pytest.mark.parametrize("ti", [0, 1])
+def test_sampling_loops_match_golden(name, ci, ti):
+    """generate_nucleus_sampling / generate_no_beam restated (oracle) vs the reference's own loops frozen in the golden
+    files, with the random draw replaced by the same deterministic pick on both sides; per step also the size of the
+    kept set and the largest kept probability."""
+    spec, gcfg, mcfg, map_w, lm_w, g = load_lm_case(name)
+    mode, kw = SAMPLING_CASES[ci]
+    tp = torch.tensor([[5, 17, 5]]) if ti else None
+    prefix = torch.from_numpy(g["prefix"])[:1]
+    seen = []
+
+    def pick(p):
+        seen.append(p.clone())
+        return RR.rank_cycle_pick(p, len(seen) - 1)
+
+    got = R.generate_sampling(lm_w, gcfg, prefix, mode, pick, ENTRY, tp, 13, **kw)
+    head = [] if tp is None else tp.reshape(-1).tolist()
+    assert head + got == g[f"samp{ci}_tp{ti}_tokens"].tolist()
+    assert [int((d > 0).sum()) for d in seen] == g[f"samp{ci}_tp{ti}_nkept"].tolist()
+    np.testing.assert_allclose([float(d.max()) for d in seen], g[f"samp{ci}_tp{ti}_pmax"], rtol=1e-4)
 
 
 def test_vit_matches_golden():
@@ -103,6 +127,33 @@ def test_restatement_vs_live_reference(windowed):
                 want = RR.reference_generate_beam(model, ref_prefix[i:i + 1], beam, 7, 1.0, stop_token=1002)
                 got, _, _ = R.generate_beam(lm_w, gcfg, ref_prefix[i:i + 1], beam, 7, 1.0, 1002)
                 assert got == want
+
+
+@needs_ref
+@pytest.mark.parametrize("ci", range(len(SAMPLING_CASES)))
+def test_sampling_restatement_vs_live_reference(ci):
+    """Per-step distributions of the restated sampling loops equal the live reference's (captured at torch.multinomial)."""
+    gcfg = R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64)
+    mcfg = R.MapperCfg(E=64, d=128, P=3, K=5, H=2, L=2)
+    map_w, lm_w = synth.mapper_weights(mcfg, seed=41), synth.gpt2_weights(gcfg, seed=42, wte_std=0.1)
+    model = RR.build_reference_model("tiny:128:2:2:1003:64", 64, 5, 3, 2, 2, map_w, lm_w)
+    mode, kw = SAMPLING_CASES[ci]
+    tp = torch.tensor([[9, 3, 9, 44]])
+    with torch.no_grad():
+        prefix = model.transformer_mapper(synth.embeddings(1, 64, seed=43))
+        want, dists = RR.reference_generate_sampling(model, prefix, mode, 7, text_prefix_tokens=tp, **kw)
+    seen = []
+
+    def pick(p):
+        seen.append(p.clone())
+        return RR.rank_cycle_pick(p, len(seen) - 1)
+
+    got = R.generate_sampling(lm_w, gcfg, prefix, mode, pick, 7, tp, 13, **kw)
+    assert tp.reshape(-1).tolist() + got == want
+    assert len(seen) == len(dists)
+    for a, b in zip(seen, dists):
+        assert torch.equal(a > 0, b > 0)
+        assert rel_err(a, b) < 1e-4
 
 
 @needs_ref
