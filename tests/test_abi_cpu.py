@@ -31,7 +31,8 @@ def test_version_and_struct_layout():
     assert C.sizeof(_ffi.cc_vit_cfg) == 32
     assert C.sizeof(_ffi.cc_mapper_cfg) == 40
     assert C.sizeof(_ffi.cc_gpt2_cfg) == 24
-    assert C.sizeof(_ffi.cc_gen_cfg) == 20
+    assert C.sizeof(_ffi.cc_gen_cfg) == 64  # 11 x 4-byte fields, padding, history pointer, 64-bit seed
+    assert _ffi.cc_gen_cfg.history.offset == 48 and _ffi.cc_gen_cfg.seed.offset == 56
 
 
 def test_null_arguments_are_rejected_without_a_device():
