@@ -203,7 +203,7 @@ def run_b200(args):
     from clipcap_b200 import _ffi
     from clipcap_b200.encoders.clip import CLIPModel, ViTImageTower
     from clipcap_b200.encoders.config import EncoderConfig
-    from clipcap_b200.inference.base import generate_greedy_tokens
+    from clipcap_b200.distributed import caption_step
     from clipcap_b200.model import ClipCapModelPrefixOnly, Config
     from oracle import synth  # seeded synthetic weights / pixels only (not the checker)
     _ffi.lib()
@@ -228,12 +228,9 @@ def run_b200(args):
     len_host = torch.empty(B, dtype=torch.int32).pin_memory()
 
     def step(pixels):
-        emb = encode_fn(pixels)                       # cc_vit_forward
-        prefix = model.transformer_mapper(emb)        # cc_mapper_forward
-        if world > 1:                                 # prefix all-gather over NVLink
-            dist.all_gather_into_tensor(prefix_all, prefix)
-            prefix = prefix_all[rank * B:(rank + 1) * B]
-        return generate_greedy_tokens(model, prefix, ENTRY_LENGTH, STOP_TOKEN)  # cc_generate
+        # cc_vit_forward -> cc_mapper_forward -> [prefix all-gather over NVLink, SURVEY §8e] -> cc_generate
+        toks, lens, _ = caption_step(encode_fn, model, pixels, ENTRY_LENGTH, STOP_TOKEN, prefix_all)
+        return toks, lens, None
 
     def step_e2e():
         px = px_host.to(dev, non_blocking=True)

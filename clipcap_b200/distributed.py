@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing of the captioning path: one process per GPU, the batch is split contiguously by rank,
+every rank encodes + maps its own images, the prefix embeddings are all-gathered so every rank holds the full
+[B, K, d] tensor (the only exchange step of the path), decode stays data-parallel on the rank that owns the image, and
+the token ids are gathered at the end. torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the transport; the
+collectives are issued on the current stream, nothing here synchronises the host.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of n units owned by `rank`: the first n % world ranks get one extra unit."""
+    if world <= 0 or not (0 <= rank < world) or n < 0:
+        raise ValueError(f"bad shard request n={n} rank={rank} world={world}")
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_gather_prefix(prefix_local: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[B_local, K, d] on every rank -> [world * B_local, K, d] on every rank, rank r's block at rows r*B_local.. .
+    Equal shard sizes (weak scaling: B per GPU fixed); a single in-place all-gather (ncclAllGather over NVLink)."""
+    if not dist.is_available() or not dist.is_initialized():
+        return prefix_local
+    world = dist.get_world_size(group)
+    if world == 1:
+        return prefix_local
+    prefix_local = prefix_local.contiguous()
+    shape = (world * prefix_local.shape[0],) + tuple(prefix_local.shape[1:])
+    if out is None:
+        out = torch.empty(shape, dtype=prefix_local.dtype, device=prefix_local.device)
+    elif tuple(out.shape) != shape or out.dtype != prefix_local.dtype:
+        raise ValueError(f"all_gather_prefix: out must be {shape} {prefix_local.dtype}, got {tuple(out.shape)} {out.dtype}")
+    dist.all_gather_into_tensor(out, prefix_local, group=group)
+    return out
+
+
+def gather_tokens(tokens_local: torch.Tensor, lengths_local: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
+    """Token ids [B_local, EL] + lengths [B_local] of every rank -> ([world*B_local, EL], [world*B_local]) on every rank."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return tokens_local, lengths_local
+    world = dist.get_world_size(group)
+    toks = torch.empty((world * tokens_local.shape[0], tokens_local.shape[1]), dtype=tokens_local.dtype,
+                       device=tokens_local.device)
+    lens = torch.empty((world * lengths_local.shape[0],), dtype=lengths_local.dtype, device=lengths_local.device)
+    dist.all_gather_into_tensor(toks, tokens_local.contiguous(), group=group)
+    dist.all_gather_into_tensor(lens, lengths_local.contiguous(), group=group)
+    return toks, lens
+
+
+def caption_step(encode_fn, model, pixels_local: torch.Tensor, entry_length: int, stop_token: int,
+                 prefix_all: Optional[torch.Tensor] = None, group: Optional[dist.ProcessGroup] = None):
+    """One pass of the hot path on this rank's shard: ViT -> mapper -> prefix all-gather -> greedy decode of the local
+    rows. Returns (tokens, lengths, prefix_all)."""
+    from clipcap_b200.inference.base import generate_greedy_tokens
+    emb = encode_fn(pixels_local)
+    prefix = model.transformer_mapper(emb)
+    gathered = all_gather_prefix(prefix, group, prefix_all)
+    if gathered is not prefix:
+        rank = dist.get_rank(group)
+        b = prefix.shape[0]
+        prefix = gathered[rank * b:(rank + 1) * b]
+    tokens, lengths, _ = generate_greedy_tokens(model, prefix, entry_length, stop_token)
+    return tokens, lengths, gathered
