@@ -21,8 +21,8 @@ int cc_op_gemm(const void* a, int64_t lda, const void* w, const float* bias, voi
   using namespace cc;
   CC_REQUIRE(a != nullptr && w != nullptr && out != nullptr, CC_EINVAL, "cc_op_gemm: null argument");
   CC_TRY(check_device_sm100());
-  CC_REQUIRE(bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 256, CC_EINVAL,
-             "cc_op_gemm: BLOCK_N %d not in {0,32,64,128,256}", bn);
+  CC_REQUIRE(bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 256 || bn == 512, CC_EINVAL,
+             "cc_op_gemm: BLOCK_N %d not in {0,32,64,128,256} or 512 (256 x 256 CTA-pair tile)", bn);
   GemmPlan p;
   CC_TRY(gemm_plan(&p, static_cast<const __half*>(a), lda, M, static_cast<const __half*>(w), N, K, epi, bias, out, ldc));
   p.force_bn = bn;

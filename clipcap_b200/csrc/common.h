@@ -68,18 +68,34 @@ struct Arena {  // owns every allocation of one engine; freed in one go
 // CLIPCAP_B200_NO_PDL=1.
 bool pdl_enabled();
 template <class... KArgs, class... Args>
-cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+cudaError_t launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,
+                               Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (cluster_x > 1) {  // thread-block cluster (CTA pairs of the cta_group::2 GEMM)
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  return launch_pdl_cluster(kern, grid, block, smem, s, 1, args...);
 }
 
 int check_device_sm100();  // CC_EARCH unless the current device is compute capability 10.x
@@ -115,7 +131,7 @@ struct GemmPlan {
   const float* bias = nullptr;
   void* out = nullptr;  // half* / float* / unsigned long long* by epilogue
   int64_t ldc = 0;
-  int force_bn = 0;  // 0 = heuristic
+  int force_bn = 0;  // 0 = heuristic; 512 = the 256 x 256 CTA-pair tile (cta_group::2)
   int splits = 1;      // EPI_PARTIAL_F32: split-K factor and the row pitch of one split inside `out`
   int split_rows = 0;
   int heads_S = 0, heads_H = 0;  // EPI_F16_HEADS: tokens per image, heads (N = 3 * H * 64)

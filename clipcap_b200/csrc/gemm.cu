@@ -17,6 +17,8 @@
 //               and the fused argmax use direct stores / atomics. `tmem_empty` hands the accumulator back as soon as
 //               it has been read, so the epilogue of tile i overlaps the main loop of tile i+1.
 // Tiles are walked n-fastest so the A row-panel and the whole W stay L2 resident.
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -30,12 +32,15 @@ constexpr int GEMM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int EPI_WARPS = 8;
 constexpr int STG_WARP_BYTES = 4096;  // per epilogue warp: two 32-row x 64-byte staging buffers
 
-template <int BN>
+// CG = 1: one CTA computes a 128 x BN tile. CG = 2 (cta_group::2): a pair of CTAs on neighbouring SMs computes a 256 x BN
+// tile; each CTA stages its own 128 rows of A and HALF of the W tile (BN/2 rows), the MMA reads the other half from the
+// peer's shared memory, so per SM both the L2->SM operand traffic and the shared-memory reads drop by a third.
+template <int BN, int CG = 1>
 struct GemmCfg {
   static constexpr int kStageA = BM * BK * 2;
-  static constexpr int kStageB = BN * BK * 2;
+  static constexpr int kStageB = (BN / CG) * BK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = BN >= 256 ? 4 : 6;
+  static constexpr int kStages = (BN >= 256 && CG == 1) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers (power of two >= 64)
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kStaging = EPI_WARPS * STG_WARP_BYTES;
@@ -98,11 +103,16 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_c, GemmArgs args) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
+  constexpr int TM = BM * CG;  // rows of one work item (tile of the CTA / CTA pair)
+  const int cta_rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = cta_rank == 0;
+  const int unit = CG == 2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);       // CTA or pair index
+  const int n_units = CG == 2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = smem_base + Cfg::kStages * Cfg::kStage;  // 1024-byte aligned
@@ -118,7 +128,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int tiles_m = (args.M + BM - 1) / BM;
+  const int tiles_m = (args.M + TM - 1) / TM;
   const int tiles_n = (args.N + BN - 1) / BN;
   const int num_work = tiles_m * tiles_n * args.splits;  // work item = (tile, k-split), split fastest
   const int num_kb = (args.K + BK - 1) / BK;
@@ -128,21 +138,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_b);
     if constexpr (EpiTraits<EPI>::kTma) tma_prefetch_desc(&map_c);
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 1);  // CG == 2: the leader's barrier; its expect_tx covers both CTAs' tiles
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4 * Cfg::kSplit);  // one arrive per active epilogue warp
+      mbar_init(tempty_bar(s), 4 * Cfg::kSplit * CG);  // one arrive per active epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // Everything above touched only this CTA's shared / tensor memory. Weights (operand B) are never written by a kernel
@@ -154,8 +170,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int pre = 0;  // k-blocks of the first work item whose B tile is already in flight
-      if (static_cast<int>(blockIdx.x) < num_work) {
-        const int w = blockIdx.x;
+      if (CG == 1 && unit < num_work) {
+        const int w = unit;
         const int tile = w / args.splits, split = w - tile * args.splits;
         const int n0 = (tile % tiles_n) * BN;
         const int kb0 = split * args.kb_per_split;
@@ -169,16 +185,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = unit; w < num_work; w += n_units) {
         const int tile = w / args.splits, split = w - tile * args.splits;
-        const int m0 = args.row_base + (tile / tiles_n) * BM;
-        const int n0 = (tile % tiles_n) * BN;
+        const int m0 = args.row_base + (tile / tiles_n) * TM + cta_rank * BM;
+        const int n0 = (tile % tiles_n) * BN + cta_rank * (BN / CG);  // CG == 2: this CTA stages its half of the W tile
         const int kb0 = split * args.kb_per_split;
         const int kb1 = min(num_kb, kb0 + args.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           const uint32_t sa = smem_base + stage * Cfg::kStage;
           const uint32_t sb = sa + Cfg::kStageA;
-          if (pre > 0) {  // stage is fresh and its B tile + expect_tx were issued above
+          if constexpr (CG == 2) {
+            // Both CTAs' tiles complete (complete_tx) on the LEADER's full barrier, where the MMA is issued; only the
+            // leader arrives, with the byte count of both. (A per-stage remote mbarrier.arrive.release.cluster from the
+            // peer costs ~1400 cycles and throttles the whole pipeline: measured.)
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t lbar = mapa_cluster(full_bar(stage), 0);
+            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStage);
+            tma_load_2d_cg2(&map_a, lbar, sa, kb * BK, m0);
+            tma_load_2d_cg2(&map_b, lbar, sb, kb * BK, n0);
+          } else if (pre > 0) {  // stage is fresh and its B tile + expect_tx were issued above
             --pre;
             tma_load_2d(&map_a, full_bar(stage), sa, kb * BK, m0);
           } else {
@@ -197,14 +222,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       pdl_wait();
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------ MMA issuer (CG == 2: the leader CTA issues for the pair)
     pdl_wait();
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_f16(TM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      for (int w = unit; w < num_work; w += n_units, ++it) {
         const int as = it & 1;
         const int split = w % args.splits;
         const int nkb = min(num_kb, (split + 1) * args.kb_per_split) - split * args.kb_per_split;
@@ -221,15 +246,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-            umma_f16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2) umma_f16_ss_cg2(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));
+          if constexpr (CG == 2) umma_commit_cg2_mc(empty_bar(stage), 0x3);  // frees the stage in both CTAs
+          else umma_commit(empty_bar(stage));
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(as));
+        if constexpr (CG == 2) umma_commit_cg2_mc(tfull_bar(as), 0x3);  // both CTAs' epilogues read their own TMEM half
+        else umma_commit(tfull_bar(as));
       }
     }
   } else if ((warp - 2) < 4 * Cfg::kSplit) {
@@ -253,10 +281,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t row_off = lane * 64;
       const uint32_t sw = (lane >> 1) & 3;
       uint32_t chunk_no = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      for (int w = unit; w < num_work; w += n_units, ++it) {
         const int as = it & 1;
         const int tile = w / args.splits, split = w - tile * args.splits;
-        const int m0 = args.row_base + (tile / tiles_n) * BM;
+        const int m0 = args.row_base + (tile / tiles_n) * TM + cta_rank * BM;
         const int n0 = (tile % tiles_n) * BN;
         const bool rows_live = (m0 + quad * 32) < args.row_base + args.M;  // warp-uniform
         const int out_row = split * args.split_rows + m0 + quad * 32;
@@ -277,7 +305,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // accumulator fully read (last load has landed): hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_remote(mapa_cluster(tempty_bar(as), 0));
+              else mbar_arrive(tempty_bar(as));
+            }
           }
           const int nc = n0 + col_base + c * CH;
           if (nc >= args.N || !rows_live) continue;  // warp-uniform
@@ -359,9 +390,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else {
       // fp32 logits (arbitrary ldc) and fused argmax: direct global stores / atomics, thread == output row
       constexpr int CH = WCOLS < 32 ? WCOLS : 32;
-      for (int tile = blockIdx.x; tile < num_work; tile += gridDim.x, ++it) {  // splits == 1 here
+      for (int tile = unit; tile < num_work; tile += n_units, ++it) {  // splits == 1 here
         const int as = it & 1;
-        const int m0 = args.row_base + (tile / tiles_n) * BM;
+        const int m0 = args.row_base + (tile / tiles_n) * TM + cta_rank * BM;
         const int n0 = (tile % tiles_n) * BN;
         const int m = m0 + row_in_tile;
         const bool row_ok = m < args.row_base + args.M;
@@ -424,7 +455,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // accumulator fully read: hand the TMEM buffer back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_remote(mapa_cluster(tempty_bar(as), 0));
+          else mbar_arrive(tempty_bar(as));
+        }
 
         if constexpr (EPI == EPI_ARGMAX) {
           if (row_ok && best_n != 0x7fffffff) {
@@ -439,10 +473,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if ((warp - 2) >= 4 * Cfg::kSplit) pdl_wait();  // idle epilogue warps (narrow tiles)
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the pair's MMAs can still touch it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -511,39 +547,62 @@ int encode_out_map(CUtensorMap* m, void* base, bool f32, uint64_t rows, uint64_t
   return CC_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 int launch(const GemmPlan& p, int bn_idx, int M, cudaStream_t s, int row0) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   static bool configured = false;
-  auto kern = gemm_tn_kernel<BN, EPI>;
+  auto kern = gemm_tn_kernel<BN, EPI, CG>;
   if (!configured) {
     CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     configured = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * ((EPI == EPI_PARTIAL_F32) ? p.splits : 1);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
   const int num_kb = (p.K + BK - 1) / BK;
   const int splits = (EPI == EPI_PARTIAL_F32) ? p.splits : 1;
   const int kb_per = (num_kb + splits - 1) / splits;
   GemmArgs a{M,      p.N,    p.K,          p.bias,    p.out, static_cast<long long>(p.ldc),
              splits, kb_per, p.split_rows, p.heads_S, p.heads_H, row0};
-  CC_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmem, s, p.map_a, p.map_b[bn_idx], p.map_c, a));
+  const int tiles = ((M + BM * CG - 1) / (BM * CG)) * ((p.N + BN - 1) / BN) * splits;
+  int units = num_sms() / CG;  // persistent: one CTA (pair) per SM (pair)
+  if (CG == 2) {
+    // not every SM pair can host a cluster (GPC shapes): size the persistent grid to what is co-resident
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(num_sms());
+      qc.blockDim = dim3(GEMM_THREADS);
+      qc.dynamicSmemBytes = Cfg::kSmem;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa;
+      qc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) != cudaSuccess || n <= 0) n = num_sms() / 2;
+      max_clusters = n;
+      if (getenv("CLIPCAP_B200_VERBOSE")) fprintf(stderr, "clipcap_b200: %d co-resident CTA pairs\n", n);
+    }
+    if (units > max_clusters) units = max_clusters;
+  }
+  const int grid = (tiles < units ? tiles : units) * CG;
+  CC_CUDA(launch_pdl_cluster(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmem, s, CG, p.map_a, p.map_b[bn_idx], p.map_c, a));
   return CC_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_epi(const GemmPlan& p, int bn_idx, int M, cudaStream_t s, int row0) {
   switch (p.epi) {
-    case EPI_F16_NONE: return launch<BN, EPI_F16_NONE>(p, bn_idx, M, s, row0);
-    case EPI_F16_RELU: return launch<BN, EPI_F16_RELU>(p, bn_idx, M, s, row0);
-    case EPI_F16_QUICKGELU: return launch<BN, EPI_F16_QUICKGELU>(p, bn_idx, M, s, row0);
-    case EPI_F16_GELU_NEW: return launch<BN, EPI_F16_GELU_NEW>(p, bn_idx, M, s, row0);
-    case EPI_F16_TANH: return launch<BN, EPI_F16_TANH>(p, bn_idx, M, s, row0);
-    case EPI_F32: return launch<BN, EPI_F32>(p, bn_idx, M, s, row0);
-    case EPI_RESID_F32: return launch<BN, EPI_RESID_F32>(p, bn_idx, M, s, row0);
-    case EPI_ARGMAX: return launch<BN, EPI_ARGMAX>(p, bn_idx, M, s, row0);
-    case EPI_PARTIAL_F32: return launch<BN, EPI_PARTIAL_F32>(p, bn_idx, M, s, row0);
-    case EPI_F16_HEADS: return launch<BN, EPI_F16_HEADS>(p, bn_idx, M, s, row0);
+    case EPI_F16_NONE: return launch<BN, EPI_F16_NONE, CG>(p, bn_idx, M, s, row0);
+    case EPI_F16_RELU: return launch<BN, EPI_F16_RELU, CG>(p, bn_idx, M, s, row0);
+    case EPI_F16_QUICKGELU: return launch<BN, EPI_F16_QUICKGELU, CG>(p, bn_idx, M, s, row0);
+    case EPI_F16_GELU_NEW: return launch<BN, EPI_F16_GELU_NEW, CG>(p, bn_idx, M, s, row0);
+    case EPI_F16_TANH: return launch<BN, EPI_F16_TANH, CG>(p, bn_idx, M, s, row0);
+    case EPI_F32: return launch<BN, EPI_F32, CG>(p, bn_idx, M, s, row0);
+    case EPI_RESID_F32: return launch<BN, EPI_RESID_F32, CG>(p, bn_idx, M, s, row0);
+    case EPI_ARGMAX: return launch<BN, EPI_ARGMAX, CG>(p, bn_idx, M, s, row0);
+    case EPI_PARTIAL_F32: return launch<BN, EPI_PARTIAL_F32, CG>(p, bn_idx, M, s, row0);
+    case EPI_F16_HEADS: return launch<BN, EPI_F16_HEADS, CG>(p, bn_idx, M, s, row0);
   }
   set_error("unknown GEMM epilogue %d", p.epi);
   return CC_EINVAL;
@@ -552,6 +611,13 @@ int launch_epi(const GemmPlan& p, int bn_idx, int M, cudaStream_t s, int row0) {
 }  // namespace
 
 namespace {
+bool two_cta_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CLIPCAP_B200_NO_2CTA");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  return on;
+}
 // Rough cycle estimate of one persistent CTA's share of the problem: per work item the slower of operand ingest
 // (~40 B/clk/SM from L2) and the tensor pipe (128 x BN x 16 MMA = BN/8... 8192 FLOP/clk/SM), plus a fixed fill/drain
 // cost; split-K adds the partial-sum store and the consumer's re-read.
@@ -723,7 +789,7 @@ void gemm_prof_read(double* ms, double* flops, long long* n) {
   *n = 0;
   cudaDeviceSynchronize();
   for (auto& r : g_prof) {
-    if (r.bn != 256) continue;
+    if (r.bn != 256 && r.bn != 512) continue;
     float t = 0.f;
     if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) continue;
     *ms += t;
@@ -736,7 +802,11 @@ int gemm_run(const GemmPlan& p, int M, cudaStream_t s, int row0) {
   CC_REQUIRE(M > 0 && row0 >= 0 && row0 + M <= p.max_rows, CC_ESHAPE, "gemm_run: rows %d..%d outside plan (max %d)", row0,
              row0 + M, p.max_rows);
   CC_REQUIRE(row0 % 32 == 0, CC_ESHAPE, "gemm_run: row group must start at a multiple of 32 (got %d)", row0);
-  const int bn = p.force_bn ? p.force_bn : gemm_pick_bn(M, p.N, p.K);
+  int bn = p.force_bn ? p.force_bn : gemm_pick_bn(M, p.N, p.K);
+  // Big problems take the 256 x 256 CTA-pair tile (cta_group::2) when there is at least one such tile per SM pair.
+  if (p.force_bn == 0 && bn == 256 && p.epi != EPI_PARTIAL_F32 && two_cta_enabled() &&
+      ((M + 255) / 256) * ((p.N + 255) / 256) >= num_sms() / 2)
+    bn = 512;
   if (g_prof_on) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(s, &cs);
@@ -759,10 +829,11 @@ int gemm_run(const GemmPlan& p, int M, cudaStream_t s, int row0) {
 namespace {
 int gemm_dispatch(const GemmPlan& p, int bn, int M, cudaStream_t s, int row0) {
   switch (bn) {
-    case 32: return launch_epi<32>(p, 0, M, s, row0);
-    case 64: return launch_epi<64>(p, 1, M, s, row0);
-    case 128: return launch_epi<128>(p, 2, M, s, row0);
-    case 256: return launch_epi<256>(p, 3, M, s, row0);
+    case 32: return launch_epi<32, 1>(p, 0, M, s, row0);
+    case 64: return launch_epi<64, 1>(p, 1, M, s, row0);
+    case 128: return launch_epi<128, 1>(p, 2, M, s, row0);
+    case 256: return launch_epi<256, 1>(p, 3, M, s, row0);
+    case 512: return launch_epi<256, 2>(p, 2, M, s, row0);  // CTA pair: each CTA stages 128 rows of the 256-row W tile
   }
   set_error("gemm_run: unsupported BLOCK_N %d", bn);
   return CC_EINVAL;

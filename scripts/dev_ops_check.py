@@ -20,10 +20,10 @@ def rel(a, b): return ((a.float() - b.float()).abs().max() / b.float().abs().max
 for (M, N, K) in [(128, 128, 64), (256, 3072, 1024), (300, 1000, 520), (1, 50257, 768), (12800, 3072, 1024), (257, 768, 1024), (65792, 1024, 4096)]:
     a = (torch.randn(M, K, device=dev) * 0.5).half(); w = (torch.randn(N, K, device=dev) * 0.05).half(); bias = torch.randn(N, device=dev)
     ref = a.float() @ w.float().t() + bias
-    for bn in (0, 32, 64, 128, 256):
+    for bn in (0, 32, 64, 128, 256, 512):
         for epi in (_ffi.EPI_F16_NONE, _ffi.EPI_F32, _ffi.EPI_RESID_F32, _ffi.EPI_F16_GELU_NEW, _ffi.EPI_ARGMAX):
             if N % 8 and epi not in (_ffi.EPI_F32, _ffi.EPI_ARGMAX): continue  # TMA epilogues need 16-byte row strides
-            if M * N > 5e7 and (bn not in (0, 256) or epi not in (_ffi.EPI_F16_NONE, _ffi.EPI_RESID_F32)): continue
+            if M * N > 5e7 and (bn not in (0, 256, 512) or epi not in (_ffi.EPI_F16_NONE, _ffi.EPI_RESID_F32)): continue
             if epi == _ffi.EPI_F16_NONE or epi == _ffi.EPI_F16_GELU_NEW:
                 out = torch.zeros(M, N, device=dev, dtype=torch.half); r = ref if epi == _ffi.EPI_F16_NONE else torch.nn.functional.gelu(ref, approximate="tanh")
             elif epi == _ffi.EPI_F32:
@@ -104,14 +104,14 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) / n
 for (M, N, K) in [(65792, 3072, 1024), (65792, 1024, 1024), (65792, 4096, 1024), (65792, 1024, 4096), (12800, 3072, 1024), (256, 3072, 1024), (256, 50264, 1024)]:
     a = torch.randn(M, K, device=dev).half(); w = torch.randn(N, K, device=dev).half(); out = torch.zeros(M, N, device=dev, dtype=torch.half)
-    for bn in (64, 128, 256):
+    for bn in (128, 256, 512):
         ms = timeit(lambda: ck(h.cc_op_gemm(a.data_ptr(), K, w.data_ptr(), None, out.data_ptr(), N, M, N, K, 0, bn, S())))
         print(f"time gemm M={M} N={N} K={K} bn={bn}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s")
     if M > 1000:
         bias = torch.randn(N, device=dev); h32 = torch.zeros(M, N, device=dev)
         for epi, nm, o in ((_ffi.EPI_F16_QUICKGELU, "quickgelu", out), (_ffi.EPI_F16_GELU_NEW, "gelu_new", out), (_ffi.EPI_RESID_F32, "resid_f32", h32)):
-            ms = timeit(lambda: ck(h.cc_op_gemm(a.data_ptr(), K, w.data_ptr(), bias.data_ptr(), o.data_ptr(), N, M, N, K, epi, 256, S())))
-            print(f"time gemm M={M} N={N} K={K} bn=256 epi={nm}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s")
+            ms = timeit(lambda: ck(h.cc_op_gemm(a.data_ptr(), K, w.data_ptr(), bias.data_ptr(), o.data_ptr(), N, M, N, K, epi, 512, S())))
+            print(f"time gemm M={M} N={N} K={K} bn=512 epi={nm}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s")
     ms = timeit(lambda: torch.matmul(a, w.t()))
     print(f"time torch(cuBLAS) M={M} N={N} K={K}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s")
 print("FAILURES:", bad)
