@@ -1,0 +1,154 @@
+"""Kernel-level parity through the C-ABI test hooks (cc_op_*): every GEMM tile shape (128x32 ... 128x256 and the 256x256
+CTA-pair tile) with every epilogue, LayerNorm, the attention kernels (tcgen05 ViT-L/14 shape and the generic one) and
+decode attention, each against a plain fp32 torch reference of the same op. Tolerances: fp16 operands / fp16 outputs,
+fp32 accumulation -> 2e-3 relative to the output's max (written per test)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from clipcap_b200 import _ffi
+
+pytestmark = pytest.mark.gpu
+
+GEMM_TOL = 2e-3
+ATTN_TOL = 3e-3
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 3072, 1024), (300, 1000, 520), (1, 2048, 768), (1031, 768, 1024),
+                                   (4096, 512, 136)])
+@pytest.mark.parametrize("bn", [0, 32, 64, 128, 256, 512])
+def test_gemm_epilogues(cuda_device, shape, bn):
+    lib = _ffi.lib()
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    a = (torch.randn(M, K, device=cuda_device, generator=g) * 0.5).half()
+    w = (torch.randn(N, K, device=cuda_device, generator=g) * 0.05).half()
+    bias = torch.randn(N, device=cuda_device, generator=g)
+    ref = a.float() @ w.float().t() + bias
+    cases = [(_ffi.EPI_F16_NONE, torch.half, lambda r: r), (_ffi.EPI_F16_RELU, torch.half, torch.relu),
+             (_ffi.EPI_F16_QUICKGELU, torch.half, lambda r: r * torch.sigmoid(1.702 * r)),
+             (_ffi.EPI_F16_GELU_NEW, torch.half, lambda r: torch.nn.functional.gelu(r, approximate="tanh")),
+             (_ffi.EPI_F16_TANH, torch.half, torch.tanh), (_ffi.EPI_F32, torch.float, lambda r: r)]
+    for epi, dt, fn in cases:
+        out = torch.zeros(M, N, device=cuda_device, dtype=dt)
+        _ffi.check(lib.cc_op_gemm(a.data_ptr(), K, w.data_ptr(), bias.data_ptr(), out.data_ptr(), N, M, N, K, epi, bn,
+                                  _stream()))
+        assert _rel(out, fn(ref)) < GEMM_TOL, (shape, bn, epi)
+    # fp32 residual update in place (TMA reduce-add): h += A W^T + bias
+    h0 = torch.randn(M, N, device=cuda_device, generator=g)
+    h = h0.clone()
+    _ffi.check(lib.cc_op_gemm(a.data_ptr(), K, w.data_ptr(), bias.data_ptr(), h.data_ptr(), N, M, N, K,
+                              _ffi.EPI_RESID_F32, bn, _stream()))
+    assert _rel(h, ref + h0) < GEMM_TOL
+    # fused arg-max (greedy LM head): the selected column must carry the row maximum
+    keys = torch.zeros(M, device=cuda_device, dtype=torch.int64)
+    _ffi.check(lib.cc_op_gemm(a.data_ptr(), K, w.data_ptr(), None, keys.data_ptr(), 1, M, N, K, _ffi.EPI_ARGMAX, bn,
+                              _stream()))
+    idx = (~keys) & 0xFFFFFFFF
+    raw = a.float() @ w.float().t()
+    got, best = raw.gather(1, idx.view(-1, 1)).squeeze(1), raw.max(1).values
+    assert ((best - got).abs().max() / best.abs().max()).item() < GEMM_TOL
+
+
+def test_gemm_odd_vocabulary_fp32(cuda_device):
+    """The LM head shape class: N = 50257 is odd, so the fp32 logits leave through the direct-store epilogue."""
+    lib = _ffi.lib()
+    M, N, K = 5, 50257, 768
+    a = (torch.randn(M, K, device=cuda_device) * 0.5).half()
+    w = (torch.randn(N, K, device=cuda_device) * 0.05).half()
+    out = torch.zeros(M, N, device=cuda_device)
+    _ffi.check(lib.cc_op_gemm(a.data_ptr(), K, w.data_ptr(), None, out.data_ptr(), N, M, N, K, _ffi.EPI_F32, 0, _stream()))
+    assert _rel(out, a.float() @ w.float().t()) < GEMM_TOL
+
+
+def test_gemm_rejects_misaligned_tma_output(cuda_device):
+    lib = _ffi.lib()
+    a = torch.zeros(4, 64, device=cuda_device, dtype=torch.half)
+    w = torch.zeros(50257, 64, device=cuda_device, dtype=torch.half)
+    out = torch.zeros(4, 50257, device=cuda_device, dtype=torch.half)
+    st = lib.cc_op_gemm(a.data_ptr(), 64, w.data_ptr(), None, out.data_ptr(), 50257, 4, 50257, 64, _ffi.EPI_F16_NONE, 0,
+                        _stream())
+    assert st == -3 and "16-byte" in _ffi.last_error()  # CC_EALIGN, not a silent slow path
+
+
+@pytest.mark.parametrize("rows,d", [(7, 768), (1000, 1024), (33, 64), (5, 2048), (4100, 1024)])
+def test_layernorm(cuda_device, rows, d):
+    lib = _ffi.lib()
+    x = torch.randn(rows, d, device=cuda_device) * 3 + 1
+    g, b = torch.randn(d, device=cuda_device), torch.randn(d, device=cuda_device)
+    y = torch.zeros(rows, d, device=cuda_device, dtype=torch.half)
+    _ffi.check(lib.cc_op_layernorm(x.data_ptr(), d, g.data_ptr(), b.data_ptr(), y.data_ptr(), d, rows, d, 1e-5, _stream()))
+    assert _rel(y, torch.nn.functional.layer_norm(x, (d,), g, b, 1e-5)) < GEMM_TOL
+
+
+@pytest.mark.parametrize("cfg", [(2, 257, 16, 64, 0), (5, 257, 2, 64, 0), (3, 50, 8, 128, 0), (2, 20, 8, 96, 0),
+                                 (2, 20, 16, 48, 0), (4, 40, 16, 64, 1), (1, 1, 2, 64, 1), (2, 130, 2, 64, 1),
+                                 (2, 256, 4, 64, 0), (2, 258, 4, 64, 0)])
+def test_attention(cuda_device, cfg):
+    """(B, S, H, hd, causal); S = 257 with hd = 64 runs the tcgen05 kernel, everything else the generic one."""
+    lib = _ffi.lib()
+    B, S, H, hd, causal = cfg
+    d = H * hd
+    qkv = torch.randn(B * S, 3 * d, device=cuda_device).half()
+    o = torch.zeros(B * S, d, device=cuda_device, dtype=torch.half)
+    _ffi.check(lib.cc_op_attention(qkv.data_ptr(), qkv.data_ptr() + 2 * d, qkv.data_ptr() + 4 * d, 3 * d, o.data_ptr(), d,
+                                   B, S, H, hd, causal, hd ** -0.5, _stream()))
+    q, k, v = [t.view(B, S, H, hd).transpose(1, 2).float() for t in qkv.split(d, dim=1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=bool(causal)).transpose(1, 2).reshape(B * S, d)
+    assert _rel(o, ref) < ATTN_TOL
+
+
+def test_vit_attention_large_scores(cuda_device):
+    """Row-max subtraction in the tcgen05 softmax: scores far outside the fp16 range of exp must not overflow."""
+    lib = _ffi.lib()
+    B, S, H, hd = 1, 257, 2, 64
+    d = H * hd
+    qkv = (torch.randn(B * S, 3 * d, device=cuda_device) * 6).half()
+    o = torch.zeros(B * S, d, device=cuda_device, dtype=torch.half)
+    _ffi.check(lib.cc_op_attention(qkv.data_ptr(), qkv.data_ptr() + 2 * d, qkv.data_ptr() + 4 * d, 3 * d, o.data_ptr(), d,
+                                   B, S, H, hd, 0, hd ** -0.5, _stream()))
+    q, k, v = [t.view(B, S, H, hd).transpose(1, 2).float() for t in qkv.split(d, dim=1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * S, d)
+    assert torch.isfinite(o.float()).all() and _rel(o, ref) < ATTN_TOL
+
+
+@pytest.mark.parametrize("use_anc", [False, True])
+def test_decode_attention(cuda_device, use_anc):
+    lib = _ffi.lib()
+    nseq, H, t_max = 6, 4, 40
+    d = H * 64
+    kc = torch.randn(nseq, H, t_max, 64, device=cuda_device).half()
+    vc = torch.randn(nseq, H, t_max, 64, device=cuda_device).half()
+    for pos in (0, 1, 7, 16, 39):
+        anc = None
+        if use_anc:  # beam ancestry: position t of row i lives in slot anc[i, t]
+            anc = torch.randint(0, nseq, (nseq, t_max), device=cuda_device, dtype=torch.int32)
+        qkv = torch.randn(nseq, 3 * d, device=cuda_device).half()
+        o = torch.zeros(nseq, d, device=cuda_device, dtype=torch.half)
+        kc0, vc0 = kc.clone(), vc.clone()
+        _ffi.check(lib.cc_op_decode_attention(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(),
+                                              None if anc is None else anc.data_ptr(), o.data_ptr(), nseq, H, t_max, pos,
+                                              0.125, _stream()))
+        torch.cuda.synchronize()
+        knew, vnew = qkv[:, d:2 * d].view(nseq, H, 64), qkv[:, 2 * d:].view(nseq, H, 64)
+        assert torch.equal(kc[:, :, pos], knew) and torch.equal(vc[:, :, pos], vnew)  # appended in place
+        if anc is None:
+            kh, vh = kc0[:, :, :pos].float(), vc0[:, :, :pos].float()
+        else:
+            sl = anc[:, :pos].long()  # [nseq, pos]
+            kh = torch.stack([kc0[sl[i], :, torch.arange(pos)] for i in range(nseq)]).transpose(1, 2).float() if pos else kc0[:, :, :0].float()
+            vh = torch.stack([vc0[sl[i], :, torch.arange(pos)] for i in range(nseq)]).transpose(1, 2).float() if pos else vc0[:, :, :0].float()
+        kk = torch.cat((kh, knew[:, :, None].float()), dim=2)
+        vv = torch.cat((vh, vnew[:, :, None].float()), dim=2)
+        q = qkv[:, :d].view(nseq, H, 1, 64).float()
+        ref = torch.nn.functional.scaled_dot_product_attention(q, kk, vv).reshape(nseq, d)
+        assert _rel(o, ref) < ATTN_TOL, (pos, use_anc)
