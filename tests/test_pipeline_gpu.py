@@ -1,0 +1,65 @@
+"""The serving loop (clipcap_b200.pipeline.CaptionPipeline) and the preprocess EncoderMapper on the GPU: pipelined results
+equal the direct stage calls; ragged last batch; pinned-memory requirement."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load_lm_case
+from oracle import restate as R
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(cuda_device):
+    from clipcap_b200.encoders.clip import CLIPModel, ViTImageTower
+    from clipcap_b200.encoders.config import EncoderConfig
+    from clipcap_b200.model import ClipCapModelPrefixOnly, Config
+    spec, gcfg, mcfg, map_w, lm_w, g = load_lm_case("tiny_a")
+    vcfg = R.VitCfg(image_size=28, patch=14, width=128, layers=2, heads=2, mlp_dim=512, out_dim=mcfg.E)
+    tower = ViTImageTower(vcfg.image_size, vcfg.patch, vcfg.width, vcfg.layers, vcfg.heads, vcfg.out_dim, vcfg.mlp_dim)
+    tower.load_state_dict(synth.vit_weights(vcfg), strict=True)
+    encode_fn = CLIPModel(tower).eval().to(cuda_device)
+    cfg = Config(language_model=spec, prefix_length=mcfg.K, projection_length=mcfg.P, transformer_layers=mcfg.L,
+                 transformer_attention_heads=mcfg.H, encoder_config=EncoderConfig(encoder_embedding_size=mcfg.E))
+    model = ClipCapModelPrefixOnly(cfg)
+    sd = {f"transformer_mapper.{k}": v for k, v in map_w.items()}
+    sd.update({f"language_model.{k}": v for k, v in lm_w.items()})
+    model.load_state_dict(sd, strict=True)
+    return encode_fn, model.eval().to(cuda_device), vcfg, int(g["stop_token"])
+
+
+def test_pipeline_equals_direct_calls(cuda_device):
+    from clipcap_b200.inference.base import generate_greedy_tokens
+    from clipcap_b200.pipeline import CaptionPipeline
+    encode_fn, model, vcfg, stop = _build(cuda_device)
+    B, EL = 4, 7
+    batches = [synth.pixels(n, vcfg.image_size, seed=50 + i).pin_memory() for i, n in enumerate((4, 4, 4, 3, 4))]
+    pipe = CaptionPipeline(encode_fn, model, B, vcfg.image_size, EL, stop, cuda_device)
+    got = [(t.clone(), l.clone()) for t, l in pipe.run(batches)]
+    assert len(got) == len(batches)
+    for px, (toks, lens) in zip(batches, got):
+        prefix = model.transformer_mapper(encode_fn(px.to(cuda_device)))
+        want_t, want_l, _ = generate_greedy_tokens(model, prefix, EL, stop)
+        assert toks.shape[0] == px.shape[0]
+        assert torch.equal(toks, want_t.cpu()) and torch.equal(lens, want_l.cpu())
+    with pytest.raises(ValueError):
+        list(pipe.run([synth.pixels(2, vcfg.image_size)]))  # pageable host memory is refused
+    assert list(pipe.run([])) == []
+
+
+def test_encoder_mapper_and_writer(cuda_device, tmp_path):
+    from clipcap_b200.preprocess import EncoderMapper, NumpyWriter
+    encode_fn, model, vcfg, _ = _build(cuda_device)
+    mapper = EncoderMapper(encode_fn, device="cuda")
+    writer = NumpyWriter(0, str(tmp_path / "out"), 1)
+    refs = []
+    for i in range(3):
+        px = synth.pixels(2, vcfg.image_size, seed=70 + i)
+        out = mapper({"data_tensor": px, "text": [f"a{i}", f"b{i}"]})
+        assert out["embeddings"].shape == (2, 64) and out["text"] == [f"a{i}", f"b{i}"]
+        refs.append(encode_fn(px.to(cuda_device)).cpu().numpy())
+        writer(out)
+    writer.flush()
+    emb = np.load(tmp_path / "out" / "embeddings" / "embeds_0.npy")
+    assert np.array_equal(emb, np.concatenate(refs))
