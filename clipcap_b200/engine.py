@@ -182,3 +182,69 @@ class Gpt2Engine(_Handle):
     @property
     def last_launches(self) -> int:
         return _ffi.lib().cc_gpt2_last_launches(self._h)
+
+
+class TrainEngine(_Handle):
+    """cc_train_* — one training step of ClipCapModelPrefixOnly (clipcap/model/model.py:94-123): forward, cross-entropy
+    loss with ignore_index 0, and the gradients of every transformer_mapper parameter; the language model is frozen.
+    `lm_weights`: `language_model.*` tensors (HF GPT-2 names)."""
+    _destroy_name = "cc_train_destroy"
+
+    def __init__(self, lm_weights: Dict[str, torch.Tensor], E=768, d=1024, P=10, K=40, H=8, L=8, lm_layers=24,
+                 lm_heads=16, V=50257, n_pos=1024, eps=1e-5, max_batch=64, max_tokens=67, device="cuda"):
+        super().__init__()
+        self.device = torch.device(device)
+        self.mcfg = _ffi.cc_mapper_cfg(_ffi.CC_MAPPER_TRANSFORMER, E, d, P, K, H, L, 1, 0, eps)
+        self.gcfg = _ffi.cc_gpt2_cfg(d, lm_layers, lm_heads, V, n_pos, eps)
+        self.max_batch, self.max_tokens = max_batch, max_tokens
+        with torch.cuda.device(self.device):
+            arr, keep = _ffi.make_tensor_table(_named(lm_weights, self.device))
+            _ffi.check(_ffi.lib().cc_train_create(C.byref(self._h), C.byref(self.mcfg), C.byref(self.gcfg), arr, len(keep),
+                                                  max_batch, max_tokens))
+            torch.cuda.synchronize()
+
+    def step(self, params: Dict[str, torch.Tensor], emb: torch.Tensor, tokens: torch.Tensor,
+             grads: Optional[Dict[str, torch.Tensor]] = None, loss_scale: float = 1024.0) -> torch.Tensor:
+        """params / grads: name -> fp32 contiguous CUDA tensor (names relative to `transformer_mapper.`). tokens: [B, Tt]
+        integer ids, negative = padding. Returns the loss as a 0-dim fp32 CUDA tensor; `grads` (if given) are overwritten
+        with d loss / d param. No host synchronisation."""
+        _require_cuda(emb, "embeddings")
+        _require_cuda(tokens, "tokens")
+        if emb.dim() != 2 or emb.shape[1] != self.mcfg.E:
+            raise ValueError(f"embeddings must be [B, {self.mcfg.E}], got {tuple(emb.shape)}")
+        if tokens.dim() != 2 or tokens.shape[0] != emb.shape[0]:
+            raise ValueError(f"tokens must be [B, Tt] with B = {emb.shape[0]}, got {tuple(tokens.shape)}")
+        for name, t in list(params.items()) + list((grads or {}).items()):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise ValueError(f"'{name}' must be a contiguous fp32 CUDA tensor")
+        emb = emb.contiguous()
+        tok32 = tokens.to(torch.int32).contiguous()
+        loss = torch.empty((), device=emb.device, dtype=torch.float32)
+        with torch.cuda.device(emb.device):
+            parr, pkeep = _ffi.make_tensor_table(list(params.items()))
+            if grads is not None:
+                garr, gkeep = _ffi.make_tensor_table(list(grads.items()))
+                ng = len(gkeep)
+            else:
+                garr, ng = None, 0
+            _ffi.check(_ffi.lib().cc_train_step(self._h, parr, len(pkeep), garr, ng, emb.data_ptr(),
+                                                _ffi.torch_dtype_code(emb), tok32.data_ptr(), emb.shape[0],
+                                                tokens.shape[1], float(loss_scale), loss.data_ptr(),
+                                                _ffi.current_stream_ptr()))
+        return loss
+
+    @property
+    def last_launches(self) -> int:
+        return _ffi.lib().cc_train_last_launches(self._h)
+
+
+def adamw_update(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, beta1=0.9, beta2=0.999,
+                 eps=1e-8, weight_decay=0.01, step=1) -> None:
+    """cc_op_adamw — torch.optim.AdamW's update on one flat fp32 CUDA parameter (in place)."""
+    for t in (p, g, m, v):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("adamw_update: contiguous fp32 CUDA tensors only")
+    with torch.cuda.device(p.device):
+        _ffi.check(_ffi.lib().cc_op_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr),
+                                          float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                          _ffi.current_stream_ptr()))

@@ -136,8 +136,13 @@ class GPT2LM(EngineModule):
             if input_ids is None:
                 raise ValueError("pass inputs_embeds or input_ids")
             inputs_embeds = self.transformer.wte(input_ids)
-        if attention_mask is not None and not bool(attention_mask.all()):
-            raise NotImplementedError("padding masks (training batches) are outside the inference hot path")
+        if attention_mask is not None and attention_mask.shape[1] > 1:
+            # Trailing padding only (what the reference's dataloader produces): under the causal mask a real position
+            # never attends to a padded one, so the logits of real positions equal HF's masked forward; the logits at
+            # padded positions are not meaningful (the training loss ignores them, model.py:109-110).
+            m = attention_mask.to(torch.bool)
+            if bool((m[:, 1:] & ~m[:, :-1]).any()):
+                raise NotImplementedError("attention masks with padding before real tokens are not supported")
         B, T, _ = inputs_embeds.shape
         logits = self._engine_for(B, T).logits(inputs_embeds, all_positions=True)
         return SimpleNamespace(logits=logits)

@@ -181,6 +181,32 @@ int cc_gpt2_last_launches(cc_gpt2* h);
 void cc_gpt2_destroy(cc_gpt2* h);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Training step of the prefix mapper with the language model frozen.
+ * Replaces: ClipCapModel.forward + training_step (clipcap/model/model.py:43-58, 94-113) followed by loss.backward() for
+ * ClipCapModelPrefixOnly (model.py:116-123: only transformer_mapper parameters train, the LM stays in eval mode):
+ *   tokens < 0 are padding (set to 0, model.py:103-104); logits[:, prefix_length-1:-1] are scored against the tokens with
+ *   cross-entropy, ignore_index = 0 (model.py:109-110), mean over the scored tokens.
+ * `lm_weights`: `language_model.*` tensors as for cc_gpt2_create. `params` / `grads`: the caller's CURRENT fp32
+ * transformer_mapper tensors and same-named fp32 buffers that receive d loss / d param (overwritten, not accumulated) —
+ * all DEVICE pointers, names as for cc_mapper_create. grads == NULL: forward + loss only (validation).
+ * Padding must be trailing (as the reference's dataloader produces): under the causal mask the scored positions then
+ * never see a padded key, which is what HF's attention_mask (model.py:52-56) enforces.
+ * loss_scale (> 0, power of two; <= 0 picks 1024): activation gradients travel between GEMMs in fp16 scaled by this
+ * factor; parameter gradients are returned unscaled. loss: DEVICE pointer to one fp32.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct cc_train cc_train;
+int cc_train_create(cc_train** h, const cc_mapper_cfg* mapper_cfg, const cc_gpt2_cfg* lm_cfg, const cc_tensor* lm_weights,
+                    int n_weights, int max_batch, int max_tokens);
+int cc_train_step(cc_train* h, const cc_tensor* params, int n_params, const cc_tensor* grads, int n_grads,
+                  const void* emb /*[B,E]*/, int emb_dtype, const int32_t* tokens /*[B,Tt]*/, int B, int Tt, float loss_scale,
+                  float* loss, void* stream);
+int cc_train_last_launches(cc_train* h);
+void cc_train_destroy(cc_train* h);
+/* torch.optim.AdamW update on flat fp32 device arrays (configure_optimizers, model.py:67-91); step counts from 1. */
+int cc_op_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                float weight_decay, int step, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Kernel-level test hooks (used by tests/ and bench.py for per-kernel parity and roofline timing; same kernels the
  * engines launch).
  * ------------------------------------------------------------------------------------------------------------------ */

@@ -123,6 +123,22 @@ def reference_generate_beam(model, embeds: torch.Tensor, beam_size: int, entry_l
     return [int(t) for t in out[0].split()] if out[0] else []
 
 
+def reference_training_step(model, tokens: torch.Tensor, emb: torch.Tensor):
+    """The reference's own ClipCapModelPrefixOnly.training_step + loss.backward() (clipcap/model/model.py:94-123).
+    Returns (loss, {mapper parameter name: gradient})."""
+    import_reference()
+    model.train()
+    for p in model.language_model.parameters():
+        p.grad = None
+    for p in model.transformer_mapper.parameters():
+        p.grad = None
+    loss = model.training_step((tokens.clone(), emb.clone()), 0)
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in model.transformer_mapper.named_parameters()}
+    model.eval()
+    return float(loss.detach()), grads
+
+
 def rank_cycle_pick(p: torch.Tensor, step: int) -> int:
     """Deterministic stand-in for torch.multinomial used on both sides of the sampling parity tests: the token of rank
     (step mod 3) among the kept (non-zero) probabilities, so the sequences are not just the arg-max path."""

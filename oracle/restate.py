@@ -321,6 +321,43 @@ def generate_sampling(w: Weights, cfg: Gpt2Cfg, embeds: torch.Tensor, mode: str,
     return out
 
 
+# ------------------------------------------------------------------------------------------------ training step
+def training_loss(map_w: Weights, lm_w: Weights, mcfg: MapperCfg, gcfg: Gpt2Cfg, tokens: torch.Tensor,
+                  emb: torch.Tensor) -> torch.Tensor:
+    """ClipCapModel.training_step (clipcap/model/model.py:94-113) with forward (model.py:43-58): tokens [B, Tt] int64 with
+    -1 padding, emb [B, E]. Differentiable in map_w (torch autograd) — the gradient oracle of cc_train_step.
+    The padding mask (model.py:52-56) is not applied: with trailing padding and a causal LM no scored position can see a
+    padded key, and padded positions are dropped by ignore_index=0 (pinned against the reference, which does apply it)."""
+    tokens = tokens.clone()
+    mask = tokens.ge(0)                                              # :103
+    tokens[~mask] = 0                                                # :104
+    token_embeddings = lm_w["transformer.wte.weight"][tokens]        # :45
+    prefix = mapper_forward(map_w, emb, mcfg)                        # :46
+    inputs = torch.cat((prefix, token_embeddings), dim=1)            # :49
+    logits = gpt2_logits(lm_w, inputs, gcfg)                         # :56
+    logits = logits[:, mcfg.K - 1:-1]                                # :109
+    return F.cross_entropy(logits.reshape(-1, logits.shape[-1]), tokens.flatten(), ignore_index=0)  # :110
+
+
+def training_loss_and_grads(map_w: Weights, lm_w: Weights, mcfg: MapperCfg, gcfg: Gpt2Cfg, tokens: torch.Tensor,
+                            emb: torch.Tensor) -> Tuple[float, Dict[str, torch.Tensor]]:
+    """loss.backward() of the step above for ClipCapModelPrefixOnly (model.py:116-123): gradients of every mapper tensor."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in map_w.items()}
+    loss = training_loss(leaves, lm_w, mcfg, gcfg, tokens, emb)
+    loss.backward()
+    return float(loss.detach()), {k: v.grad.detach() for k, v in leaves.items()}
+
+
+def adamw_reference(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
+    """torch.optim.AdamW single-tensor update (torch/optim/adamw.py _single_tensor_adamw, amsgrad=False)."""
+    p = p * (1 - lr * weight_decay)
+    m = beta1 * m + (1 - beta1) * g
+    v = beta2 * v + (1 - beta2) * g * g
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    denom = v.sqrt() / math.sqrt(bc2) + eps
+    return p - (lr / bc1) * (m / denom), m, v
+
+
 # ------------------------------------------------------------------------------------------------ whole path
 def caption_greedy(vit_w: Weights, map_w: Weights, lm_w: Weights, vcfg: VitCfg, mcfg: MapperCfg, gcfg: Gpt2Cfg,
                    pixels: torch.Tensor, entry_length: int, stop_token: int, normalize: bool = False):

@@ -87,5 +87,42 @@ def main():
     print("vit_tiny", {k: getattr(v, "shape", v) for k, v in out.items()})
 
 
+TRAIN_KEEP = ("linear.bias", "prefix_const", "transformer.layers.0.norm1.weight", "transformer.layers.0.norm1.bias",
+              "transformer.layers.0.attn.to_queries.weight", "transformer.layers.0.attn.project.bias",
+              "transformer.layers.0.norm2.weight", "transformer.layers.0.mlp.fc1.bias",
+              "transformer.layers.0.mlp.fc2.bias")  # full tensors; every other gradient is pinned through its L2 norm
+
+
+def train_batch(gcfg, mcfg, B=4, Tt=7):
+    """Seeded caption batch as the reference's dataloader hands it to training_step: -1 padding at the end of some rows,
+    one real token with id 0 (which ignore_index=0 also drops — reference quirk, model.py:110)."""
+    g = torch.Generator().manual_seed(11)
+    tokens = torch.randint(1, gcfg.V, (B, Tt), generator=g)
+    tokens[1, Tt - 2:] = -1
+    tokens[2, Tt - 4:] = -1
+    tokens[3, 1] = 0
+    return tokens, synth.embeddings(B, mcfg.E, seed=77)
+
+
+def make_train():
+    """training_step + loss.backward() of the reference's ClipCapModelPrefixOnly (model.py:94-123) -> train_<case>.npz"""
+    for name, (spec, gcfg, mcfg) in CASES.items():
+        map_w, lm_w = synth.mapper_weights(mcfg), synth.gpt2_weights(gcfg, wte_std=0.1)
+        model = RR.build_reference_model(spec, mcfg.E, mcfg.K, mcfg.P, mcfg.H, mcfg.L, map_w, lm_w)
+        tokens, emb = train_batch(gcfg, mcfg)
+        loss, grads = RR.reference_training_step(model, tokens, emb)
+        out = {"tokens": tokens.numpy(), "emb": emb.numpy(), "loss": np.float64(loss),
+               "w_checksum": np.float64(synth.checksum(map_w) + synth.checksum(lm_w)),
+               "names": np.asarray(sorted(grads)), "norms": np.asarray([float(grads[k].norm()) for k in sorted(grads)])}
+        for k in TRAIN_KEEP:
+            out["grad:" + k] = grads[k].numpy()
+        np.savez_compressed(os.path.join(HERE, f"train_{name}.npz"), **out)
+        print("train_" + name, "loss", loss, {k: getattr(v, "shape", v) for k, v in out.items() if k.startswith("grad:")})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        make_train()
+    else:
+        main()
+        make_train()

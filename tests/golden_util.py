@@ -49,3 +49,16 @@ def load_vit_case():
 
 def golden_rows(arr):
     return [[int(t) for t in row if t >= 0] for row in arr]
+
+
+def load_train_case(name):
+    """Fixture of the reference's training_step + backward (tests/golden/make_golden.py make_train)."""
+    spec, gcfg, mcfg = LM_CASES[name]
+    g = np.load(os.path.join(GOLDEN_DIR, f"train_{name}.npz"))
+    map_w, lm_w = synth.mapper_weights(mcfg), synth.gpt2_weights(gcfg, wte_std=0.1)
+    cs = synth.checksum(map_w) + synth.checksum(lm_w)
+    if abs(cs - float(g["w_checksum"])) > 1e-6 * abs(cs):
+        pytest.skip("seeded weights differ from the ones the fixture was made with (torch RNG drift)")
+    grads = {k[5:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("grad:")}
+    norms = {str(n): float(v) for n, v in zip(g["names"], g["norms"])}
+    return spec, gcfg, mcfg, map_w, lm_w, torch.from_numpy(g["tokens"]), torch.from_numpy(g["emb"]), float(g["loss"]), grads, norms
