@@ -2,6 +2,7 @@
 // include/clipcap_b200.h.  The hooks launch exactly the kernels the engines launch (same plans, same heuristics).
 #include "common.h"
 #include "decode.h"
+#include "train.h"
 
 extern "C" {
 
@@ -46,6 +47,20 @@ int cc_op_attention(const void* q, const void* k, const void* v, int64_t ld, voi
   CC_TRY(check_device_sm100());
   return attention_run(static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v), ld,
                        static_cast<__half*>(o), ldo, B, S, H, hd, causal != 0, scale, static_cast<cudaStream_t>(stream));
+}
+
+int cc_op_attention_bwd(const void* q, const void* k, const void* v, int64_t ld, const void* d_o, int64_t ldo, void* dq,
+                        void* dk, void* dv, int64_t ldd, int B, int S, int H, int hd, int causal, float scale,
+                        void* stream) {
+  using namespace cc;
+  CC_REQUIRE(q != nullptr && k != nullptr && v != nullptr && d_o != nullptr && dq != nullptr && dk != nullptr &&
+                 dv != nullptr,
+             CC_EINVAL, "cc_op_attention_bwd: null argument");
+  CC_TRY(check_device_sm100());
+  return attention_bwd_run(static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v), ld,
+                           static_cast<const __half*>(d_o), ldo, static_cast<__half*>(dq), static_cast<__half*>(dk),
+                           static_cast<__half*>(dv), ldd, B, S, H, hd, causal != 0, scale,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int cc_op_decode_attention(const void* qkv, void* kcache, void* vcache, const int32_t* anc, void* o, int nseq, int H,

@@ -3,6 +3,7 @@
 // weight gradients TN GEMMs, bias reductions and the AdamW update. All GEMM-shaped work of the backward pass runs on the
 // tcgen05 GEMM (gemm.cu); what is here is HBM-bound element-wise / reduction work plus the small attention backward.
 #include <algorithm>
+#include <cstdlib>
 
 #include "train.h"
 // (common.h first: ptx.cuh uses printf)
@@ -342,6 +343,183 @@ attention_bwd_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
   }
 }
 
+// ---------------------------------------------------------------- attention backward on warp MMA (mma.m16n8k16)
+// Same contract as attention_bwd_kernel for the shapes of the training step (S <= 8 * NTMAX keys): Q, K, V, dO and the two
+// S x S matrices P and dS live in shared memory as fp16 with a 16-byte row pad (conflict-free ldmatrix); every product
+//   S = Q K^T, dP = dO V^T (A row-major, B stored [n][k]);  dV = P^T dO, dK = dS^T Q (A transposed, B stored [k][n]);
+//   dQ = dS K (A row-major, B stored [k][n])
+// is a strip of 16 output rows per warp. Softmax statistics and dS are formed in fp32 registers.
+template <int HD, int NTMAX>
+__global__ void __launch_bounds__(256)
+attention_bwd_mma_kernel(const __half* __restrict__ q, const __half* __restrict__ k, const __half* __restrict__ v,
+                         long long ld, const __half* __restrict__ d_o, long long ldo, __half* __restrict__ dq,
+                         __half* __restrict__ dk, __half* __restrict__ dv, long long ldd, int S, int H, int causal,
+                         float scale) {
+  extern __shared__ __align__(16) uint8_t atm_smem[];
+  constexpr int PH = HD * 2 + 16;  // row pitch (bytes) of the [S][HD] tiles
+  const int SPAD = (S + 15) & ~15;
+  const int PS = SPAD * 2 + 16;    // row pitch of the [S][S] matrices
+  const uint32_t sQ = smem_u32(atm_smem);
+  const uint32_t sK = sQ + SPAD * PH, sV = sK + SPAD * PH, sO = sV + SPAD * PH;
+  const uint32_t sP = sO + SPAD * PH, sD = sP + SPAD * PS;
+  uint8_t* pP = atm_smem + 4 * SPAD * PH;
+  uint8_t* pD = pP + SPAD * PS;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const long long row0 = static_cast<long long>(b) * S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3, mi = lane >> 3, rr = lane & 7;
+
+  {  // operand tiles, rows >= S zero-filled
+    constexpr int CPR = HD / 8;
+    for (int i = threadIdx.x; i < SPAD * CPR; i += blockDim.x) {
+      const int r = i / CPR, c = i - r * CPR;
+      const bool ok = r < S;
+      const long long gq = (row0 + (ok ? r : 0)) * ld + h * HD + c * 8;
+      const long long go = (row0 + (ok ? r : 0)) * ldo + h * HD + c * 8;
+      const uint32_t so = r * PH + c * 16;
+      cp_async_16(sQ + so, q + gq, ok);
+      cp_async_16(sK + so, k + gq, ok);
+      cp_async_16(sV + so, v + gq, ok);
+      cp_async_16(sO + so, d_o + go, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+  }
+  __syncthreads();
+
+  const int strips = SPAD >> 4;
+  // ---- phase 1: P and dS, one strip of 16 query rows per warp
+  for (int st = warp; st < strips; st += nwarps) {
+    const int m0 = st * 16;
+    float acc[NTMAX][4];
+    // acc = X[m0 strip] Y^T with X, Y in {Q, K} or {dO, V}
+    auto strip_xyT = [&](uint32_t sX, uint32_t sY) {
+#pragma unroll
+      for (int nt = 0; nt < NTMAX; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) {
+        uint32_t a[4];
+        ldmatrix_x4(a, sX + (m0 + (mi & 1) * 8 + rr) * PH + (ks * 16 + (mi >> 1) * 8) * 2);
+#pragma unroll
+        for (int np = 0; np < NTMAX / 2; ++np) {
+          if (np * 16 < SPAD) {
+            uint32_t bf[4];
+            ldmatrix_x4(bf, sY + (np * 16 + (mi >> 1) * 8 + rr) * PH + (ks * 16 + (mi & 1) * 8) * 2);
+            mma_16816(acc[np * 2], a, bf[0], bf[1]);
+            mma_16816(acc[np * 2 + 1], a, bf[2], bf[3]);
+          }
+        }
+      }
+    };
+    strip_xyT(sQ, sK);
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < NTMAX; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = nt * 8 + 2 * t + (e & 1), row = m0 + g + (e >> 1) * 8;
+        const bool ok = key < S && (!causal || key <= row);
+        acc[nt][e] = ok ? acc[nt][e] * scale : -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], acc[nt][e]);
+      }
+    }
+    float sum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      if (mx[r] == -INFINITY) mx[r] = 0.f;  // padded query rows: every key masked
+    }
+#pragma unroll
+    for (int nt = 0; nt < NTMAX; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pe = __expf(acc[nt][e] - mx[e >> 1]);
+        acc[nt][e] = pe;
+        sum[e >> 1] += pe;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+      sum[r] = sum[r] > 0.f ? 1.f / sum[r] : 0.f;
+    }
+#pragma unroll
+    for (int nt = 0; nt < NTMAX; ++nt) {
+      if (nt * 8 < SPAD) {
+        const int c = nt * 8 + 2 * t;
+        *reinterpret_cast<uint32_t*>(pP + (m0 + g) * PS + c * 2) = pack_half2(acc[nt][0] * sum[0], acc[nt][1] * sum[0]);
+        *reinterpret_cast<uint32_t*>(pP + (m0 + g + 8) * PS + c * 2) = pack_half2(acc[nt][2] * sum[1], acc[nt][3] * sum[1]);
+      }
+    }
+    __syncwarp();
+    strip_xyT(sO, sV);  // dP
+    float dsum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < NTMAX; ++nt) {
+      if (nt * 8 < SPAD) {
+        const int c = nt * 8 + 2 * t;
+        const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(pP + (m0 + g) * PS + c * 2));
+        const float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(pP + (m0 + g + 8) * PS + c * 2));
+        dsum[0] += p0.x * acc[nt][0] + p0.y * acc[nt][1];
+        dsum[1] += p1.x * acc[nt][2] + p1.y * acc[nt][3];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 1);
+      dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 2);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NTMAX; ++nt) {
+      if (nt * 8 < SPAD) {
+        const int c = nt * 8 + 2 * t;
+        const float2 p0 = __half22float2(*reinterpret_cast<const __half2*>(pP + (m0 + g) * PS + c * 2));
+        const float2 p1 = __half22float2(*reinterpret_cast<const __half2*>(pP + (m0 + g + 8) * PS + c * 2));
+        *reinterpret_cast<uint32_t*>(pD + (m0 + g) * PS + c * 2) =
+            pack_half2(scale * p0.x * (acc[nt][0] - dsum[0]), scale * p0.y * (acc[nt][1] - dsum[0]));
+        *reinterpret_cast<uint32_t*>(pD + (m0 + g + 8) * PS + c * 2) =
+            pack_half2(scale * p1.x * (acc[nt][2] - dsum[1]), scale * p1.y * (acc[nt][3] - dsum[1]));
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: the three [S, HD] outputs, one strip of 16 output rows per (warp, product)
+  // out[m0 strip] = op(A) B, B stored [k][n] with pitch PH; TRANS_A: A[m][k] = X[k][m] (X = P or dS, pitch PS)
+  auto strip_out = [&](uint32_t sX, bool trans_a, uint32_t sB, int m0, int k_lo, int k_hi, __half* out) {
+    float acc[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
+      uint32_t a[4];
+      if (trans_a) ldmatrix_x4_trans(a, sX + (k0 + (mi >> 1) * 8 + rr) * PS + (m0 + (mi & 1) * 8) * 2);
+      else ldmatrix_x4(a, sX + (m0 + (mi & 1) * 8 + rr) * PS + (k0 + (mi >> 1) * 8) * 2);
+#pragma unroll
+      for (int np = 0; np < HD / 16; ++np) {
+        uint32_t bf[4];
+        ldmatrix_x4_trans(bf, sB + (k0 + (mi & 1) * 8 + rr) * PH + (np * 16 + (mi >> 1) * 8) * 2);
+        mma_16816(acc[np * 2], a, bf[0], bf[1]);
+        mma_16816(acc[np * 2 + 1], a, bf[2], bf[3]);
+      }
+    }
+    const int ra = m0 + g, rb = m0 + g + 8;
+#pragma unroll
+    for (int nt = 0; nt < HD / 8; ++nt) {
+      const int c = h * HD + nt * 8 + 2 * t;
+      if (ra < S) *reinterpret_cast<uint32_t*>(out + (row0 + ra) * ldd + c) = pack_half2(acc[nt][0], acc[nt][1]);
+      if (rb < S) *reinterpret_cast<uint32_t*>(out + (row0 + rb) * ldd + c) = pack_half2(acc[nt][2], acc[nt][3]);
+    }
+  };
+  for (int w = warp; w < 3 * strips; w += nwarps) {
+    const int which = w / strips, m0 = (w - which * strips) * 16;
+    if (which == 0) strip_out(sP, true, sO, m0, causal ? m0 : 0, SPAD, dv);        // dV[j] = sum_{i >= j} P[i][j] dO[i]
+    else if (which == 1) strip_out(sD, true, sQ, m0, causal ? m0 : 0, SPAD, dk);   // dK[j] = sum_{i >= j} dS[i][j] Q[i]
+    else strip_out(sD, false, sK, m0, 0, causal ? m0 + 16 : SPAD, dq);             // dQ[i] = sum_{j <= i} dS[i][j] K[j]
+  }
+}
+
 // ---------------------------------------------------------------- cross-entropy (ignore_index 0)
 __global__ void count_valid_kernel(const int32_t* __restrict__ targets, int n, int* __restrict__ n_valid) {
   __shared__ int red[32];
@@ -563,11 +741,59 @@ int layernorm_bwd_run(const float* dy, int64_t dy_ld, const float* x, int64_t x_
   return CC_OK;
 }
 
+namespace {
+template <int HD, int NTMAX>
+int launch_attn_bwd_mma(const __half* q, const __half* k, const __half* v, int64_t ld, const __half* d_o, int64_t ldo,
+                        __half* dq, __half* dk, __half* dv, int64_t ldd, int B, int S, int H, bool causal, float scale,
+                        cudaStream_t s) {
+  const int spad = (S + 15) & ~15;
+  const size_t smem = 4 * static_cast<size_t>(spad) * (HD * 2 + 16) + 2 * static_cast<size_t>(spad) * (spad * 2 + 16);
+  if (smem > 227 * 1024) return CC_ESHAPE;
+  auto kern = attention_bwd_mma_kernel<HD, NTMAX>;
+  static bool configured = false;
+  if (!configured) {
+    CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  kern<<<B * H, 256, smem, s>>>(q, k, v, ld, d_o, ldo, dq, dk, dv, ldd, S, H, causal ? 1 : 0, scale);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+bool attn_bwd_scalar_forced() {
+  static const bool on = [] {
+    const char* e = getenv("CLIPCAP_B200_ATTN_BWD_SCALAR");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+}  // namespace
+
 int attention_bwd_run(const __half* q, const __half* k, const __half* v, int64_t ld, const __half* d_o, int64_t ldo,
                       __half* dq, __half* dk, __half* dv, int64_t ldd, int B, int S, int H, int hd, bool causal,
                       float scale, cudaStream_t s) {
   CC_REQUIRE(B > 0 && S > 0 && H > 0 && hd > 0 && hd % 2 == 0, CC_ESHAPE, "attention_bwd: B=%d S=%d H=%d hd=%d", B, S, H, hd);
   CC_REQUIRE(ld % 2 == 0 && ldo % 2 == 0 && ldd % 2 == 0, CC_EALIGN, "attention_bwd: strides must be even");
+  // tensor-core kernel: 16-byte aligned rows, head dim 48/64/96/128, S <= 160 (within shared memory)
+  const bool aligned = ld % 8 == 0 && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(k) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(d_o) & 15) == 0 && hd % 8 == 0;
+  if (aligned && !attn_bwd_scalar_forced()) {
+    int st = CC_ESHAPE;
+#define CC_ATB_CASE(HD, NT)                                                                                          \
+  if (st == CC_ESHAPE && hd == HD && S <= 8 * NT)                                                                    \
+    st = launch_attn_bwd_mma<HD, NT>(q, k, v, ld, d_o, ldo, dq, dk, dv, ldd, B, S, H, causal, scale, s);
+    CC_ATB_CASE(64, 8)
+    CC_ATB_CASE(64, 14)
+    CC_ATB_CASE(64, 20)
+    CC_ATB_CASE(48, 8)
+    CC_ATB_CASE(48, 14)
+    CC_ATB_CASE(96, 8)
+    CC_ATB_CASE(96, 14)
+    CC_ATB_CASE(128, 8)
+    CC_ATB_CASE(128, 14)
+#undef CC_ATB_CASE
+    if (st != CC_ESHAPE) return st;
+  }
   CC_REQUIRE(S <= 32 * ATB_MAXJ, CC_ESHAPE, "attention_bwd: sequence length %d exceeds %d", S, 32 * ATB_MAXJ);
   const size_t tiles = 4 * static_cast<size_t>(S) * (hd + 2) * sizeof(__half);
   const size_t smem = ((tiles + 15) & ~static_cast<size_t>(15)) + static_cast<size_t>(S) * (S + 1) * sizeof(float);

@@ -227,6 +227,12 @@ int cc_op_decode_attention(const void* qkv, void* kcache, void* vcache, const in
 int cc_op_sample(const float* logits, int rows, int V, const cc_gen_cfg* cfg, int step, int32_t* tokens,
                  int32_t* stopped, int32_t* lengths, void* stream);
 
+/* Backward of cc_op_attention (training step): given d_o = d loss / d o, writes dq, dk, dv in the layout of q, k, v
+ * (row stride ldd). */
+int cc_op_attention_bwd(const void* q, const void* k, const void* v, int64_t ld, const void* d_o, int64_t ldo, void* dq,
+                        void* dk, void* dv, int64_t ldd, int B, int S, int H, int hd, int causal, float scale,
+                        void* stream);
+
 /* Live per-launch timing of the dominant kernel (the 128x256-tile tcgen05 GEMM): while enabled, every such launch that
  * is not inside a graph capture is bracketed by CUDA events on its own stream. cc_prof_read synchronises the device and
  * returns the summed duration (ms), algorithmic FLOPs (2*M*N*K) and launch count since cc_prof_enable(1). */

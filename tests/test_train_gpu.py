@@ -90,6 +90,36 @@ def test_train_step_gpt2_small_shapes(cuda_device):
     _check_grads(grads, want)
 
 
+@pytest.mark.parametrize("cfg", [(2, 107, 16, 64, 1), (3, 50, 8, 128, 0), (2, 33, 4, 96, 0), (1, 160, 2, 64, 1),
+                                 (2, 20, 3, 48, 0), (2, 1, 2, 64, 1), (1, 170, 2, 64, 0)])
+def test_attention_backward_kernels(cuda_device, cfg):
+    """cc_op_attention_bwd vs torch autograd: the warp-MMA kernel (S <= 160) and, for the last shape, the scalar kernel
+    that covers what is left."""
+    from clipcap_b200 import _ffi
+    B, S, H, hd, causal = cfg
+    d = H * hd
+    g = torch.Generator().manual_seed(S * 7 + hd)
+    qkv = (torch.randn(B * S, 3 * d, generator=g) * 0.7).half()
+    d_o = (torch.randn(B * S, d, generator=g) * 0.3).half()
+    scale = hd ** -0.5
+    x = qkv.float().reshape(B, S, 3, H, hd).requires_grad_(True)
+    qq, kk, vv = [x[:, :, i].transpose(1, 2) for i in range(3)]
+    att = (qq @ kk.transpose(-1, -2)) * scale
+    if causal:
+        att = att + torch.full((S, S), float("-inf")).triu(1)
+    o = (att.softmax(-1) @ vv).transpose(1, 2).reshape(B * S, d)
+    o.backward(d_o.float())
+    want = x.grad.reshape(B * S, 3 * d)
+    qd, dod = qkv.to(cuda_device), d_o.to(cuda_device)
+    out = torch.full((B * S, 3 * d), float("nan"), device=cuda_device, dtype=torch.half)
+    p = qd.data_ptr()
+    _ffi.check(_ffi.lib().cc_op_attention_bwd(p, p + 2 * d, p + 4 * d, 3 * d, dod.data_ptr(), d, out.data_ptr(),
+                                              out.data_ptr() + 2 * d, out.data_ptr() + 4 * d, 3 * d, B, S, H, hd, causal,
+                                              scale, _ffi.current_stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel_err(out, want) < 4e-3, cfg
+
+
 def test_all_padding_gives_nan_like_torch(cuda_device):
     spec, gcfg, mcfg, map_w, lm_w, tokens, emb, *_ = load_train_case("tiny_a")
     eng = _engine(gcfg, mcfg, lm_w, 4, tokens.shape[1], cuda_device)
