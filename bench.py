@@ -316,7 +316,7 @@ def run_b200(args):
                         traffic = json.load(f).get("traffic_bytes_per_launch")
                 roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                         "frac": ach / peaks["tf_sustained"], "traffic": traffic,
-                        "kernel": "gemm_tn_kernel (tcgen05, 128x256 tile) over the ViT-L/14 block GEMMs",
+                        "kernel": "gemm_tn_kernel<256,*,2> (tcgen05 cta_group::2, 256x256 CTA-pair tile) over the ViT-L/14 block GEMMs",
                         "launches_timed": n.value, "avg_launch_ms": ms.value / n.value,
                         "flops_per_launch": fl.value / n.value, "peak_source": peaks["source"] + ", sustained bf16"}
 

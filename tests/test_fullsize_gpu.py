@@ -1,0 +1,100 @@
+"""Size-independent properties at BASELINE.json's full sizes (configs[1]: ViT-L/14 -> TransformerMapper L=8 K=40 P=10 H=8 ->
+GPT-2-medium, B=256, 20 greedy tokens; configs[3] per-GPU shard: beam 5 over 256 images = 1280 sequences), where the CPU
+oracle can only afford a few samples:
+  * determinism: the same batch twice gives identical token ids and scores;
+  * batch invariance: row i of the B=256 run equals row i of a small batch holding the same images (the path is
+    data-parallel over images; this is also what makes the multi-GPU split exact);
+  * spot parity: a few rows of the full batch against the oracle (greedy bit-exact with the margin rule; beam-5 best beam);
+  * the stop token ends a caption and the remaining positions keep the reference's truncation (lengths).
+"""
+import pytest
+import torch
+
+from conftest import rel_err
+from helpers import check_tokens_against_oracle
+from oracle import restate as R
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+EL, STOP = 20, 50256
+
+
+@pytest.fixture(scope="module")
+def full(cuda_device):
+    import bench
+    from clipcap_b200.engine import Gpt2Engine, MapperEngine, VitEngine
+    state = bench.synthetic_state()
+    g = R.Gpt2Cfg()
+    vit = VitEngine(state["vit"], max_batch=256, device=cuda_device)
+    mapper = MapperEngine(state["mapper"], E=768, d=1024, P=10, K=40, H=8, L=8, max_batch=256, device=cuda_device)
+    lm = Gpt2Engine(state["lm"], g.d, g.L, g.H, g.V, g.n_pos, max_seqs=256 * 5, max_len=40 + EL, device=cuda_device)
+    px = synth.pixels(256, 224, seed=1234)
+    emb = vit.forward(px.to(cuda_device))
+    prefix = mapper.forward(emb)
+    return dict(state=state, vit=vit, mapper=mapper, lm=lm, px=px, emb=emb, prefix=prefix, dev=cuda_device)
+
+
+def test_greedy_full_batch_deterministic_and_batch_invariant(full):
+    lm, prefix = full["lm"], full["prefix"]
+    t1, l1, _ = lm.generate(prefix, "greedy", 1, EL, 1.0, STOP)
+    t2, l2, _ = lm.generate(prefix, "greedy", 1, EL, 1.0, STOP)
+    assert torch.equal(t1, t2) and torch.equal(l1, l2)
+    assert int(l1.min()) >= 1 and int(l1.max()) <= EL
+    # rows 40..47 alone (a different batch size picks different GEMM tiles; the per-row arithmetic is the same)
+    ts, ls, _ = lm.generate(prefix[40:48].contiguous(), "greedy", 1, EL, 1.0, STOP)
+    assert torch.equal(ts, t1[40:48]) and torch.equal(ls, l1[40:48])
+    # The encode path is batch invariant up to the tile shape: a small batch runs 128-row tiles where the full batch runs
+    # 256-row CTA-pair tiles, the fp32 sums differ in the last bits (ViT: < 1e-5) and an fp16 operand rounding can then
+    # flip by one ulp further down (mapper: < 5e-4, inside the 1e-3 stage tolerance).
+    emb8 = full["vit"].forward(full["px"][40:48].to(full["dev"]))
+    assert rel_err(emb8, full["emb"][40:48]) < 1e-5
+    pre8 = full["mapper"].forward(emb8)
+    assert rel_err(pre8, prefix[40:48]) < 5e-4
+    assert torch.equal(full["mapper"].forward(full["emb"]), prefix)  # same batch, same bits
+
+
+def test_greedy_full_size_rows_match_oracle(full):
+    st = full["state"]
+    rows = [0, 101, 255]
+    px = full["px"][rows]
+    _, _, oracle = R.caption_greedy(st["vit"], st["mapper"], st["lm"], R.VitCfg(), R.MapperCfg(E=768, d=1024, P=10, K=40, H=8, L=8),
+                                    R.Gpt2Cfg(), px, EL, STOP)
+    t, l, _ = full["lm"].generate(full["prefix"], "greedy", 1, EL, 1.0, STOP)
+    exact, flips = check_tokens_against_oracle(t[rows], l[rows], oracle, margin_tol=5e-3)
+    assert exact >= len(rows) - 1, (exact, flips)
+
+
+def test_beam5_full_shard(full):
+    """configs[3] per-GPU shard: 256 images x 5 beams in one call; deterministic, batch invariant, best beam of a row equal
+    to the oracle's generate_beam(beam_size=5) on that image alone."""
+    lm, prefix = full["lm"], full["prefix"]
+    t1, l1, s1 = lm.generate(prefix, "beam", 5, EL, 1.0, STOP)
+    t2, l2, s2 = lm.generate(prefix, "beam", 5, EL, 1.0, STOP)
+    assert torch.equal(t1, t2) and torch.equal(l1, l2) and torch.equal(s1, s2)
+    ts, ls, ss = lm.generate(prefix[7:11].contiguous(), "beam", 5, EL, 1.0, STOP)
+    assert torch.equal(ts, t1[7:11]) and torch.equal(ls, l1[7:11])
+    assert rel_err(ss, s1[7:11]) < 1e-5
+    st = full["state"]
+    i = 9
+    pre_cpu = R.mapper_forward(st["mapper"], R.vit_encode(st["vit"], full["px"][i:i + 1], R.VitCfg()),
+                               R.MapperCfg(E=768, d=1024, P=10, K=40, H=8, L=8))
+    toks, score, trace = R.generate_beam(st["lm"], R.Gpt2Cfg(), pre_cpu, 5, EL, 1.0, STOP)
+    got = t1[i, :int(l1[i])].tolist()
+    if got != toks:  # beam search amplifies near-ties: accept only if the scores are indistinguishable
+        assert abs(float(s1[i]) - score) < 2e-3 * abs(score), (got, toks, float(s1[i]), score)
+    else:
+        assert abs(float(s1[i]) - score) < 2e-3 * abs(score)
+
+
+def test_stop_token_truncates_at_full_size(full):
+    """Pick the token a row emits at step 3 as the stop token: that row's caption must end there (stop token included,
+    base.py:119-125) while rows that never emit it run to entry_length."""
+    lm, prefix = full["lm"], full["prefix"][:32].contiguous()
+    t, l, _ = lm.generate(prefix, "greedy", 1, EL, 1.0, STOP)
+    stop = int(t[5, 3])
+    t2, l2, _ = lm.generate(prefix, "greedy", 1, EL, 1.0, stop)
+    for i in range(32):
+        row = t[i].tolist()
+        want = row.index(stop) + 1 if stop in row else EL
+        assert int(l2[i]) == want, i
+        assert t2[i, :want].tolist() == row[:want]
