@@ -76,3 +76,53 @@ def test_get_encoder_errors():
     import clipcap_b200 as clipcap
     with pytest.raises(ValueError, match="invalid encoder name"):
         clipcap.get_encoder("nope", "x")
+
+
+def test_windowed_sequence(cuda_device):
+    """use_windowed_embeddings=True end to end (clipcap/encoders/clip.py:112-129 flatten/unflatten + TransformerMapperWindowed,
+    mapper.py:133-160, window_size passed as W+1, model.py:28): [B, W+1, 3, S, S] pixels -> [B, W+1, E] -> prefix -> beam."""
+    from clipcap_b200.encoders.clip import CLIPModel, ViTImageTower
+    from clipcap_b200.encoders.config import EncoderConfig
+    from clipcap_b200.inference.base import generate_beam_tokens
+    from clipcap_b200.model import ClipCapModelPrefixOnly, Config
+    gcfg = R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64)
+    W = 3  # window_size 2 -> W + 1 = 3 windows per sample (global view + 2 tiles)
+    mcfg = R.MapperCfg(kind="windowed", E=64, d=128, P=2, K=5, H=2, L=2, W=W, use_pos=True)
+    vcfg = R.VitCfg(image_size=28, patch=14, width=128, layers=2, heads=2, mlp_dim=512, out_dim=64)
+    map_w, lm_w, vit_w = synth.mapper_weights(mcfg), synth.gpt2_weights(gcfg, wte_std=0.1), synth.vit_weights(vcfg)
+    cfg = Config(language_model="tiny:128:2:2:1003:64", prefix_length=5, projection_length=2, transformer_layers=2,
+                 transformer_attention_heads=2, use_positional_embeddings=True,
+                 encoder_config=EncoderConfig(encoder_embedding_size=64, use_windowed_embeddings=True, window_size=W - 1))
+    model = ClipCapModelPrefixOnly(cfg)
+    sd = {f"transformer_mapper.{k}": v for k, v in map_w.items()}
+    sd.update({f"language_model.{k}": v for k, v in lm_w.items()})
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().to("cuda")
+    tower = ViTImageTower(vcfg.image_size, vcfg.patch, vcfg.width, vcfg.layers, vcfg.heads, vcfg.out_dim, vcfg.mlp_dim)
+    tower.load_state_dict(vit_w, strict=True)
+    encode_fn = CLIPModel(tower, normalize_embeddings=True, use_windowed_embeddings=True).eval().to("cuda")
+
+    B = 2
+    px = synth.pixels(B * W, vcfg.image_size).view(B, W, 3, vcfg.image_size, vcfg.image_size)
+    emb_ref = R.vit_encode(vit_w, px.flatten(0, 1), vcfg, normalize=True).view(B, W, -1)
+    prefix_ref = R.mapper_forward(map_w, emb_ref, mcfg)
+    emb = encode_fn(px.to("cuda"))
+    assert tuple(emb.shape) == (B, W, 64) and rel_err(emb, emb_ref) < 1e-3
+    prefix = model.transformer_mapper(emb)
+    assert tuple(prefix.shape) == (B, 5, 128) and rel_err(prefix, prefix_ref) < 2e-3
+    toks, lens, _ = generate_beam_tokens(model, prefix, beam_size=1, entry_length=8, stop_token=1002)
+    oracle = R.generate_greedy_batch(lm_w, gcfg, prefix_ref, 8, 1002)
+    exact, _ = check_tokens_against_oracle(toks, lens, oracle, margin_tol=5e-3)
+    assert exact >= B - 1
+
+
+def test_windowed_mapper_reference_size(cuda_device):
+    """The reference's default windowed shape: 16 windows + the global view (W+1 = 17), P=10, K=40 -> 210 tokens, d=1024."""
+    from clipcap_b200.engine import MapperEngine
+    cfg = R.MapperCfg(kind="windowed", E=768, d=1024, P=10, K=40, H=8, L=2, W=17, use_pos=True)
+    w = synth.mapper_weights(cfg, 3)
+    emb = synth.embeddings(2 * 17, 768, seed=8).view(2, 17, 768)
+    ref = R.mapper_forward(w, emb, cfg)
+    eng = MapperEngine(w, kind="windowed", E=768, d=1024, P=10, K=40, H=8, L=2, W=17, use_pos=True, max_batch=2,
+                       device=cuda_device)
+    assert rel_err(eng.forward(emb.to(cuda_device)), ref) < 1e-3
