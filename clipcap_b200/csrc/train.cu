@@ -42,7 +42,9 @@ struct cc_train {
   __half *emb16 = nullptr, *ln16 = nullptr, *hid16 = nullptr, *g16 = nullptr, *dbig16 = nullptr, *dqkv16 = nullptr,
          *datt16 = nullptr, *lnf16 = nullptr, *dlogits16 = nullptr, *tr_a = nullptr, *tr_b = nullptr, *dlin16 = nullptr;
   float *hm = nullptr, *h = nullptr, *dh = nullptr, *dln32 = nullptr, *hsel = nullptr, *dhsel = nullptr, *logits = nullptr,
-        *dlnf32 = nullptr, *row_loss = nullptr, *loss = nullptr, *ln_scratch = nullptr, *wqkv_grad = nullptr;
+        *dlnf32 = nullptr, *row_loss = nullptr, *loss = nullptr, *ln_scratch = nullptr, *wqkv_grad = nullptr,
+        *cs_scratch = nullptr;
+  size_t cs_floats = 0;
   int32_t *tokens = nullptr, *targets = nullptr;
   int* n_valid = nullptr;
   int launches = 0;
@@ -191,7 +193,14 @@ int train_build(cc_train* t, const cc_tensor* w, int nw) {
   CC_TRY(A.alloc_t(&t->n_valid, 1));
   CC_TRY(A.alloc_t(&t->tokens, rs));
   CC_TRY(A.alloc_t(&t->targets, rs));
-  CC_TRY(A.alloc_t(&t->ln_scratch, ln_bwd_scratch_floats(d) + 2 * static_cast<size_t>(d)));
+  CC_TRY(A.alloc_t(&t->ln_scratch, ln_bwd_scratch_floats(d)));
+  {
+    int widest = 2 * d;
+    if (mc.K * d > widest) widest = mc.K * d;
+    if (mc.P * d > widest) widest = mc.P * d;
+    t->cs_floats = colsum_scratch_floats(widest);
+    CC_TRY(A.alloc_t(&t->cs_scratch, t->cs_floats));
+  }
   // transposed operands of the weight-gradient GEMMs: dY^T up to [max(3d, P*d), rows] and X^T up to [max(2d, E), rows]
   size_t a_rows = 3 * static_cast<size_t>(d), b_rows = 2 * static_cast<size_t>(d);
   size_t a_elems = a_rows * rows_pad, b_elems = b_rows * rows_pad;
@@ -439,14 +448,14 @@ int cc_train_step(cc_train* t, const cc_tensor* params, int n_params, const cc_t
     const MapParams& g = mg[l];
     // ---- MLP branch
     CC_TRY(convert_to_f16_run(dhm, CC_F32, t->g16, n_m, s));
-    CC_TRY(colsum_f32_run(dhm, d, rows_m, d, inv_scale, const_cast<float*>(g.f2b), s));
+    CC_TRY(colsum_f32_run(dhm, d, rows_m, d, inv_scale, const_cast<float*>(g.f2b), t->cs_scratch, t->cs_floats, s));
     CC_TRY(transpose16_run(t->g16, d, rows_m, d, t->tr_a, mp_rows, s));
     CC_TRY(transpose16_run(M.hid, 2 * d, rows_m, 2 * d, t->tr_b, mp_rows, s));
     CC_TRY(gemm(t->tr_a, mp_rows, d, t->tr_b, 2 * d, mp_rows, EPI_F32, nullptr, const_cast<float*>(g.f2w), 2 * d, s, nl));
     CC_TRY(scale_f32_run(const_cast<float*>(g.f2w), 2 * dd, inv_scale, s));
     CC_TRY(gemm(t->g16, d, rows_m, M.w2_t, 2 * d, d, EPI_F16_NONE, nullptr, t->dbig16, 2 * d, s, nl));
     CC_TRY(relu_bwd_run(t->dbig16, M.hid, static_cast<int64_t>(rows_m) * 2 * d, s));
-    CC_TRY(colsum_f16_run(t->dbig16, 2 * d, rows_m, 2 * d, inv_scale, const_cast<float*>(g.f1b), s));
+    CC_TRY(colsum_f16_run(t->dbig16, 2 * d, rows_m, 2 * d, inv_scale, const_cast<float*>(g.f1b), t->cs_scratch, t->cs_floats, s));
     CC_TRY(layernorm_run(M.hmid, d, w.n2_g, w.n2_b, t->ln16, d, rows_m, d, mc.eps, s));  // LN2 output, recomputed
     CC_TRY(transpose16_run(t->dbig16, 2 * d, rows_m, 2 * d, t->tr_a, mp_rows, s));
     CC_TRY(transpose16_run(t->ln16, d, rows_m, d, t->tr_b, mp_rows, s));
@@ -457,7 +466,7 @@ int cc_train_step(cc_train* t, const cc_tensor* params, int n_params, const cc_t
                              const_cast<float*>(g.n2_b), inv_scale, t->ln_scratch, s));
     // ---- attention branch
     CC_TRY(convert_to_f16_run(dhm, CC_F32, t->g16, n_m, s));
-    CC_TRY(colsum_f32_run(dhm, d, rows_m, d, inv_scale, const_cast<float*>(g.bp), s));
+    CC_TRY(colsum_f32_run(dhm, d, rows_m, d, inv_scale, const_cast<float*>(g.bp), t->cs_scratch, t->cs_floats, s));
     CC_TRY(transpose16_run(t->g16, d, rows_m, d, t->tr_a, mp_rows, s));
     CC_TRY(transpose16_run(M.att, d, rows_m, d, t->tr_b, mp_rows, s));
     CC_TRY(gemm(t->tr_a, mp_rows, d, t->tr_b, d, mp_rows, EPI_F32, nullptr, const_cast<float*>(g.wp), d, s, nl));
@@ -479,8 +488,8 @@ int cc_train_step(cc_train* t, const cc_tensor* params, int n_params, const cc_t
     *nl += 26;
   }
   // ---- inputs of the transformer: x = cat(linear(emb).view(B, P, d), prefix_const)   (mapper.py:123-126)
-  CC_TRY(colsum_f32_run(dhm + static_cast<size_t>(P) * d, static_cast<int64_t>(S) * d, B, K * d, inv_scale, g_pc, s));
-  CC_TRY(colsum_f32_run(dhm, static_cast<int64_t>(S) * d, B, P * d, inv_scale, gl_b, s));
+  CC_TRY(colsum_f32_run(dhm + static_cast<size_t>(P) * d, static_cast<int64_t>(S) * d, B, K * d, inv_scale, g_pc, t->cs_scratch, t->cs_floats, s));
+  CC_TRY(colsum_f32_run(dhm, static_cast<int64_t>(S) * d, B, P * d, inv_scale, gl_b, t->cs_scratch, t->cs_floats, s));
   CC_TRY(convert_from_f32_run(dhm, static_cast<int64_t>(S) * d, t->dlin16, CC_F16, B, P * d, s));
   const int bp_rows = (B + 7) / 8 * 8;
   CC_TRY(transpose16_run(t->dlin16, static_cast<int64_t>(P) * d, B, P * d, t->tr_a, bp_rows, s));

@@ -8,9 +8,14 @@ namespace cc {
 // dst[c][r] = src[r][c] for r < rows, c < cols; dst columns rows .. ld_dst-1 are zeroed (ld_dst % 8 == 0): the
 // MN-major -> K-major turn that makes a weight gradient dW = dY^T X a TN GEMM over the token dimension.
 int transpose16_run(const __half* src, int64_t ld, int rows, int cols, __half* dst, int64_t ld_dst, cudaStream_t s);
-// out[c] = alpha * sum_r x[r * ld + c]   (bias / prefix_const gradients; fixed summation order)
-int colsum_f32_run(const float* x, int64_t ld, int rows, int cols, float alpha, float* out, cudaStream_t s);
-int colsum_f16_run(const __half* x, int64_t ld, int rows, int cols, float alpha, float* out, cudaStream_t s);
+// out[c] = alpha * sum_r x[r * ld + c]   (bias / prefix_const gradients; two stages in a fixed summation order).
+// `scratch` holds the per-slice partial sums: colsum_scratch_floats(cols) floats are always enough, fewer just mean fewer
+// slices (at least `cols`).
+size_t colsum_scratch_floats(int max_cols);
+int colsum_f32_run(const float* x, int64_t ld, int rows, int cols, float alpha, float* out, float* scratch,
+                   size_t scratch_floats, cudaStream_t s);
+int colsum_f16_run(const __half* x, int64_t ld, int rows, int cols, float alpha, float* out, float* scratch,
+                   size_t scratch_floats, cudaStream_t s);
 // x[i] *= alpha
 int scale_f32_run(float* x, int64_t n, float alpha, cudaStream_t s);
 

@@ -640,33 +640,32 @@ int transpose16_run(const __half* src, int64_t ld, int rows, int cols, __half* d
 
 namespace {
 constexpr int COLSUM_MAX_SLICES = 64;
-float* g_colsum_scratch = nullptr;  // per process: [COLSUM_MAX_SLICES][cols] partial sums, grown on demand
-size_t g_colsum_floats = 0;
 template <typename T>
-int colsum_run(const T* x, int64_t ld, int rows, int cols, float alpha, float* out, cudaStream_t s) {
+int colsum_run(const T* x, int64_t ld, int rows, int cols, float alpha, float* out, float* scratch, size_t scratch_floats,
+               cudaStream_t s) {
   CC_REQUIRE(rows > 0 && cols > 0, CC_ESHAPE, "colsum: rows=%d cols=%d", rows, cols);
+  CC_REQUIRE(scratch != nullptr && scratch_floats >= static_cast<size_t>(cols), CC_EINVAL,
+             "colsum: scratch of %zu floats cannot hold one slice of %d columns", scratch_floats, cols);
   int slices = std::min(COLSUM_MAX_SLICES, (rows + 63) / 64);
+  slices = std::min<size_t>(slices, scratch_floats / cols);
   const int per = (rows + slices - 1) / slices;
   slices = (rows + per - 1) / per;
-  const size_t need = static_cast<size_t>(slices) * cols;
-  if (need > g_colsum_floats) {
-    // stream-ordered growth: earlier launches still own the old block until the stream reaches this point
-    if (g_colsum_scratch) CC_CUDA(cudaFreeAsync(g_colsum_scratch, s));
-    CC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&g_colsum_scratch), need * sizeof(float), s));
-    g_colsum_floats = need;
-  }
-  colsum_partial_kernel<T><<<dim3((cols + 31) / 32, slices), dim3(32, 8), 0, s>>>(x, ld, rows, cols, per, g_colsum_scratch);
-  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, s>>>(g_colsum_scratch, slices, cols, alpha, out);
+  colsum_partial_kernel<T><<<dim3((cols + 31) / 32, slices), dim3(32, 8), 0, s>>>(x, ld, rows, cols, per, scratch);
+  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, s>>>(scratch, slices, cols, alpha, out);
   CC_CUDA(cudaGetLastError());
   return CC_OK;
 }
 }  // namespace
 
-int colsum_f32_run(const float* x, int64_t ld, int rows, int cols, float alpha, float* out, cudaStream_t s) {
-  return colsum_run<float>(x, ld, rows, cols, alpha, out, s);
+size_t colsum_scratch_floats(int max_cols) { return static_cast<size_t>(COLSUM_MAX_SLICES) * max_cols; }
+
+int colsum_f32_run(const float* x, int64_t ld, int rows, int cols, float alpha, float* out, float* scratch,
+                   size_t scratch_floats, cudaStream_t s) {
+  return colsum_run<float>(x, ld, rows, cols, alpha, out, scratch, scratch_floats, s);
 }
-int colsum_f16_run(const __half* x, int64_t ld, int rows, int cols, float alpha, float* out, cudaStream_t s) {
-  return colsum_run<__half>(x, ld, rows, cols, alpha, out, s);
+int colsum_f16_run(const __half* x, int64_t ld, int rows, int cols, float alpha, float* out, float* scratch,
+                   size_t scratch_floats, cudaStream_t s) {
+  return colsum_run<__half>(x, ld, rows, cols, alpha, out, scratch, scratch_floats, s);
 }
 
 int scale_f32_run(float* x, int64_t n, float alpha, cudaStream_t s) {
@@ -698,7 +697,9 @@ int relu_bwd_run(__half* dhid, const __half* hid, int64_t n, cudaStream_t s) {
   return CC_OK;
 }
 
-size_t ln_bwd_scratch_floats(int d) { return static_cast<size_t>(LNB_MAX_BLOCKS) * 2 * d; }
+size_t ln_bwd_scratch_floats(int d) {  // block partials [LNB_MAX_BLOCKS][2d] + result [2d] + column-sum slices
+  return static_cast<size_t>(LNB_MAX_BLOCKS) * 2 * d + 2 * static_cast<size_t>(d) + colsum_scratch_floats(2 * d);
+}
 
 int layernorm_bwd_run(const float* dy, int64_t dy_ld, const float* x, int64_t x_ld, const float* gamma, float* dx_accum,
                       int64_t dx_ld, int rows, int d, float eps, float* dgamma, float* dbeta, float alpha,
@@ -733,8 +734,8 @@ int layernorm_bwd_run(const float* dy, int64_t dy_ld, const float* x, int64_t x_
   CC_CUDA(cudaGetLastError());
   if (param) {
     // scratch is [grid][2][d]: one column sum over the blocks gives dgamma (first d columns) and dbeta (last d)
-    float* both = scratch + static_cast<size_t>(grid) * 2 * d;  // tail of the scratch area: [2][d]
-    CC_TRY(colsum_f32_run(scratch, 2 * d, grid, 2 * d, alpha, both, s));
+    float* both = scratch + static_cast<size_t>(LNB_MAX_BLOCKS) * 2 * d;  // [2][d] result, then the column-sum slices
+    CC_TRY(colsum_f32_run(scratch, 2 * d, grid, 2 * d, alpha, both, both + 2 * d, colsum_scratch_floats(2 * d), s));
     CC_CUDA(cudaMemcpyAsync(dgamma, both, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
     CC_CUDA(cudaMemcpyAsync(dbeta, both + d, sizeof(float) * d, cudaMemcpyDeviceToDevice, s));
   }
