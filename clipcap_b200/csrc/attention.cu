@@ -14,6 +14,7 @@
 #include <cstdlib>
 
 #include "common.h"
+#include "decode.h"
 #include "ptx.cuh"
 
 namespace cc {
@@ -362,6 +363,137 @@ decode_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, 
   }
 }
 
+// Beam search: the `beam` sequences of one image share their whole prefix — positions 0 .. shared_len-1 live in ONE cache
+// slot (the image's prefill slot, decode.cu beam_init / beam_step) — so one CTA takes an (image, head) with one warp per
+// beam: the shared K / V rows are pulled into shared memory once with two bulk copies (instead of once per beam from
+// L2 / HBM), the few generated positions come through the ancestry table as in decode_attn_kernel. The chunks are walked
+// from the newest key down, so the ancestry loads are in flight while the bulk copy lands. Same lane layout and
+// online-softmax arithmetic per row as decode_attn_kernel (the summation order over chunks differs).
+__global__ void __launch_bounds__(kMaxBeam * 32)
+decode_attn_beam_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, __half* __restrict__ vcache,
+                        const int32_t* __restrict__ anc, __half* __restrict__ o, int beam, int H, int t_max, int pos,
+                        int shared_len, float scale_log2) {
+  extern __shared__ __align__(128) uint8_t bsm[];
+  __shared__ __align__(8) unsigned long long bbar;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.x / H, h = blockIdx.x % H;
+  const uint32_t bar = smem_u32(&bbar);
+  const uint32_t kbuf = smem_u32(bsm), vbuf = kbuf + shared_len * 128;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
+  const int d = H * 64;
+  const int seq = img * beam + warp;  // warp == beam index (blockDim.x == beam * 32)
+  const int kq = lane >> 3;
+  const int c = lane & 7;
+  const int32_t* arow = anc + static_cast<long long>(seq) * t_max;
+  if (threadIdx.x == 0 && shared_len > 0) {
+    const long long src = ((static_cast<long long>(arow[0]) * H + h) * t_max) * 64;  // slot of position 0 = the shared slot
+    mbar_arrive_expect_tx(bar, 2u * shared_len * 128u);
+    bulk_load(kbuf, kcache + src, shared_len * 128u, bar);
+    bulk_load(vbuf, vcache + src, shared_len * 128u, bar);
+  }
+  const __half* qrow = qkv + static_cast<long long>(seq) * 3 * d + h * 64;
+  const uint4 knew = *reinterpret_cast<const uint4*>(qrow + d + c * 8);
+  const uint4 vnew = *reinterpret_cast<const uint4*>(qrow + 2 * d + c * 8);
+  {  // append this step's k, v to the row's own slot
+    const long long dst = ((static_cast<long long>(seq) * H + h) * t_max + pos) * 64 + c * 8;
+    if (kq == 0) *reinterpret_cast<uint4*>(kcache + dst) = knew;
+    else if (kq == 1) *reinterpret_cast<uint4*>(vcache + dst) = vnew;
+  }
+  float qf[8];
+  unpack8(*reinterpret_cast<const uint4*>(qrow + c * 8), qf);
+  const int T = pos + 1;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  float mx = -INFINITY, lsum = 0.f;
+  bool landed = shared_len == 0;
+
+  for (int t0 = ((T - 1) / DEC_KEYS) * DEC_KEYS; t0 >= 0; t0 -= DEC_KEYS) {
+    if (!landed && t0 < shared_len) {  // warp-uniform: first chunk that needs the shared rows
+      mbar_wait(bar, 0);
+      landed = true;
+    }
+    uint4 kk[4], vv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int tt = t0 + 4 * j + kq;
+      if (tt < shared_len) {
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(kk[j].x), "=r"(kk[j].y), "=r"(kk[j].z), "=r"(kk[j].w)
+                     : "r"(kbuf + tt * 128 + c * 16));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(vv[j].x), "=r"(vv[j].y), "=r"(vv[j].z), "=r"(vv[j].w)
+                     : "r"(vbuf + tt * 128 + c * 16));
+      } else if (tt < pos) {
+        const long long base = ((static_cast<long long>(arow[tt]) * H + h) * t_max + tt) * 64 + c * 8;
+        kk[j] = *reinterpret_cast<const uint4*>(kcache + base);
+        vv[j] = *reinterpret_cast<const uint4*>(vcache + base);
+      } else if (tt == pos) {
+        kk[j] = knew;
+        vv[j] = vnew;
+      } else {
+        kk[j] = make_uint4(0u, 0u, 0u, 0u);
+        vv[j] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    float dot[4];
+    float bm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float kf[8];
+      unpack8(kk[j], kf);
+      float dd = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dd += qf[i] * kf[i];
+      dd += __shfl_xor_sync(0xffffffffu, dd, 1);
+      dd += __shfl_xor_sync(0xffffffffu, dd, 2);
+      dd += __shfl_xor_sync(0xffffffffu, dd, 4);
+      dot[j] = (t0 + 4 * j + kq < T) ? dd : -INFINITY;
+      bm = fmaxf(bm, dot[j]);
+    }
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+    const float nm = fmaxf(mx, bm);  // finite: every chunk visited holds at least one valid key
+    const float corr = exp2f((mx - nm) * scale_log2);
+    mx = nm;
+    lsum *= corr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= corr;
+    const float nms = nm * scale_log2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float p = exp2f(dot[j] * scale_log2 - nms);
+      lsum += p;
+      float vf[8];
+      unpack8(vv[j], vf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += p * vf[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+  lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+  if (kq == 0) {
+    const float inv = 1.f / lsum;
+    uint4 out;
+    out.x = pack_half2(acc[0] * inv, acc[1] * inv);
+    out.y = pack_half2(acc[2] * inv, acc[3] * inv);
+    out.z = pack_half2(acc[4] * inv, acc[5] * inv);
+    out.w = pack_half2(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(o + static_cast<long long>(seq) * d + h * 64 + c * 8) = out;
+  }
+}
+
 // Greedy decode (no ancestry table): the keys and values of one (sequence, head) are contiguous in the cache, so each
 // warp pulls them into shared memory with two bulk copies (all bytes in flight at once, completion on the warp's own
 // mbarrier) instead of walking them 16 keys per round trip. Same arithmetic and lane layout as decode_attn_kernel.
@@ -534,10 +666,29 @@ int attention_run(const __half* q, const __half* k, const __half* v, int64_t ld,
 }
 
 int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, const int32_t* anc, __half* o, int nseq,
-                         int H, int t_max, int pos, float scale, cudaStream_t s) {
+                         int H, int t_max, int pos, float scale, cudaStream_t s, int beam, int shared_len) {
   CC_REQUIRE(pos >= 0 && pos < t_max, CC_ESHAPE, "decode attention: position %d outside cache (t_max %d)", pos, t_max);
   const int pairs = nseq * H;
   const int grid = (pairs + DEC_WARPS - 1) / DEC_WARPS;
+  if (anc != nullptr && beam > 1 && beam <= kMaxBeam && nseq % beam == 0 && shared_len > 0 && shared_len <= pos &&
+      static_cast<size_t>(shared_len) * 256 <= 64 * 1024) {
+    // beams of an image share the cache rows of positions 0 .. shared_len-1: one CTA per (image, head), warp per beam
+    static const bool off = [] {
+      const char* e = getenv("CLIPCAP_B200_NO_BEAM_ATTN");
+      return e != nullptr && e[0] == '1';
+    }();
+    if (!off) {
+      static bool configured = false;
+      if (!configured) {
+        CC_CUDA(cudaFuncSetAttribute(decode_attn_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        configured = true;
+      }
+      CC_CUDA(launch_pdl(decode_attn_beam_kernel, dim3((nseq / beam) * H), dim3(beam * 32),
+                         static_cast<size_t>(shared_len) * 256, s, qkv, kcache, vcache, anc, o, beam, H, t_max, pos,
+                         shared_len, scale * 1.4426950408889634f));
+      return CC_OK;
+    }
+  }
   // bulk-copy variant: no ancestry indirection, cache rows 16-byte aligned, staging fits beside two other CTAs
   const size_t bulk_smem = static_cast<size_t>(DEC_WARPS) * 2 * pos * 128;  // the pos cached rows of K and V per warp
   if (anc == nullptr && bulk_smem <= 72 * 1024) {

@@ -194,8 +194,10 @@ constexpr int kVitAttnTokens = 257;
 // KV cache: [layer][k|v][slot][head][t_max][64] fp16. Decode step: append this step's k,v (from qkv[nseq,3d]) at position
 // `pos` of slot `seq`, then attend over positions 0..pos, position t being read from slot anc[seq*t_max + t]
 // (anc == nullptr: the sequence's own slot).
+// beam > 1 (with anc): rows seq = img * beam + b belong to one image and positions 0 .. shared_len-1 of all of them live
+// in one cache slot (the prefix): those rows are loaded once per image.
 int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, const int32_t* anc, __half* o, int nseq,
-                         int H, int t_max, int pos, float scale, cudaStream_t s);
+                         int H, int t_max, int pos, float scale, cudaStream_t s, int beam = 1, int shared_len = 0);
 // Prefill: scatter k,v of [nseq*T, 3d] into the cache at positions pos0 .. pos0+T-1 of slot seq*slot_stride.
 int kv_scatter_run(const __half* qkv, __half* kcache, __half* vcache, int nseq, int T, int H, int t_max, int pos0,
                    int slot_stride, cudaStream_t s);
@@ -280,7 +282,9 @@ struct Stack {
   int layer_full(int l, int B, int S, KvCache* kv, int slot_stride, cudaStream_t s);
   // One decode step of layer l for nseq single-row sequences at cache position pos.
   // row0 > 0 (greedy only, anc == nullptr): the rows row0 .. row0 + nseq - 1, an independent group on its own stream.
-  int layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int pos, cudaStream_t s, int row0 = 0);
+  // beam / shared_len: rows per image and length of their common prefix when `anc` is given (beam search).
+  int layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int pos, cudaStream_t s, int row0 = 0, int beam = 1,
+                   int shared_len = 0);
 };
 
 }  // namespace cc

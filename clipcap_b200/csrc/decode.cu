@@ -10,7 +10,6 @@
 namespace cc {
 namespace {
 
-constexpr int TOPK_THREADS = 256;
 
 __global__ void gen_reset_kernel(int32_t* stopped, int32_t* lengths, unsigned long long* keys, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -48,7 +47,7 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) { retur
 
 // One CTA per sequence row: lp = log(softmax(logits / T)) (base.py:83-84) and the row's `beam` best (value, token).
 // Stopped rows contribute the single candidate (0, token 0) (base.py:96-97).
-template <int BEAM_MAX>
+template <int BEAM_MAX, int TOPK_THREADS>
 __global__ void __launch_bounds__(TOPK_THREADS)
 row_topk_kernel(const float* __restrict__ logits, long long ldl, int V, float inv_temp, int beam,
                 const int32_t* __restrict__ stopped, float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
@@ -73,10 +72,17 @@ row_topk_kernel(const float* __restrict__ logits, long long ldl, int V, float in
   Cand top[BEAM_MAX];
 #pragma unroll
   for (int k = 0; k < BEAM_MAX; ++k) top[k] = Cand{-INFINITY, 0x7fffffff};
-  float m = -INFINITY;
-  for (int c = tid; c < V; c += TOPK_THREADS) {
-    const float v = x[c] * inv_temp;
-    m = fmaxf(m, v);
+  // One pass over the row (it is read from HBM exactly once): per-thread running max / rescaled sum of exponentials
+  // (online softmax) and the thread's sorted candidate list; 16-byte loads when the row allows.
+  float m = -INFINITY, sum = 0.f;
+  auto visit = [&](float raw, int c) {
+    const float v = raw * inv_temp;
+    if (v > m) {
+      sum = sum * __expf(m - v) + 1.f;  // exp(-inf) = 0 on the first element
+      m = v;
+    } else {
+      sum += __expf(v - m);
+    }
     if (better(v, c, top[BEAM_MAX - 1].v, top[BEAM_MAX - 1].i)) {
       top[BEAM_MAX - 1] = Cand{v, c};
 #pragma unroll
@@ -88,10 +94,26 @@ row_topk_kernel(const float* __restrict__ logits, long long ldl, int V, float in
         }
       }
     }
+  };
+  int c_tail = 0;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int n4 = V >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (int c4 = tid; c4 < n4; c4 += TOPK_THREADS) {
+      const float4 q = __ldcs(x4 + c4);  // streamed: the logits are dead after this kernel
+      visit(q.x, 4 * c4);
+      visit(q.y, 4 * c4 + 1);
+      visit(q.z, 4 * c4 + 2);
+      visit(q.w, 4 * c4 + 3);
+    }
+    c_tail = n4 << 2;
   }
+  for (int c = c_tail + tid; c < V; c += TOPK_THREADS) visit(x[c], c);
+  // block-wide max, then the sums rescaled to it
+  float gm = m;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if (lane == 0) s_red[warp] = m;
+  for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+  if (lane == 0) s_red[warp] = gm;
   __syncthreads();
   if (tid == 0) {
     float mm = s_red[0];
@@ -99,9 +121,9 @@ row_topk_kernel(const float* __restrict__ logits, long long ldl, int V, float in
     s_m = mm;
   }
   __syncthreads();
-  m = s_m;
-  float sum = 0.f;
-  for (int c = tid; c < V; c += TOPK_THREADS) sum += expf(x[c] * inv_temp - m);
+  gm = s_m;
+  sum = m == -INFINITY ? 0.f : sum * __expf(m - gm);
+  m = gm;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   __syncthreads();
@@ -303,7 +325,12 @@ int greedy_select_run(unsigned long long* keys, int32_t* tokens, int entry_len, 
 int row_topk_run(const float* logits, int64_t ldl, int V, float inv_temp, int beam, const int32_t* stopped,
                  float* out_val, int32_t* out_idx, int rows, cudaStream_t s) {
   CC_REQUIRE(beam >= 1 && beam <= kMaxBeam, CC_ESHAPE, "beam size %d outside 1..%d", beam, kMaxBeam);
-  row_topk_kernel<kMaxBeam><<<rows, TOPK_THREADS, 0, s>>>(logits, ldl, V, inv_temp, beam, stopped, out_val, out_idx);
+  // 256-thread CTAs fit 8 to an SM: from 1185 rows on a second, nearly empty wave would double the time, so big beam
+  // batches run 128-thread CTAs (16 per SM) and the rows spread evenly.
+  if (rows > num_sms() * 8)
+    row_topk_kernel<kMaxBeam, 128><<<rows, 128, 0, s>>>(logits, ldl, V, inv_temp, beam, stopped, out_val, out_idx);
+  else
+    row_topk_kernel<kMaxBeam, 256><<<rows, 256, 0, s>>>(logits, ldl, V, inv_temp, beam, stopped, out_val, out_idx);
   CC_CUDA(cudaGetLastError());
   return CC_OK;
 }

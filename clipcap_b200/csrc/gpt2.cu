@@ -269,7 +269,7 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
     for (int step = 1; step < EL; ++step) {
       const int pos = Tp + step - 1;  // position of the token fed this step
       CC_TRY(gpt2_embed_tokens_run(m->beam.tokens[cur] + (step - 1), EL, m->wte32, m->wpe32, st.h, nseq, d, pos, c.V, s));
-      for (int l = 0; l < c.L; ++l) CC_TRY(st.layer_decode(l, nseq, &m->kv, m->beam.anc[cur], pos, s));
+      for (int l = 0; l < c.L; ++l) CC_TRY(st.layer_decode(l, nseq, &m->kv, m->beam.anc[cur], pos, s, 0, beam, Tp));
       CC_TRY(st.ln_decode(m->lnf_g, m->lnf_b, m->lnf16, nseq, s));  // absorbs the last layer's fc2 partial sums
       CC_TRY(gemm_run(m->p_head_logits, nseq, s));
       CC_TRY(row_topk_run(m->logits, m->v_ld, c.V, inv_temp, beam, m->beam.stopped, m->cand_val, m->cand_idx, nseq, s));

@@ -119,7 +119,8 @@ int Stack::layer_full(int l, int B, int S, KvCache* kv, int slot_stride, cudaStr
   return CC_OK;
 }
 
-int Stack::layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int pos, cudaStream_t s, int row0) {
+int Stack::layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int pos, cudaStream_t s, int row0, int beam,
+                        int shared_len) {
   CC_REQUIRE(row0 + nseq <= max_rows && row0 + nseq <= kv->slots, CC_ESHAPE, "stack: %d sequences exceed handle capacity",
              row0 + nseq);
   CC_REQUIRE(row0 == 0 || anc == nullptr, CC_EINVAL, "stack: row groups need the ancestry-free (greedy) cache layout");
@@ -131,7 +132,7 @@ int Stack::layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int po
   CC_TRY(ln_decode(w.ln1_g, w.ln1_b, ln16, nseq, s, row0));  // absorbs the previous layer's fc2 partial sums
   CC_TRY(gemm_run(p_qkv[l], nseq, s, row0));
   CC_TRY(decode_attention_run(qkv16 + static_cast<size_t>(row0) * 3 * d, kv->k + cache_off, kv->v + cache_off, anc,
-                              att16 + static_cast<size_t>(row0) * d, nseq, H, kv->t_max, pos, scale, s));
+                              att16 + static_cast<size_t>(row0) * d, nseq, H, kv->t_max, pos, scale, s, beam, shared_len));
   CC_TRY(gemm_run(p_o_dec[l], nseq, s, row0));
   pend_splits = p_o_dec[l].splits;
   pend_bias = w.bo;
