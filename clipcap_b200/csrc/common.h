@@ -263,9 +263,17 @@ struct Stack {
   // follows (LN2, the next layer's LN1, or ln_f) folds bias + partial sums into h in a fixed order (deterministic).
   int dec_rows = 0, dec_rows_pad = 0;
   Arena* arena_ = nullptr;  // the owning engine's arena (set by init)
-  float* part = nullptr;  // [max splits][dec_rows_pad][d] fp32
-  std::vector<GemmPlan> p_o_dec, p_2_dec;
+  // Tile shape and split factor depend on how many 128-row blocks a step really has (a handle created for 1280 beam rows
+  // must not run a 256-row greedy step with the 1280-row plan), so the split-K plans are kept per row-block count and
+  // built on first use; split s of a plan lives at part + s * split_rows * d with split_rows = blocks * 128.
+  struct DecPlans {
+    std::vector<GemmPlan> o, p2;
+  };
+  float* part = nullptr;  // fp32 partial sums, sized in plan() for the largest splits * split_rows over all block counts
+  std::vector<DecPlans> dec_plans;  // index = row blocks - 1
+  int dec_plans_for(int blocks, DecPlans** out);
   int pend_splits = 0;  // partial sums waiting in `part` for the next LayerNorm (0 = none)
+  int64_t pend_stride = 0;  // elements between two splits of the pending partial sums
   const float* pend_bias = nullptr;
 
   // ViT-L/14 shape only (tokens per image == kVitAttnTokens, head dim 64): QKV is written head-major and attention

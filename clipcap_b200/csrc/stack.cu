@@ -65,31 +65,57 @@ int Stack::plan() {
     CC_TRY(gemm_plan(&p_2[l], mlp16, dff, max_rows, w.w2, d, dff, EPI_RESID_F32, w.b2, h, d));
   }
   if (dec_rows > 0) {
-    int bn_o, sp_o, bn_2, sp_2;
-    gemm_pick_split(dec_rows, d, d, &bn_o, &sp_o);
-    gemm_pick_split(dec_rows, d, dff, &bn_2, &sp_2);
-    const int sp_max = sp_o > sp_2 ? sp_o : sp_2;
+    const int max_blocks = dec_rows_pad / 128;
+    size_t need = 0;
+    for (int nb = 1; nb <= max_blocks; ++nb) {
+      int bn_o, sp_o, bn_2, sp_2;
+      gemm_pick_split(nb * 128, d, d, &bn_o, &sp_o);
+      gemm_pick_split(nb * 128, d, dff, &bn_2, &sp_2);
+      const size_t n = static_cast<size_t>(sp_o > sp_2 ? sp_o : sp_2) * nb * 128 * d;
+      if (n > need) need = n;
+    }
     // `part` is allocated once per stack; plan() runs once after the layers are filled
-    if (part == nullptr) CC_TRY(arena_->alloc_t(&part, static_cast<size_t>(sp_max) * dec_rows_pad * d));
-    p_o_dec.resize(L);
-    p_2_dec.resize(L);
+    if (part == nullptr) CC_TRY(arena_->alloc_t(&part, need));
+    dec_plans.assign(max_blocks, DecPlans{});
+    DecPlans* unused = nullptr;
+    CC_TRY(dec_plans_for(max_blocks, &unused));  // the capacity plans exist from the start; smaller steps add theirs
+  }
+  return CC_OK;
+}
+
+int Stack::dec_plans_for(int blocks, DecPlans** out) {
+  CC_REQUIRE(blocks >= 1 && blocks <= static_cast<int>(dec_plans.size()), CC_ESHAPE, "stack: %d decode row blocks (max %zu)",
+             blocks, dec_plans.size());
+  DecPlans& dp = dec_plans[blocks - 1];
+  if (dp.o.empty()) {
+    const size_t L = layers.size();
+    const int rows = blocks * 128;
+    int bn_o, sp_o, bn_2, sp_2;
+    gemm_pick_split(rows, d, d, &bn_o, &sp_o);
+    gemm_pick_split(rows, d, dff, &bn_2, &sp_2);
+    std::vector<GemmPlan> po(L), p2(L);
+    const int plan_rows = rows < dec_rows ? rows : dec_rows;
     for (size_t l = 0; l < L; ++l) {
       const LayerW& w = layers[l];
-      CC_TRY(gemm_plan_partial(&p_o_dec[l], att16, d, dec_rows, w.wo, d, d, part, dec_rows_pad, sp_o, bn_o));
-      CC_TRY(gemm_plan_partial(&p_2_dec[l], mlp16, dff, dec_rows, w.w2, d, dff, part, dec_rows_pad, sp_2, bn_2));
+      CC_TRY(gemm_plan_partial(&po[l], att16, d, plan_rows, w.wo, d, d, part, rows, sp_o, bn_o));
+      CC_TRY(gemm_plan_partial(&p2[l], mlp16, dff, plan_rows, w.w2, d, dff, part, rows, sp_2, bn_2));
     }
+    dp.o.swap(po);
+    dp.p2.swap(p2);
   }
+  *out = &dp;
   return CC_OK;
 }
 
 int Stack::ln_decode(const float* g, const float* b, __half* y, int nseq, cudaStream_t s, int row0) {
   const int sp = pend_splits;
   const float* bias = pend_bias;
+  const int64_t stride = pend_stride;
   pend_splits = 0;
   pend_bias = nullptr;
   launches += 1;
   const size_t off = static_cast<size_t>(row0) * d;
-  return layernorm_reduce_run(h + off, d, sp > 0 ? part + off : nullptr, sp, static_cast<int64_t>(dec_rows_pad) * d, bias, g,
+  return layernorm_reduce_run(h + off, d, sp > 0 ? part + off : nullptr, sp, stride, bias, g,
                               b, y + off, d, nseq, d, eps, s);
 }
 
@@ -128,18 +154,22 @@ int Stack::layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int po
   CC_REQUIRE(row0 + nseq <= dec_rows, CC_ESHAPE, "stack: %d sequences exceed the %d decode rows planned", row0 + nseq,
              dec_rows);
   const LayerW& w = layers[l];
+  DecPlans* dp = nullptr;  // plans for this step's row-block count (row groups use the capacity plans: they share `part`)
+  CC_TRY(dec_plans_for(row0 == 0 ? (nseq + 127) / 128 : static_cast<int>(dec_plans.size()), &dp));
   const size_t cache_off = l * kv->layer_elems + static_cast<size_t>(row0) * H * kv->t_max * 64;  // slot == row
   CC_TRY(ln_decode(w.ln1_g, w.ln1_b, ln16, nseq, s, row0));  // absorbs the previous layer's fc2 partial sums
   CC_TRY(gemm_run(p_qkv[l], nseq, s, row0));
   CC_TRY(decode_attention_run(qkv16 + static_cast<size_t>(row0) * 3 * d, kv->k + cache_off, kv->v + cache_off, anc,
                               att16 + static_cast<size_t>(row0) * d, nseq, H, kv->t_max, pos, scale, s, beam, shared_len));
-  CC_TRY(gemm_run(p_o_dec[l], nseq, s, row0));
-  pend_splits = p_o_dec[l].splits;
+  CC_TRY(gemm_run(dp->o[l], nseq, s, row0));
+  pend_splits = dp->o[l].splits;
+  pend_stride = static_cast<int64_t>(dp->o[l].split_rows) * d;
   pend_bias = w.bo;
   CC_TRY(ln_decode(w.ln2_g, w.ln2_b, ln16, nseq, s, row0));
   CC_TRY(gemm_run(p_1[l], nseq, s, row0));
-  CC_TRY(gemm_run(p_2_dec[l], nseq, s, row0));
-  pend_splits = p_2_dec[l].splits;
+  CC_TRY(gemm_run(dp->p2[l], nseq, s, row0));
+  pend_splits = dp->p2[l].splits;
+  pend_stride = static_cast<int64_t>(dp->p2[l].split_rows) * d;
   pend_bias = w.b2;
   launches += 5;
   return CC_OK;
