@@ -83,6 +83,7 @@ PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {
     "cc_op_gemm": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "cc_op_layernorm": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _vp]),
     "cc_op_attention": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp]),
+    "cc_op_skinny_gemm": (_i, [_vp, _vp, _vp, _f, _vp, _i64, _i, _vp, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "cc_op_attention_bwd": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "cc_op_decode_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "cc_op_sample": (_i, [_vp, _i, _i, C.POINTER(cc_gen_cfg), _i, _vp, _vp, _vp, _vp]),

@@ -49,6 +49,15 @@ int cc_op_attention(const void* q, const void* k, const void* v, int64_t ld, voi
                        static_cast<__half*>(o), ldo, B, S, H, hd, causal != 0, scale, static_cast<cudaStream_t>(stream));
 }
 
+int cc_op_skinny_gemm(const float* x32, const float* gamma, const float* beta, float eps, const void* x16, int64_t ldx, int M,
+                      const void* w, int N, int K, int epi, const float* bias, void* out, int64_t ldc, void* stream) {
+  using namespace cc;
+  CC_REQUIRE(w != nullptr && out != nullptr, CC_EINVAL, "cc_op_skinny_gemm: null argument");
+  CC_TRY(check_device_sm100());
+  return skinny_gemm_run(x32, gamma, beta, eps, static_cast<const __half*>(x16), ldx, M, static_cast<const __half*>(w), N, K,
+                         epi, bias, out, ldc, static_cast<cudaStream_t>(stream));
+}
+
 int cc_op_attention_bwd(const void* q, const void* k, const void* v, int64_t ld, const void* d_o, int64_t ldo, void* dq,
                         void* dk, void* dv, int64_t ldd, int B, int S, int H, int hd, int causal, float scale,
                         void* stream) {

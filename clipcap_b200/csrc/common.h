@@ -164,6 +164,16 @@ void gemm_prof_read(double* ms, double* flops, long long* n);
 // pack(acc, n) used by EPI_ARGMAX: high 32 bits = order-preserving float key, low 32 bits = ~n (ties -> lowest index)
 __host__ __device__ inline uint32_t argmax_key_index(unsigned long long key) { return ~static_cast<uint32_t>(key); }
 
+// ------------------------------------------------------------------ skinny GEMM (skinny.cu): M <= 16 rows, weight streaming
+// y[M, N] = X[M, K] W[N, K]^T with X = LayerNorm(x32; gamma, beta, eps) (x32 != nullptr, fp32 rows of stride ldx) or the
+// fp16 rows x16; epilogues EPI_F16_NONE, EPI_F16_GELU_NEW, EPI_RESID_F32 (out += acc + bias), EPI_F32, EPI_ARGMAX.
+// The single-image / small-beam decode step is built from it (Stack::layer_decode, gpt2.cu head).
+constexpr int kSkinnyMaxRows = 16;
+bool skinny_enabled();  // CLIPCAP_B200_NO_SKINNY=1 keeps the tcgen05 path for every row count
+int skinny_gemm_run(const float* x32, const float* gamma, const float* beta, float eps, const __half* x16, int64_t ldx,
+                    int M, const __half* w, int N, int K, int epi, const float* bias, void* out, int64_t ldc,
+                    cudaStream_t s);
+
 // ------------------------------------------------------------------ LayerNorm (fp32 in, fp16 out), row-strided
 int layernorm_run(const float* x, int64_t x_ld, const float* gamma, const float* beta, __half* y, int64_t y_ld, int rows,
                   int d, float eps, cudaStream_t s);
@@ -272,6 +282,8 @@ struct Stack {
   float* part = nullptr;  // fp32 partial sums, sized in plan() for the largest splits * split_rows over all block counts
   std::vector<DecPlans> dec_plans;  // index = row blocks - 1
   int dec_plans_for(int blocks, DecPlans** out);
+  // true when a decode step of nseq rows runs on the skinny kernels (<= 16 rows, no partial sums pending)
+  bool skinny_step(int nseq, int row0) const;
   int pend_splits = 0;  // partial sums waiting in `part` for the next LayerNorm (0 = none)
   int64_t pend_stride = 0;  // elements between two splits of the pending partial sums
   const float* pend_bias = nullptr;

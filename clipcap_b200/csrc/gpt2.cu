@@ -175,6 +175,19 @@ int gpt2_build(cc_gpt2* m, const cc_tensor* w, int nw) {
   return CC_OK;
 }
 
+// ln_f + tied LM head of a decode step: fused-argmax keys (greedy) or fp32 logits (beam / sampling). Up to 16 rows run as
+// one skinny kernel (LayerNorm applied while the rows are staged), otherwise LayerNorm(+reduce) + the tcgen05 head.
+int head_decode(cc_gpt2* m, int nseq, bool keys, cudaStream_t s, int row0 = 0) {
+  Stack& st = m->st;
+  const cc_gpt2_cfg& c = m->cfg;
+  if (st.skinny_step(nseq, row0))
+    return skinny_gemm_run(st.h, m->lnf_g, m->lnf_b, c.eps, nullptr, c.d, nseq, m->wte16, c.V, c.d,
+                           keys ? EPI_ARGMAX : EPI_F32, nullptr, keys ? static_cast<void*>(m->keys) : static_cast<void*>(m->logits),
+                           keys ? 1 : m->v_ld, s);
+  CC_TRY(st.ln_decode(m->lnf_g, m->lnf_b, m->lnf16, nseq, s, row0));  // absorbs the last layer's fc2 partial sums
+  return gemm_run(keys ? m->p_head_keys : m->p_head_logits, nseq, s, row0);
+}
+
 inline float inv_temp_of(const cc_gen_cfg& g) { return 1.0f / (g.temperature > 0.f ? g.temperature : 1.0f); }
 inline int nseq_of(int B, int beam) { return B * beam; }
 
@@ -228,8 +241,7 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
       const int pos = Tp + step - 1;
       CC_TRY(gpt2_embed_tokens_run(m->g_tokens + (step - 1), EL, m->wte32, m->wpe32, st.h, nseq, d, pos, c.V, s));
       for (int l = 0; l < c.L; ++l) CC_TRY(st.layer_decode(l, nseq, &m->kv, nullptr, pos, s));
-      CC_TRY(st.ln_decode(m->lnf_g, m->lnf_b, m->lnf16, nseq, s));
-      CC_TRY(gemm_run(m->p_head_logits, nseq, s));
+      CC_TRY(head_decode(m, nseq, false, s));
       CC_TRY(sample_step(step));
       extra += 4;
     }
@@ -254,8 +266,7 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
         CC_TRY(gpt2_embed_tokens_run(m->g_tokens + static_cast<size_t>(row0) * EL + (step - 1), EL, m->wte32, m->wpe32,
                                      st.h + static_cast<size_t>(row0) * d, n, d, pos, c.V, gs));
         for (int l = 0; l < c.L; ++l) CC_TRY(st.layer_decode(l, n, &m->kv, nullptr, pos, gs, row0));
-        CC_TRY(st.ln_decode(m->lnf_g, m->lnf_b, m->lnf16, n, gs, row0));  // absorbs the last layer's fc2 partial sums
-        CC_TRY(gemm_run(m->p_head_keys, n, gs, row0));
+        CC_TRY(head_decode(m, n, true, gs, row0));
         CC_TRY(greedy_select_run(m->keys + row0, m->g_tokens + static_cast<size_t>(row0) * EL, EL, step,
                                  m->g_stopped + row0, m->g_lengths + row0, g.stop_token, n, gs));
         extra += 3;
@@ -270,8 +281,7 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
       const int pos = Tp + step - 1;  // position of the token fed this step
       CC_TRY(gpt2_embed_tokens_run(m->beam.tokens[cur] + (step - 1), EL, m->wte32, m->wpe32, st.h, nseq, d, pos, c.V, s));
       for (int l = 0; l < c.L; ++l) CC_TRY(st.layer_decode(l, nseq, &m->kv, m->beam.anc[cur], pos, s, 0, beam, Tp));
-      CC_TRY(st.ln_decode(m->lnf_g, m->lnf_b, m->lnf16, nseq, s));  // absorbs the last layer's fc2 partial sums
-      CC_TRY(gemm_run(m->p_head_logits, nseq, s));
+      CC_TRY(head_decode(m, nseq, false, s));
       CC_TRY(row_topk_run(m->logits, m->v_ld, c.V, inv_temp, beam, m->beam.stopped, m->cand_val, m->cand_idx, nseq, s));
       CC_TRY(beam_step_run(m->cand_val, m->cand_idx, m->beam, cur, beam, c.V, EL, m->t_max, step, pos, g.stop_token, B,
                            s));

@@ -107,6 +107,11 @@ int Stack::dec_plans_for(int blocks, DecPlans** out) {
   return CC_OK;
 }
 
+bool Stack::skinny_step(int nseq, int row0) const {
+  return nseq <= kSkinnyMaxRows && row0 == 0 && pend_splits == 0 && act_epi == EPI_F16_GELU_NEW && d % 32 == 0 &&
+         d <= 2048 && dff % 32 == 0 && skinny_enabled();
+}
+
 int Stack::ln_decode(const float* g, const float* b, __half* y, int nseq, cudaStream_t s, int row0) {
   const int sp = pend_splits;
   const float* bias = pend_bias;
@@ -154,6 +159,18 @@ int Stack::layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int po
   CC_REQUIRE(row0 + nseq <= dec_rows, CC_ESHAPE, "stack: %d sequences exceed the %d decode rows planned", row0 + nseq,
              dec_rows);
   const LayerW& w = layers[l];
+  if (skinny_step(nseq, row0)) {
+    // <= 16 rows: five weight-streaming kernels per layer, LayerNorms applied while the rows are staged (skinny.cu)
+    const size_t koff = l * kv->layer_elems;
+    CC_TRY(skinny_gemm_run(h, w.ln1_g, w.ln1_b, eps, nullptr, d, nseq, w.wqkv, 3 * d, d, EPI_F16_NONE, w.bqkv, qkv16, 3 * d, s));
+    CC_TRY(decode_attention_run(qkv16, kv->k + koff, kv->v + koff, anc, att16, nseq, H, kv->t_max, pos, scale, s, beam,
+                                shared_len));
+    CC_TRY(skinny_gemm_run(nullptr, nullptr, nullptr, eps, att16, d, nseq, w.wo, d, d, EPI_RESID_F32, w.bo, h, d, s));
+    CC_TRY(skinny_gemm_run(h, w.ln2_g, w.ln2_b, eps, nullptr, d, nseq, w.w1, dff, d, EPI_F16_GELU_NEW, w.b1, mlp16, dff, s));
+    CC_TRY(skinny_gemm_run(nullptr, nullptr, nullptr, eps, mlp16, dff, nseq, w.w2, d, dff, EPI_RESID_F32, w.b2, h, d, s));
+    launches += 5;
+    return CC_OK;
+  }
   DecPlans* dp = nullptr;  // plans for this step's row-block count (row groups use the capacity plans: they share `part`)
   CC_TRY(dec_plans_for(row0 == 0 ? (nseq + 127) / 128 : static_cast<int>(dec_plans.size()), &dp));
   const size_t cache_off = l * kv->layer_elems + static_cast<size_t>(row0) * H * kv->t_max * 64;  // slot == row

@@ -227,6 +227,12 @@ int cc_op_decode_attention(const void* qkv, void* kcache, void* vcache, const in
 int cc_op_sample(const float* logits, int rows, int V, const cc_gen_cfg* cfg, int step, int32_t* tokens,
                  int32_t* stopped, int32_t* lengths, void* stream);
 
+/* Skinny GEMM of the single-image / small-beam decode step (M <= 16 rows, csrc/skinny.cu):
+ * out[M,N] = X W^T with W [N,K] fp16 and X = LayerNorm(x32; gamma, beta, eps) when x32 != NULL (fp32 rows, stride ldx)
+ * or the fp16 rows x16. epi as for cc_op_gemm: 0 fp16, 3 fp16 gelu_new, 5 fp32, 6 fp32 in-place residual add, 7 argmax keys. */
+int cc_op_skinny_gemm(const float* x32, const float* gamma, const float* beta, float eps, const void* x16, int64_t ldx, int M,
+                      const void* w, int N, int K, int epi, const float* bias, void* out, int64_t ldc, void* stream);
+
 /* Backward of cc_op_attention (training step): given d_o = d loss / d o, writes dq, dk, dv in the layout of q, k, v
  * (row stride ldd). */
 int cc_op_attention_bwd(const void* q, const void* k, const void* v, int64_t ld, const void* d_o, int64_t ldo, void* dq,

@@ -152,3 +152,59 @@ def test_decode_attention(cuda_device, use_anc):
         q = qkv[:, :d].view(nseq, H, 1, 64).float()
         ref = torch.nn.functional.scaled_dot_product_attention(q, kk, vv).reshape(nseq, d)
         assert _rel(o, ref) < ATTN_TOL, (pos, use_anc)
+
+
+@pytest.mark.parametrize("M", [1, 5, 8, 9, 16])
+@pytest.mark.parametrize("shape", [(3072, 1024), (1024, 4096), (50257, 768), (2304, 768), (40, 64), (1000, 1600)])
+def test_skinny_gemm(cuda_device, M, shape):
+    """cc_op_skinny_gemm (decode steps of <= 16 rows): every epilogue, with and without the fused LayerNorm, against fp32
+    torch on the fp16-rounded operands."""
+    from clipcap_b200 import _ffi
+    N, K = shape
+    g = torch.Generator().manual_seed(M * 131 + N)
+    w = (torch.randn(N, K, generator=g) * 0.05).half()
+    bias = torch.randn(N, generator=g) * 0.1
+    x32 = torch.randn(M, K, generator=g) * 2 + 0.3
+    gamma, beta = torch.rand(K, generator=g) + 0.5, torch.randn(K, generator=g) * 0.1
+    wd, bd = w.to(cuda_device), bias.to(cuda_device)
+    lib, S = _ffi.lib(), _ffi.current_stream_ptr
+
+    def run(epi, ln, out, ldc, use_bias=True):
+        if ln:
+            xd, gd, btd = x32.to(cuda_device), gamma.to(cuda_device), beta.to(cuda_device)
+            _ffi.check(lib.cc_op_skinny_gemm(xd.data_ptr(), gd.data_ptr(), btd.data_ptr(), 1e-5, None, K, M, wd.data_ptr(), N, K,
+                                             epi, bd.data_ptr() if use_bias else None, out.data_ptr(), ldc, S()))
+        else:
+            xd = x32.half().to(cuda_device)
+            _ffi.check(lib.cc_op_skinny_gemm(None, None, None, 1e-5, xd.data_ptr(), K, M, wd.data_ptr(), N, K, epi,
+                                             bd.data_ptr() if use_bias else None, out.data_ptr(), ldc, S()))
+        torch.cuda.synchronize()
+
+    x_ln = torch.nn.functional.layer_norm(x32, (K,), gamma, beta, 1e-5).half().float()
+    x_pl = x32.half().float()
+    wf = w.float()
+    for ln, xr in ((True, x_ln), (False, x_pl)):
+        if ln and K > 2048:
+            continue  # the fused LayerNorm holds a row in registers: K <= 2048 (every GPT-2 width); fc2 (K = 4d) has none
+        ref = xr @ wf.t() + bias
+        out16 = torch.zeros(M, N, device=cuda_device, dtype=torch.half)
+        run(0, ln, out16, N)
+        assert _rel(out16.cpu(), ref) < 2e-3
+        run(3, ln, out16, N)
+        gel = 0.5 * ref * (1 + torch.tanh(0.7978845608028654 * (ref + 0.044715 * ref ** 3)))
+        assert _rel(out16.cpu(), gel) < 2e-3
+        ldc = N + 3
+        out32 = torch.full((M, ldc), 7.0, device=cuda_device)
+        run(5, ln, out32, ldc)
+        assert _rel(out32[:, :N].cpu(), ref) < 1e-4 and bool((out32[:, N:] == 7.0).all())
+        res = torch.randn(M, N, generator=g)
+        acc = res.to(cuda_device).contiguous()
+        run(6, ln, acc, N)
+        assert _rel(acc.cpu(), res + ref) < 1e-4
+        keys = torch.zeros(M, device=cuda_device, dtype=torch.int64)
+        run(7, ln, keys, 1, use_bias=False)
+        idx = (~keys.cpu()) & 0xFFFFFFFF
+        best = (xr @ wf.t())
+        top = best.max(dim=1)
+        for m in range(M):  # ties / near-ties: the picked column must hold the row maximum up to rounding
+            assert float(best[m, int(idx[m])]) >= float(top.values[m]) - 1e-4 * max(1.0, abs(float(top.values[m])))
