@@ -22,22 +22,24 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def all_gather_prefix(prefix_local: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
-                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      out: Optional[torch.Tensor] = None, async_op: bool = False):
     """[B_local, K, d] on every rank -> [world * B_local, K, d] on every rank, rank r's block at rows r*B_local.. .
-    Equal shard sizes (weak scaling: B per GPU fixed); a single in-place all-gather (ncclAllGather over NVLink)."""
+    Equal shard sizes (weak scaling: B per GPU fixed); a single in-place all-gather (ncclAllGather over NVLink).
+    async_op=True returns (out, work): the collective runs on the communicator's stream behind the producer of
+    `prefix_local`; `work.wait()` orders the caller's stream after it."""
     if not dist.is_available() or not dist.is_initialized():
-        return prefix_local
+        return (prefix_local, None) if async_op else prefix_local
     world = dist.get_world_size(group)
     if world == 1:
-        return prefix_local
+        return (prefix_local, None) if async_op else prefix_local
     prefix_local = prefix_local.contiguous()
     shape = (world * prefix_local.shape[0],) + tuple(prefix_local.shape[1:])
     if out is None:
         out = torch.empty(shape, dtype=prefix_local.dtype, device=prefix_local.device)
     elif tuple(out.shape) != shape or out.dtype != prefix_local.dtype:
         raise ValueError(f"all_gather_prefix: out must be {shape} {prefix_local.dtype}, got {tuple(out.shape)} {out.dtype}")
-    dist.all_gather_into_tensor(out, prefix_local, group=group)
-    return out
+    work = dist.all_gather_into_tensor(out, prefix_local, group=group, async_op=async_op)
+    return (out, work) if async_op else out
 
 
 def gather_tokens(tokens_local: torch.Tensor, lengths_local: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
@@ -56,14 +58,14 @@ def gather_tokens(tokens_local: torch.Tensor, lengths_local: torch.Tensor, group
 def caption_step(encode_fn, model, pixels_local: torch.Tensor, entry_length: int, stop_token: int,
                  prefix_all: Optional[torch.Tensor] = None, group: Optional[dist.ProcessGroup] = None):
     """One pass of the hot path on this rank's shard: ViT -> mapper -> prefix all-gather -> greedy decode of the local
-    rows. Returns (tokens, lengths, prefix_all)."""
+    rows. Returns (tokens, lengths, prefix_all). Decode reads only this rank's own prefix, so the all-gather runs behind
+    it on the communicator's stream and is joined at the end of the step: a rank never idles waiting for a slower peer's
+    mapper before it may start decoding."""
     from clipcap_b200.inference.base import generate_greedy_tokens
     emb = encode_fn(pixels_local)
     prefix = model.transformer_mapper(emb)
-    gathered = all_gather_prefix(prefix, group, prefix_all)
-    if gathered is not prefix:
-        rank = dist.get_rank(group)
-        b = prefix.shape[0]
-        prefix = gathered[rank * b:(rank + 1) * b]
+    gathered, work = all_gather_prefix(prefix, group, prefix_all, async_op=True)
     tokens, lengths, _ = generate_greedy_tokens(model, prefix, entry_length, stop_token)
+    if work is not None:
+        work.wait()  # the caller's stream now sees the complete [world * B, K, d] tensor
     return tokens, lengths, gathered

@@ -41,6 +41,11 @@ def _worker(rank, world, port, q):
         ok = torch.equal(out, full)                                # multi-rank result == single-rank result, exactly
         pre = torch.empty_like(full)
         ok &= all_gather_prefix(local, out=pre) is pre and torch.equal(pre, full)
+        # asynchronous form (what caption_step uses to run the all-gather behind the decode): same bytes after wait()
+        pre2 = torch.zeros_like(full)
+        got, work = all_gather_prefix(local, out=pre2, async_op=True)
+        work.wait()
+        ok &= got is pre2 and torch.equal(pre2, full)
         toks_full = torch.arange(world * B * EL, dtype=torch.int32).view(world * B, EL)
         lens_full = torch.arange(world * B, dtype=torch.int32)
         toks, lens = gather_tokens(toks_full[lo:hi].clone(), lens_full[lo:hi].clone())
@@ -72,5 +77,7 @@ def test_prefix_all_gather_world2_gloo():
 def test_single_process_is_identity():
     x = torch.randn(2, 3, 4)
     assert all_gather_prefix(x) is x
+    same, work = all_gather_prefix(x, async_op=True)
+    assert same is x and work is None
     t, l = gather_tokens(torch.zeros(2, 5, dtype=torch.int32), torch.zeros(2, dtype=torch.int32))
     assert t.shape == (2, 5) and l.shape == (2,)
