@@ -190,6 +190,13 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
+    # stdout must carry exactly ONE JSON line. Native libraries write there too (NCCL prints its version banner on
+    # communicator creation), so file descriptor 1 points at stderr while the run lasts and the result line is written to
+    # the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -198,8 +205,6 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug lines (NCCL_DEBUG=VERSION|INFO) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     from clipcap_b200 import _ffi
@@ -361,7 +366,8 @@ def run_b200(args):
         out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": f"first {n} images of the same batch, one at a time (reference is batch-size-1), "
                                          f"fp32, no KV cache; {agree}/{n} captions token-identical to the GPU run"}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
