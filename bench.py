@@ -143,11 +143,28 @@ def cpu_caption(R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg, pixels_one):
 
 
 def synthetic_state(seed=0):
-    """Random-init weights of the named architectures (no checkpoints / network here)."""
-    from oracle import restate as R
-    from oracle import synth
-    return {"vit": synth.vit_weights(R.VitCfg(), seed), "mapper": synth.mapper_weights(R.MapperCfg(E=768, d=1024, P=10, K=40, H=8, L=8), seed + 1),
-            "lm": synth.gpt2_weights(R.Gpt2Cfg(), seed + 2)}
+    """Random-init weights of the named architectures (no checkpoints / network here): the product package's own
+    parameter containers under their default initialisers (OpenAI-clip init for the ViT tower, torch defaults +
+    prefix_const ~ N(0,1) for the mapper as in the reference, HF GPT-2 init), seeded. The oracle is not involved."""
+    import torch
+    from clipcap_b200.encoders.clip import ViTImageTower
+    from clipcap_b200.encoders.config import EncoderConfig
+    from clipcap_b200.model import ClipCapModelPrefixOnly, Config
+    torch.manual_seed(seed)
+    tower = ViTImageTower()
+    cfg = Config(language_model="gpt2-medium", prefix_length=40, projection_length=10, transformer_layers=8,
+                 transformer_attention_heads=8, encoder_config=EncoderConfig(encoder_embedding_size=768))
+    model = ClipCapModelPrefixOnly(cfg)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    return {"vit": {k: v.detach().clone() for k, v in tower.state_dict().items()},
+            "mapper": {k[len("transformer_mapper."):]: v for k, v in sd.items() if k.startswith("transformer_mapper.")},
+            "lm": {k[len("language_model."):]: v for k, v in sd.items() if k.startswith("language_model.")}}
+
+
+def synthetic_pixels(B, seed):
+    """CLIP-normalised images are roughly unit-scale noise for throughput purposes: seeded N(0,1), fp32 [B,3,224,224]."""
+    import torch
+    return torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(seed))
 
 
 def run_reference(args):
@@ -159,10 +176,9 @@ def run_reference(args):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    from oracle import synth
     state = synthetic_state()
     R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg = cpu_reference_setup(state)
-    px = synth.pixels(max(1, min(4, args.steps + args.warmup)), 224)
+    px = synthetic_pixels(max(1, min(4, args.steps + args.warmup)), 1234)
     for i in range(args.warmup):
         cpu_caption(R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg, px[i % px.shape[0]:i % px.shape[0] + 1])
     times = []
@@ -213,7 +229,6 @@ def run_b200(args):
     from clipcap_b200.distributed import caption_step
     from clipcap_b200.model import ClipCapModelPrefixOnly, Config
     from clipcap_b200.pipeline import CaptionPipeline
-    from oracle import synth  # seeded synthetic weights / pixels only (not the checker)
     _ffi.lib()
 
     B = args.batch
@@ -229,7 +244,7 @@ def run_b200(args):
     model.load_state_dict(sd, strict=True)
     model = model.eval().to(dev)
 
-    px_host = synth.pixels(B, 224, seed=1234 + rank).pin_memory()  # fp32, as the reference's preprocess produces
+    px_host = synthetic_pixels(B, 1234 + rank).pin_memory()  # fp32, as the reference's preprocess produces
     px_dev = px_host.to(dev, non_blocking=True)
     prefix_all = torch.empty(world * B, 40, 1024, device=dev, dtype=torch.float32) if world > 1 else None
     tok_host = torch.empty(B, ENTRY_LENGTH, dtype=torch.int32).pin_memory()
