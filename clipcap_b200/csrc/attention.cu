@@ -615,6 +615,105 @@ decode_attn_bulk_kernel(const __half* __restrict__ qkv, __half* __restrict__ kca
   }
 }
 
+// Attention of query row 0 (the class token) of every (sequence, head) over all S keys: one warp per (b, h). A lane owns
+// keys lane, lane + 32, ...: it scores them against the query held in registers (whole 128-byte K rows, all loads
+// independent), the softmax is one warp reduction, then the lane accumulates p_j * V_j over ITS keys into 64 registers
+// (again whole rows, all loads in flight) and the 32 partial vectors are folded through shared memory. HBM-bound: K and V
+// are read exactly once.
+constexpr int CLS_KEYS_PER_LANE = 9;  // 288 keys per pass (ViT-L/14: 257 tokens = one pass)
+__global__ void __launch_bounds__(128)
+cls_attn_kernel(const __half* __restrict__ qkv, long long sb, long long sw, long long sh, long long st,
+                __half* __restrict__ o, long long ldo, int B, int S, int H, float scale_log2) {
+  __shared__ float fold[4][32][65];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * 4 + warp;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (pair >= B * H) return;
+  const int b = pair / H, h = pair % H;
+  const __half* qp = qkv + b * sb + h * sh;
+  const __half* kp = qp + sw;
+  const __half* vp = qp + 2 * sw;
+  float acc[64];
+#pragma unroll
+  for (int e = 0; e < 64; ++e) acc[e] = 0.f;
+  float run_max = -INFINITY, run_sum = 0.f;
+  for (int t0 = 0; t0 < S; t0 += 32 * CLS_KEYS_PER_LANE) {
+    const int n = min(32 * CLS_KEYS_PER_LANE, S - t0);
+    float sc[CLS_KEYS_PER_LANE];
+    float mx = -INFINITY;
+    {
+      float qf[64];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float tmp[8];
+        unpack8(*reinterpret_cast<const uint4*>(qp + 8 * c), tmp);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qf[8 * c + e] = tmp[e];
+      }
+#pragma unroll
+      for (int i = 0; i < CLS_KEYS_PER_LANE; ++i) {
+        const int j = lane + 32 * i;
+        sc[i] = -INFINITY;
+        if (j < n) {
+          const __half* kr = kp + (t0 + j) * st;
+          float d = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float kf[8];
+            unpack8(*reinterpret_cast<const uint4*>(kr + 8 * c), kf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d += qf[8 * c + e] * kf[e];
+          }
+          sc[i] = d;
+          mx = fmaxf(mx, d);
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    const float new_max = fmaxf(run_max, mx);
+    const float corr = exp2f((run_max - new_max) * scale_log2);  // exp2(-inf) = 0 on the first pass
+    run_max = new_max;
+    float psum = 0.f;
+#pragma unroll
+    for (int e = 0; e < 64; ++e) acc[e] *= corr;
+#pragma unroll
+    for (int i = 0; i < CLS_KEYS_PER_LANE; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n) {
+        const float p = exp2f((sc[i] - new_max) * scale_log2);
+        psum += p;
+        const __half* vr = vp + (t0 + j) * st;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float vf[8];
+          unpack8(*reinterpret_cast<const uint4*>(vr + 8 * c), vf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[8 * c + e] += p * vf[e];
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, off);
+    run_sum = run_sum * corr + psum;
+  }
+  // fold the 32 lanes' partial output vectors: lane c sums columns c and c + 32
+#pragma unroll
+  for (int e = 0; e < 64; ++e) fold[warp][lane][e] = acc[e];
+  __syncwarp();
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    o0 += fold[warp][r][lane];
+    o1 += fold[warp][r][lane + 32];
+  }
+  const float inv = 1.f / run_sum;
+  __half* orow = o + b * ldo + h * 64;
+  orow[lane] = __float2half_rn(o0 * inv);
+  orow[lane + 32] = __float2half_rn(o1 * inv);
+}
+
 __global__ void kv_scatter_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache,
                                   __half* __restrict__ vcache, int nseq, int T, int H, int t_max, int pos0,
                                   int slot_stride) {
@@ -703,6 +802,17 @@ int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, cons
   }
   CC_CUDA(launch_pdl(decode_attn_kernel, dim3(grid), dim3(DEC_WARPS * 32), 0, s, qkv, kcache, vcache, anc, o, nseq, H,
                      t_max, pos, scale * 1.4426950408889634f));
+  return CC_OK;
+}
+
+int cls_attention_run(const __half* qkv, long long sb, long long sw, long long sh, long long st, __half* o, int64_t ldo,
+                      int B, int S, int H, float scale, cudaStream_t s) {
+  CC_REQUIRE(B > 0 && S > 0 && H > 0, CC_ESHAPE, "cls attention: B=%d S=%d H=%d", B, S, H);
+  CC_REQUIRE(sb % 8 == 0 && sw % 8 == 0 && sh % 8 == 0 && st % 8 == 0 && ldo % 2 == 0, CC_EALIGN,
+             "cls attention: strides must keep 16-byte rows");
+  const int pairs = B * H;
+  CC_CUDA(launch_pdl(cls_attn_kernel, dim3((pairs + 3) / 4), dim3(128), 0, s, qkv, sb, sw, sh, st, o,
+                     static_cast<long long>(ldo), B, S, H, scale * 1.4426950408889634f));
   return CC_OK;
 }
 

@@ -212,6 +212,11 @@ int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, cons
 int kv_scatter_run(const __half* qkv, __half* kcache, __half* vcache, int nseq, int T, int H, int t_max, int pos0,
                    int slot_stride, cudaStream_t s);
 
+// Attention of the FIRST token of every sequence only (ViT class token of the last block): o[b, h*64 ..] for query row
+// (b, 0) over all S keys. q/k/v element (b, which, h, t, c) lives at qkv[b*sb + which*sw + h*sh + t*st + c]; head dim 64.
+int cls_attention_run(const __half* qkv, long long sb, long long sw, long long sh, long long st, __half* o, int64_t ldo,
+                      int B, int S, int H, float scale, cudaStream_t s);
+
 // ------------------------------------------------------------------ element-wise glue (elementwise.cu)
 int convert_to_f16_run(const void* src, int src_dtype, __half* dst, int64_t n, cudaStream_t s);
 int convert_from_f32_run(const float* src, int64_t src_ld, void* dst, int dst_dtype, int rows, int cols, cudaStream_t s);
@@ -291,6 +296,13 @@ struct Stack {
   // ViT-L/14 shape only (tokens per image == kVitAttnTokens, head dim 64): QKV is written head-major and attention
   // runs on the tcgen05 kernel. Set before plan().
   int heads_S = 0;
+  // Only token 0 of every sequence is consumed after the last layer (ViT: ln_post(x[:, 0]), clip encode_image): with
+  // cls_last_S = tokens per sequence set before plan(), layer_cls_only() runs that layer's attention output, out-proj and
+  // MLP for the class-token rows alone (K and V still come from every token). Results for those rows are the same
+  // function of the same inputs; the other rows of h are left as the previous layer wrote them.
+  int cls_last_S = 0;
+  GemmPlan p_o_cls, p_2_cls;
+  int layer_cls_only(int l, int B, int S, cudaStream_t s);
 
   int init(Arena& arena, int d_, int dff_, int H_, int act_epi_, bool causal_, float eps_, int max_rows_,
            int dec_rows_ = 0);

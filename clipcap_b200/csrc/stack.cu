@@ -64,6 +64,15 @@ int Stack::plan() {
     CC_TRY(gemm_plan(&p_1[l], ln16, d, max_rows, w.w1, dff, d, act_epi, w.b1, mlp16, dff));
     CC_TRY(gemm_plan(&p_2[l], mlp16, dff, max_rows, w.w2, d, dff, EPI_RESID_F32, w.b2, h, d));
   }
+  if (cls_last_S > 0 && L > 0 && hd == 64 && !causal) {
+    const LayerW& w = layers[L - 1];
+    const int nb = max_rows / cls_last_S;
+    const int64_t ld = static_cast<int64_t>(cls_last_S) * d;  // class-token rows of h are cls_last_S rows apart
+    CC_TRY(gemm_plan(&p_o_cls, att16, d, nb, w.wo, d, d, EPI_RESID_F32, w.bo, h, ld));
+    CC_TRY(gemm_plan(&p_2_cls, mlp16, dff, nb, w.w2, d, dff, EPI_RESID_F32, w.b2, h, ld));
+  } else {
+    cls_last_S = 0;
+  }
   if (dec_rows > 0) {
     const int max_blocks = dec_rows_pad / 128;
     size_t need = 0;
@@ -147,6 +156,28 @@ int Stack::layer_full(int l, int B, int S, KvCache* kv, int slot_stride, cudaStr
   CC_TRY(gemm_run(p_1[l], rows, s));
   CC_TRY(gemm_run(p_2[l], rows, s));
   launches += 4;
+  return CC_OK;
+}
+
+int Stack::layer_cls_only(int l, int B, int S, cudaStream_t s) {
+  CC_REQUIRE(cls_last_S == S && l == static_cast<int>(layers.size()) - 1, CC_EINVAL,
+             "stack: class-token-only pass is planned for the last layer with %d tokens per sequence", cls_last_S);
+  const int rows = B * S;
+  CC_REQUIRE(rows <= max_rows, CC_ESHAPE, "stack: %d x %d rows exceed the %d the handle was created for", B, S, max_rows);
+  const LayerW& w = layers[l];
+  CC_TRY(layernorm_run(h, d, w.ln1_g, w.ln1_b, ln16, d, rows, d, eps, s));
+  CC_TRY(gemm_run(p_qkv[l], rows, s));  // K and V of every token (and Q, of which only the class rows are read)
+  if (heads_S > 0) {  // head-major planes [(b*3 + which)*H + h][S][64]
+    const long long plane = static_cast<long long>(S) * 64;
+    CC_TRY(cls_attention_run(qkv16, 3LL * H * plane, static_cast<long long>(H) * plane, plane, 64, att16, d, B, S, H, scale, s));
+  } else {  // packed rows [b*S + t][3d]
+    CC_TRY(cls_attention_run(qkv16, static_cast<long long>(S) * 3 * d, d, 64, 3LL * d, att16, d, B, S, H, scale, s));
+  }
+  CC_TRY(gemm_run(p_o_cls, B, s));  // h[b*S] += att_cls Wo^T + bo
+  CC_TRY(layernorm_run(h, static_cast<int64_t>(S) * d, w.ln2_g, w.ln2_b, ln16, d, B, d, eps, s));
+  CC_TRY(gemm_run(p_1[l], B, s));
+  CC_TRY(gemm_run(p_2_cls, B, s));  // h[b*S] += act(...) W2^T + b2
+  launches += 7;
   return CC_OK;
 }
 

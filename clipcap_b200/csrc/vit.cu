@@ -105,6 +105,12 @@ int vit_build(cc_vit* m, const cc_tensor* w, int nw) {
     const bool no_tc = e != nullptr && e[0] == '1';
     if (!no_tc && m->T == kVitAttnTokens && m->st.hd == 64) m->st.heads_S = m->T;
   }
+  {
+    // Only the class token leaves the tower: the last block's out-proj / MLP run on the B class rows alone.
+    // CLIPCAP_B200_FULL_LAST_LAYER=1 computes every row like the reference (A/B measurements).
+    const char* e = getenv("CLIPCAP_B200_FULL_LAST_LAYER");
+    if (!(e != nullptr && e[0] == '1')) m->st.cls_last_S = m->T;
+  }
   CC_TRY(m->st.plan());
   return CC_OK;
 }
@@ -151,7 +157,9 @@ int cc_vit_forward(cc_vit* m, const void* pixels, int pix_dtype, int B, int norm
   CC_TRY(gemm_run(m->p_patch, B * np, s));
   CC_TRY(vit_embed_lnpre_run(m->patches32, m->cls, m->pos, m->lnpre_g, m->lnpre_b, m->st.h, B, m->T, c.width, c.eps, s));
   m->st.launches = 0;
-  for (int l = 0; l < c.layers; ++l) CC_TRY(m->st.layer_full(l, B, m->T, nullptr, 0, s));
+  const int full_layers = m->st.cls_last_S > 0 ? c.layers - 1 : c.layers;
+  for (int l = 0; l < full_layers; ++l) CC_TRY(m->st.layer_full(l, B, m->T, nullptr, 0, s));
+  if (full_layers < c.layers) CC_TRY(m->st.layer_cls_only(c.layers - 1, B, m->T, s));
   // LN_post on the class token of every image (row b*T of h), then the output projection
   CC_TRY(layernorm_run(m->st.h, static_cast<int64_t>(m->T) * c.width, m->lnpost_g, m->lnpost_b, m->cls16, c.width, B,
                        c.width, c.eps, s));

@@ -73,7 +73,7 @@ def test_beam5_full_shard(full):
     assert torch.equal(t1, t2) and torch.equal(l1, l2) and torch.equal(s1, s2)
     ts, ls, ss = lm.generate(prefix[7:11].contiguous(), "beam", 5, EL, 1.0, STOP)
     assert torch.equal(ts, t1[7:11]) and torch.equal(ls, l1[7:11])
-    assert rel_err(ss, s1[7:11]) < 1e-5
+    assert rel_err(ss, s1[7:11]) < 1e-4  # scores: fp32 sums over differently tiled GEMMs (tokens are identical)
     st = full["state"]
     i = 9
     pre_cpu = R.mapper_forward(st["mapper"], R.vit_encode(st["vit"], full["px"][i:i + 1], R.VitCfg()),
