@@ -623,7 +623,7 @@ decode_attn_bulk_kernel(const __half* __restrict__ qkv, __half* __restrict__ kca
 constexpr int CLS_KEYS_PER_LANE = 9;  // 288 keys per pass (ViT-L/14: 257 tokens = one pass)
 __global__ void __launch_bounds__(128)
 cls_attn_kernel(const __half* __restrict__ qkv, long long sb, long long sw, long long sh, long long st,
-                __half* __restrict__ o, long long ldo, int B, int S, int H, float scale_log2) {
+                __half* __restrict__ o, long long ldo, int B, int S, int H, int qrow, float scale_log2) {
   __shared__ float fold[4][32][65];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * 4 + warp;
@@ -631,9 +631,10 @@ cls_attn_kernel(const __half* __restrict__ qkv, long long sb, long long sw, long
   pdl_wait();
   if (pair >= B * H) return;
   const int b = pair / H, h = pair % H;
-  const __half* qp = qkv + b * sb + h * sh;
-  const __half* kp = qp + sw;
-  const __half* vp = qp + 2 * sw;
+  const __half* base = qkv + b * sb + h * sh;
+  const __half* qp = base + qrow * st;
+  const __half* kp = base + sw;
+  const __half* vp = base + 2 * sw;
   float acc[64];
 #pragma unroll
   for (int e = 0; e < 64; ++e) acc[e] = 0.f;
@@ -806,13 +807,13 @@ int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, cons
 }
 
 int cls_attention_run(const __half* qkv, long long sb, long long sw, long long sh, long long st, __half* o, int64_t ldo,
-                      int B, int S, int H, float scale, cudaStream_t s) {
-  CC_REQUIRE(B > 0 && S > 0 && H > 0, CC_ESHAPE, "cls attention: B=%d S=%d H=%d", B, S, H);
+                      int B, int S, int H, float scale, cudaStream_t s, int qrow) {
+  CC_REQUIRE(B > 0 && S > 0 && H > 0 && qrow >= 0 && qrow < S, CC_ESHAPE, "cls attention: B=%d S=%d H=%d qrow=%d", B, S, H, qrow);
   CC_REQUIRE(sb % 8 == 0 && sw % 8 == 0 && sh % 8 == 0 && st % 8 == 0 && ldo % 2 == 0, CC_EALIGN,
              "cls attention: strides must keep 16-byte rows");
   const int pairs = B * H;
   CC_CUDA(launch_pdl(cls_attn_kernel, dim3((pairs + 3) / 4), dim3(128), 0, s, qkv, sb, sw, sh, st, o,
-                     static_cast<long long>(ldo), B, S, H, scale * 1.4426950408889634f));
+                     static_cast<long long>(ldo), B, S, H, qrow, scale * 1.4426950408889634f));
   return CC_OK;
 }
 

@@ -212,10 +212,11 @@ int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, cons
 int kv_scatter_run(const __half* qkv, __half* kcache, __half* vcache, int nseq, int T, int H, int t_max, int pos0,
                    int slot_stride, cudaStream_t s);
 
-// Attention of the FIRST token of every sequence only (ViT class token of the last block): o[b, h*64 ..] for query row
-// (b, 0) over all S keys. q/k/v element (b, which, h, t, c) lives at qkv[b*sb + which*sw + h*sh + t*st + c]; head dim 64.
+// Attention of ONE query token per sequence over all S keys (the ViT class token of the last block: qrow = 0; the last
+// prefix position of the last GPT-2 prefill block: qrow = S - 1, for which the causal mask hides nothing): o[b, h*64 ..].
+// q/k/v element (b, which, h, t, c) lives at qkv[b*sb + which*sw + h*sh + t*st + c]; head dim 64.
 int cls_attention_run(const __half* qkv, long long sb, long long sw, long long sh, long long st, __half* o, int64_t ldo,
-                      int B, int S, int H, float scale, cudaStream_t s);
+                      int B, int S, int H, float scale, cudaStream_t s, int qrow = 0);
 
 // ------------------------------------------------------------------ element-wise glue (elementwise.cu)
 int convert_to_f16_run(const void* src, int src_dtype, __half* dst, int64_t n, cudaStream_t s);
@@ -303,6 +304,9 @@ struct Stack {
   int cls_last_S = 0;
   GemmPlan p_o_cls, p_2_cls;
   int layer_cls_only(int l, int B, int S, cudaStream_t s);
+  // Last block of a causal prefill whose only consumer is the last position (the LM head of the first generated token):
+  // K, V of every position still go to the cache, everything after the attention scores runs for row S-1 of each sequence.
+  int layer_last_row(int l, int B, int S, KvCache* kv, int slot_stride, cudaStream_t s);
 
   int init(Arena& arena, int d_, int dff_, int H_, int act_epi_, bool causal_, float eps_, int max_rows_,
            int dec_rows_ = 0);

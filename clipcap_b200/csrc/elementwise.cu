@@ -92,27 +92,24 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int rows, int 
 // Non-overlapping 14x14 patches: row (b, py, px) of the GEMM operand gathers 3 x 14 x 14 pixels, column order
 // (c, ky, kx) = the flattening of conv1.weight [w, 3, 14, 14]; columns >= 588 are zero padding (16-byte rows for TMA).
 template <typename SRC>
-__global__ void vit_im2col_kernel(const SRC* __restrict__ px, __half* __restrict__ out, int B, int img, int patch,
-                                  int k_pad) {
+__global__ void __launch_bounds__(256)
+vit_im2col_kernel(const SRC* __restrict__ px, __half* __restrict__ out, int img, int patch, int k_pad) {
+  // one CTA per (image, patch row): 32-bit index arithmetic only, the output rows of the CTA are contiguous
   const int grid_w = img / patch;
-  const int kk = 3 * patch * patch;
-  const long long n = static_cast<long long>(B) * grid_w * grid_w * k_pad;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
-    const int col = static_cast<int>(i % k_pad);
-    long long r = i / k_pad;
-    const int pxi = static_cast<int>(r % grid_w);
-    r /= grid_w;
-    const int pyi = static_cast<int>(r % grid_w);
-    const long long b = r / grid_w;
+  const int pp = patch * patch, kk = 3 * pp;
+  const int b = blockIdx.x / grid_w, pyi = blockIdx.x - b * grid_w;
+  const SRC* src = px + static_cast<long long>(b) * 3 * img * img;
+  __half* dst = out + static_cast<long long>(blockIdx.x) * grid_w * k_pad;
+  const int n = grid_w * k_pad;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int pxi = i / k_pad, col = i - pxi * k_pad;
     float v = 0.f;
     if (col < kk) {
-      const int c = col / (patch * patch);
-      const int rem = col - c * patch * patch;
+      const int c = col / pp, rem = col - c * pp;
       const int ky = rem / patch, kx = rem - ky * patch;
-      v = static_cast<float>(px[((b * 3 + c) * img + (pyi * patch + ky)) * img + pxi * patch + kx]);
+      v = static_cast<float>(src[(c * img + pyi * patch + ky) * img + pxi * patch + kx]);
     }
-    out[i] = __float2half_rn(v);
+    dst[i] = __float2half_rn(v);
   }
 }
 
@@ -276,11 +273,10 @@ int pack_weight_run(const float* src, int rows, int cols, bool transpose, __half
 
 int vit_im2col_run(const void* pixels, int dtype, __half* out, int B, int img, int patch, int k_pad, cudaStream_t s) {
   const int gw = img / patch;
-  const long long n = static_cast<long long>(B) * gw * gw * k_pad;
   if (dtype == CC_F32)
-    vit_im2col_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(static_cast<const float*>(pixels), out, B, img, patch, k_pad);
+    vit_im2col_kernel<float><<<B * gw, 256, 0, s>>>(static_cast<const float*>(pixels), out, img, patch, k_pad);
   else if (dtype == CC_F16)
-    vit_im2col_kernel<__half><<<grid_for(n, 256), 256, 0, s>>>(static_cast<const __half*>(pixels), out, B, img, patch, k_pad);
+    vit_im2col_kernel<__half><<<B * gw, 256, 0, s>>>(static_cast<const __half*>(pixels), out, img, patch, k_pad);
   else {
     set_error("vit: unknown pixel dtype %d", dtype);
     return CC_EINVAL;

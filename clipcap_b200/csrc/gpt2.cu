@@ -215,7 +215,15 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
   int extra = 0;
 
   // ---- prefill: all Tp prefix positions at once; K,V go to slot img*beam
-  for (int l = 0; l < c.L; ++l) CC_TRY(st.layer_full(l, B, Tp, &m->kv, beam, s));
+  // The first token needs only the last prefix position of the last block (LM head on row Tp-1): that block runs its
+  // out-proj / MLP for those B rows alone (K, V of every position still go to the cache).
+  static const bool full_last = [] {
+    const char* e = getenv("CLIPCAP_B200_FULL_LAST_LAYER");
+    return e != nullptr && e[0] == '1';
+  }();
+  const bool last_row = !full_last && Tp > 1;
+  for (int l = 0; l < c.L - (last_row ? 1 : 0); ++l) CC_TRY(st.layer_full(l, B, Tp, &m->kv, beam, s));
+  if (last_row) CC_TRY(st.layer_last_row(c.L - 1, B, Tp, &m->kv, beam, s));
   CC_TRY(layernorm_run(st.h + static_cast<size_t>(Tp - 1) * d, static_cast<int64_t>(Tp) * d, m->lnf_g, m->lnf_b,
                        m->lnf16, d, B, d, c.eps, s));
   extra += 1;

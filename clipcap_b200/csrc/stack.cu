@@ -181,6 +181,31 @@ int Stack::layer_cls_only(int l, int B, int S, cudaStream_t s) {
   return CC_OK;
 }
 
+int Stack::layer_last_row(int l, int B, int S, KvCache* kv, int slot_stride, cudaStream_t s) {
+  const int rows = B * S;
+  CC_REQUIRE(rows <= max_rows, CC_ESHAPE, "stack: %d x %d rows exceed the %d the handle was created for", B, S, max_rows);
+  CC_REQUIRE(hd == 64 && causal && heads_S == 0, CC_EINVAL, "stack: last-row pass needs the causal packed-QKV stack, head dim 64");
+  const LayerW& w = layers[l];
+  CC_TRY(layernorm_run(h, d, w.ln1_g, w.ln1_b, ln16, d, rows, d, eps, s));
+  CC_TRY(gemm_run(p_qkv[l], rows, s));
+  if (kv != nullptr)
+    CC_TRY(kv_scatter_run(qkv16, kv->k + l * kv->layer_elems, kv->v + l * kv->layer_elems, B, S, H, kv->t_max, 0,
+                          slot_stride, s));
+  // query = last position: every key is visible, so the causal mask is a no-op
+  CC_TRY(cls_attention_run(qkv16, static_cast<long long>(S) * 3 * d, d, 64, 3LL * d, att16, d, B, S, H, scale, s, S - 1));
+  float* hl = h + static_cast<size_t>(S - 1) * d;  // row S-1 of every sequence, S rows apart
+  const int64_t ld = static_cast<int64_t>(S) * d;
+  GemmPlan po, p2;
+  CC_TRY(gemm_plan(&po, att16, d, B, w.wo, d, d, EPI_RESID_F32, w.bo, hl, ld));
+  CC_TRY(gemm_run(po, B, s));
+  CC_TRY(layernorm_run(hl, ld, w.ln2_g, w.ln2_b, ln16, d, B, d, eps, s));
+  CC_TRY(gemm_run(p_1[l], B, s));
+  CC_TRY(gemm_plan(&p2, mlp16, dff, B, w.w2, d, dff, EPI_RESID_F32, w.b2, hl, ld));
+  CC_TRY(gemm_run(p2, B, s));
+  launches += kv != nullptr ? 8 : 7;
+  return CC_OK;
+}
+
 int Stack::layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int pos, cudaStream_t s, int row0, int beam,
                         int shared_len) {
   CC_REQUIRE(row0 + nseq <= max_rows && row0 + nseq <= kv->slots, CC_ESHAPE, "stack: %d sequences exceed handle capacity",
