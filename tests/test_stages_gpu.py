@@ -150,3 +150,89 @@ def test_beam_matches_oracle(cuda_device, beam, temperature):
         else:  # only a near-tie between beams may differ: the returned score must then match the oracle's best
             assert abs(scores[i] - oscore) < 2e-3 * max(1.0, abs(oscore)), (i, got, otoks, scores[i], oscore)
     assert n_exact >= B - 1
+
+
+@pytest.mark.parametrize("beam", [1, 5])
+def test_beam_with_text_prefix_matches_oracle(cuda_device, beam):
+    """generate_beam(text_prefix_tokens=...) — the VQA-style prompt of base.py:75-77: the text-prefix embeddings follow the
+    mapper prefix, then beam search as usual. Through the drop-in function, against the oracle's generate_beam."""
+    from clipcap_b200.encoders.config import EncoderConfig
+    from clipcap_b200.inference.base import generate_beam, generate_beam_tokens
+    from clipcap_b200.model import ClipCapModelPrefixOnly, Config
+    from oracle import ref_runner as RR
+    gcfg = R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64)
+    mcfg = R.MapperCfg(E=64, d=128, P=3, K=5, H=2, L=2)
+    map_w, lm_w = synth.mapper_weights(mcfg), synth.gpt2_weights(gcfg, wte_std=0.1)
+    cfg = Config(language_model="tiny:128:2:2:1003:64", prefix_length=5, projection_length=3, transformer_layers=2,
+                 transformer_attention_heads=2, encoder_config=EncoderConfig(encoder_embedding_size=64))
+    model = ClipCapModelPrefixOnly(cfg)
+    sd = {f"transformer_mapper.{k}": v for k, v in map_w.items()}
+    sd.update({f"language_model.{k}": v for k, v in lm_w.items()})
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().to(cuda_device)
+    emb = synth.embeddings(3, 64, seed=31)
+    tp = torch.tensor([[7, 900, 42, 7]])
+    prefix_ref = R.mapper_forward(map_w, emb, mcfg)
+    stop = 1002
+    want = [R.generate_beam(lm_w, gcfg, prefix_ref[i:i + 1], beam, 8, 1.0, stop, text_prefix_tokens=tp) for i in range(3)]
+    prefix = model.transformer_mapper(emb.to(cuda_device))
+    toks, lens, scores = generate_beam_tokens(model, prefix, tp.to(cuda_device), beam, 8, 1.0, stop)
+    ok = 0
+    for i in range(3):
+        got = toks[i, :int(lens[i])].tolist()
+        if got == want[i][0]:
+            ok += 1
+            if beam > 1:
+                assert abs(float(scores[i]) - want[i][1]) < 2e-3 * abs(want[i][1])
+        else:  # only a near-tie in the oracle's own scores may flip a beam
+            assert min(min(t["margin"]) for t in want[i][2]) < 5e-3, (i, got, want[i][0])
+    assert ok >= 2
+    text = generate_beam(model, RR.FakeTokenizer(stop), prefix[:1], text_prefix_tokens=tp.to(cuda_device), beam_size=beam,
+                         entry_length=8)
+    assert text[0] == " ".join(str(t) for t in toks[0, :int(lens[0])].tolist())
+
+
+def test_generate_wrapper(cuda_device):
+    """clipcap.inference.generate (generate.py:8-44): BOS (+ text prefix) embeddings after the mapper prefix, then
+    generate_no_beam with the same text_prefix_tokens. With top_k=1 the draw is deterministic: compare with the oracle's
+    restatement of that exact call sequence."""
+    from clipcap_b200.encoders.config import EncoderConfig
+    from clipcap_b200.inference.generate import generate
+    from clipcap_b200.model import ClipCapModelPrefixOnly, Config
+    gcfg = R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=128)  # generate() always decodes up to 67 tokens
+    mcfg = R.MapperCfg(E=64, d=128, P=3, K=5, H=2, L=2)
+    map_w, lm_w = synth.mapper_weights(mcfg), synth.gpt2_weights(gcfg, wte_std=0.1)
+    cfg = Config(language_model="tiny:128:2:2:1003:128", prefix_length=5, projection_length=3, transformer_layers=2,
+                 transformer_attention_heads=2, encoder_config=EncoderConfig(encoder_embedding_size=64))
+    model = ClipCapModelPrefixOnly(cfg)
+    sd = {f"transformer_mapper.{k}": v for k, v in map_w.items()}
+    sd.update({f"language_model.{k}": v for k, v in lm_w.items()})
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().to(cuda_device)
+
+    class Tok:  # the slice of the HF tokenizer interface generate() uses
+        bos_token = "1001"
+
+        def encode(self, text, return_tensors=None):
+            if text == ".":
+                return [13]
+            ids = [int(t) for t in text.replace("1001", "1001 ").split()]
+            return torch.tensor([ids]) if return_tensors == "pt" else ids
+
+        def decode(self, ids):
+            return " ".join(str(int(i)) for i in ids)
+
+    emb = synth.embeddings(1, 64, seed=5)
+    out = generate(model, Tok(), emb.to(cuda_device), top_p=0.9, top_k=1, temperature=1.0, number_to_generate=1,
+                   text_prefix="17 5", seed=1)
+    tpt = torch.tensor([[1001, 17, 5]])
+    # oracle: prompt = [mapper prefix, wte(BOS + text prefix)], then generate_no_beam appends wte(text prefix tokens) AGAIN
+    # (generate.py:30-41 feeding no_beam.py:27-29) and starts its history with them
+    prompt = torch.cat((R.mapper_forward(map_w, emb, mcfg), lm_w["transformer.wte.weight"][tpt]), dim=1)
+    want = R.generate_sampling(lm_w, gcfg, prompt, "sample", lambda p: int(p.argmax()), entry_length=67,
+                               text_prefix_tokens=tpt, stop_token=13, top_p=0.9, top_k=1, temperature=1.0,
+                               repetition_penalty=1.2)
+    got = [int(t) for t in out[0].split()]
+    assert got[:3] == [1001, 17, 5]
+    n = min(len(want), len(got) - 3, 20)
+    assert n >= 1 and got[3:3 + n] == want[:n], (got, want)
