@@ -236,3 +236,45 @@ def test_generate_wrapper(cuda_device):
     assert got[:3] == [1001, 17, 5]
     n = min(len(want), len(got) - 3, 20)
     assert n >= 1 and got[3:3 + n] == want[:n], (got, want)
+
+
+@pytest.mark.parametrize("B,Tp,EL", [
+    (37, 5, 6),    # ragged batch: not a multiple of the 32-row epilogue groups / 128-row tiles (tcgen05 decode path)
+    (17, 3, 4),    # one row more than the skinny path takes
+    (16, 3, 4),    # the most the skinny path takes
+    (2, 7, 1),     # entry_length 1: prefill + head only, no decode step
+    (3, 1, 63),    # single prefix token, decode up to the last position the model has (1 + 63 = n_positions)
+])
+def test_greedy_edge_shapes(cuda_device, B, Tp, EL):
+    """Ragged and boundary shapes of the decode loop against the oracle (a few rows of it when the batch is large), plus
+    batch invariance of every row against the same rows decoded in a smaller call."""
+    from clipcap_b200.engine import Gpt2Engine
+    cfg = R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64)
+    w, prefix = _lm_setup(cfg, B, Tp)
+    stop = cfg.V - 1
+    rows = sorted(set([0, B // 2, B - 1]))
+    oracle = R.generate_greedy_batch(w, cfg, prefix[rows], EL, stop)
+    eng = Gpt2Engine(w, cfg.d, cfg.L, cfg.H, cfg.V, cfg.n_pos, max_seqs=B, max_len=Tp + EL, device=cuda_device)
+    toks, lens, _ = eng.generate(prefix.to(cuda_device), "greedy", 1, EL, 1.0, stop)
+    assert tuple(toks.shape) == (B, EL) and int(lens.min()) >= 1 and int(lens.max()) <= EL
+    exact, _ = check_tokens_against_oracle(toks[rows], lens[rows], oracle, margin_tol=5e-3)
+    assert exact >= len(rows) - 1
+    if B > 4:  # the last three rows alone: another kernel path (skinny) or other tiles, same tokens up to near-ties
+        t3, l3, _ = eng.generate(prefix[B - 3:].contiguous().to(cuda_device), "greedy", 1, EL, 1.0, stop)
+        same = sum(int(torch.equal(t3[i, :l3[i]], toks[B - 3 + i, :lens[B - 3 + i]])) for i in range(3))
+        assert same >= 2
+
+
+def test_entry_length_limits(cuda_device):
+    """entry_length up to 128 per call (the handle's state buffers); beyond that, and beyond max_len, a CC_ESHAPE error."""
+    from clipcap_b200._ffi import CCError
+    from clipcap_b200.engine import Gpt2Engine
+    cfg = R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=256)
+    w, prefix = _lm_setup(cfg, 2, 4)
+    eng = Gpt2Engine(w, cfg.d, cfg.L, cfg.H, cfg.V, cfg.n_pos, max_seqs=2, max_len=4 + 200, device=cuda_device)
+    toks, lens, _ = eng.generate(prefix.to(cuda_device), "greedy", 1, 128, 1.0, cfg.V + 5)  # stop token never produced
+    assert tuple(toks.shape) == (2, 128) and lens.tolist() == [128, 128]
+    oracle = R.generate_greedy_batch(w, cfg, prefix[:1], 24, cfg.V + 5)
+    exact, _ = check_tokens_against_oracle(toks[:1, :24], torch.tensor([24]), oracle, margin_tol=5e-3)
+    with pytest.raises(CCError, match="CC_ESHAPE"):
+        eng.generate(prefix.to(cuda_device), "greedy", 1, 129, 1.0, 0)
