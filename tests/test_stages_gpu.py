@@ -278,3 +278,29 @@ def test_entry_length_limits(cuda_device):
     exact, _ = check_tokens_against_oracle(toks[:1, :24], torch.tensor([24]), oracle, margin_tol=5e-3)
     with pytest.raises(CCError, match="CC_ESHAPE"):
         eng.generate(prefix.to(cuda_device), "greedy", 1, 129, 1.0, 0)
+
+
+def test_vit_l14_ragged_batch(cuda_device):
+    """Full-size ViT-L/14 on 9 images inside a handle created for 16 (a batch that fills neither a 256-row CTA-pair tile nor a
+    persistent wave evenly), fp16 pixels, with normalisation; one more image in a second call re-uses the handle."""
+    from clipcap_b200.engine import VitEngine
+    cfg = R.VitCfg()
+    w = synth.vit_weights(cfg)
+    px = synth.pixels(9, 224, seed=77)
+    ref = R.vit_encode(w, px.half().float(), cfg, normalize=True)
+    eng = VitEngine(w, max_batch=16, device=cuda_device)
+    out = eng.forward(px.half().to(cuda_device), normalize=True)
+    assert out.dtype == torch.float16 and rel_err(out, ref) < 3e-3
+    one = eng.forward(px[4:5].to(cuda_device), normalize=True)
+    assert rel_err(one, ref[4:5]) < TOL
+
+
+def test_mapper_ragged_batch(cuda_device):
+    """257 samples through a handle created for 300: the last 128-row tile of every GEMM is a single row."""
+    from clipcap_b200.engine import MapperEngine
+    cfg = R.MapperCfg(E=64, d=128, P=3, K=5, H=2, L=2)
+    w = synth.mapper_weights(cfg)
+    emb = synth.embeddings(257, cfg.E, seed=9)
+    ref = R.mapper_forward(w, emb, cfg)
+    eng = MapperEngine(w, E=cfg.E, d=cfg.d, P=cfg.P, K=cfg.K, H=cfg.H, L=cfg.L, max_batch=300, device=cuda_device)
+    assert rel_err(eng.forward(emb.to(cuda_device)), ref) < TOL
