@@ -191,3 +191,24 @@ def test_training_step_api_drop_in(cuda_device):
         prefix = model.transformer_mapper(emb.to(cuda_device))
     want = R.mapper_forward({k: v.detach() for k, v in ref_p.items()}, emb, mcfg)
     assert rel_err(prefix, want) < 3e-3
+
+
+@pytest.mark.parametrize("B,Tt", [(1, 1), (5, 9), (2, 59)])
+def test_train_step_edge_shapes(cuda_device, B, Tt):
+    """One sample with one token; a batch with a fully padded row and a row of token-0 only; captions that fill the model's
+    positions (K + Tt = n_positions). Loss and every gradient against the oracle."""
+    spec, gcfg, mcfg, map_w, lm_w, *_ = load_train_case("tiny_a")   # K = 5, n_pos = 64
+    g = torch.Generator().manual_seed(B * 100 + Tt)
+    tokens = torch.randint(1, gcfg.V, (B, Tt), generator=g)
+    if B >= 5:
+        tokens[1, :] = -1                 # nothing to score in this row
+        tokens[2, :] = 0                  # real tokens with id 0: ignored as well (ignore_index = 0)
+        tokens[3, Tt // 2:] = -1
+    emb = synth.embeddings(B, mcfg.E, seed=Tt)
+    want_loss, want = R.training_loss_and_grads(map_w, lm_w, mcfg, gcfg, tokens, emb)
+    eng = _engine(gcfg, mcfg, lm_w, B, Tt, cuda_device)
+    params = {k: v.to(cuda_device).contiguous() for k, v in map_w.items()}
+    grads = {k: torch.full_like(v, float("nan")) for k, v in params.items()}
+    loss = eng.step(params, emb.to(cuda_device), tokens.to(cuda_device), grads)
+    assert abs(float(loss) - want_loss) < LOSS_TOL * abs(want_loss)
+    _check_grads(grads, want)
