@@ -104,3 +104,39 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
+
+
+def test_training_surface_matches_reference():
+    """ClipCapModelPrefixOnly's training-side surface (clipcap/model/model.py:60-123): parameters() = the mapper's,
+    train() keeps the language model in eval mode, configure_optimizers() needs a TrainingConfig (same assertion text) and
+    returns the Lightning dict; on a CPU model training_step refuses to run (no CPU path)."""
+    import pytest
+    import torch
+    from clipcap_b200.encoders.config import EncoderConfig
+    from clipcap_b200.model import ClipCapModel, ClipCapModelPrefixOnly, Config, TrainingConfig
+    cfg = Config(language_model="tiny:128:2:2:1003:64", prefix_length=5, projection_length=3, transformer_layers=2,
+                 transformer_attention_heads=2, encoder_config=EncoderConfig(encoder_embedding_size=64))
+    model = ClipCapModelPrefixOnly(cfg)
+    mapper_ids = {id(p) for p in model.transformer_mapper.parameters()}
+    assert {id(p) for p in model.parameters()} == mapper_ids and mapper_ids
+    model.train()
+    assert model.training and model.transformer_mapper.training and not model.language_model.training
+    with pytest.raises(AssertionError, match="set_training_config"):
+        model.configure_optimizers()
+    model.set_training_config(TrainingConfig(optimizer_lr=1e-4, use_deepspeed_optimisers=True, scheduler_warmup_steps=3,
+                                             total_steps=10))
+    oc = model.configure_optimizers()
+    assert set(oc) == {"optimizer", "lr_scheduler"} and oc["lr_scheduler"]["interval"] == "step"
+    assert oc["optimizer"].param_groups[0]["weight_decay"] == 0.0  # deepspeed FusedAdam default; torch AdamW: 0.01
+    assert {id(p) for g in oc["optimizer"].param_groups for p in g["params"]} == mapper_ids
+    lrs = []
+    for _ in range(5):
+        lrs.append(oc["lr_scheduler"]["scheduler"].get_last_lr()[0])
+        oc["lr_scheduler"]["scheduler"].step()
+    assert lrs[0] == 0.0 and abs(lrs[3] - 1e-4) < 1e-12 and lrs[4] < lrs[3]
+    tokens = torch.tensor([[4, 9, -1]])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model.training_step((tokens, torch.zeros(1, 64)), 0)
+    assert tokens.tolist() == [[4, 9, 0]]  # padding rewritten in place before anything else, like the reference (model.py:104)
+    with pytest.raises(NotImplementedError):  # fine-tuning the language model is not built
+        ClipCapModel(cfg).training_step((tokens, torch.zeros(1, 64)), 0)
