@@ -1,34 +1,47 @@
-"""Encoder factory — same names, arguments and error behaviour as clipcap/encoders/base.py:10-39."""
-from typing import Callable, Optional, Tuple, Union
+"""Encoder factories of the drop-in surface — `get_encoder`, `get_encoder_from_config`, `get_encoder_from_model` with the
+reference's names, arguments, return value `(encoder module, transform)` and error for an unknown encoder name
+(clipcap/encoders/base.py:10-39). Dispatch is a table of builders; only the CLIP image tower is built here."""
+from typing import Callable, Dict, Optional, Tuple
 
 from torch.nn import Module
 
+from clipcap_b200.configs import EncoderConfig
 from clipcap_b200.encoders.clip import get_clip_encoder
-from clipcap_b200.encoders.config import EncoderConfig
+
+Encoder = Tuple[Module, Callable]
+
+
+def _build_clip(variant: str, **options) -> Encoder:
+    return get_clip_encoder(variant, **options)
+
+
+def _build_clap(variant: str, **options) -> Encoder:
+    # the CLAP path is broken in the reference as committed (clap.py:136,152) and is a "next" row.
+    raise NotImplementedError("the CLAP audio encoder is not part of the clipcap_b200 hot path yet")
+
+
+_BUILDERS: Dict[str, Callable[..., Encoder]] = {"clip": _build_clip, "clap": _build_clap}
 
 
 def get_encoder(encoder_model_name: str, encoder_model_variant: str, normalize_embeddings: bool = False,
                 window_size: Optional[int] = None, use_windowed_embeddings: bool = False,
-                window_overlap_percentage: float = 0.0, device: str = "cuda") -> Tuple[Module, Callable]:
-    kwargs = {"normalize_embeddings": normalize_embeddings, "device": device}
-    if encoder_model_name == "clip":
-        return get_clip_encoder(encoder_model_variant, use_windowed_embeddings=use_windowed_embeddings,
-                                window_size=window_size, window_overlap_percentage=window_overlap_percentage, **kwargs)
-    elif encoder_model_name == "clap":
-        # the CLAP path is broken in the reference as committed (clap.py:136,152) and is a "next" row.
-        raise NotImplementedError("the CLAP audio encoder is not part of the clipcap_b200 hot path yet")
-    else:
+                window_overlap_percentage: float = 0.0, device: str = "cuda") -> Encoder:
+    builder = _BUILDERS.get(encoder_model_name)
+    if builder is None:
         raise ValueError(f"invalid encoder name: '{encoder_model_name}'")
+    return builder(encoder_model_variant, normalize_embeddings=normalize_embeddings, device=device,
+                   use_windowed_embeddings=use_windowed_embeddings, window_size=window_size,
+                   window_overlap_percentage=window_overlap_percentage)
 
 
-def get_encoder_from_config(config: EncoderConfig, device: str = "cpu") -> Tuple[Module, Callable]:
+def get_encoder_from_config(config: EncoderConfig, device: str = "cpu") -> Encoder:
     if config.encoder_model_name == "clip":
+        # YAML-safe variant names ("ViT-L_14") back to CLIP's ("ViT-L/14"); written back like the reference does (base.py:30)
         config.encoder_model_variant = config.encoder_model_variant.replace("_", "/")
-    return get_encoder(
-        config.encoder_model_name, config.encoder_model_variant, normalize_embeddings=config.normalize_embeddings,
-        use_windowed_embeddings=config.use_windowed_embeddings, window_size=config.window_size,
-        window_overlap_percentage=config.window_overlap_percentage, device=device)
+    options = {k: getattr(config, k) for k in ("normalize_embeddings", "use_windowed_embeddings", "window_size",
+                                                "window_overlap_percentage")}
+    return get_encoder(config.encoder_model_name, config.encoder_model_variant, device=device, **options)
 
 
-def get_encoder_from_model(model, device: str = "cpu") -> Tuple[Module, Callable]:
+def get_encoder_from_model(model, device: str = "cpu") -> Encoder:
     return get_encoder_from_config(model.config.encoder_config, device=device)

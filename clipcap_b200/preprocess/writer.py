@@ -1,66 +1,62 @@
-"""The reference's preprocess output format (clipcap/preprocess/writer.py:10-100): `encoder_config.yaml`,
-`embeddings/embeds_<id>.npy` ([N, E], dtype as produced by the encoder) and `captions/captions_<id>.parquet` (one
-`caption` column), `<id>` zero-padded to the width of the partition count. Paths go through fsspec like the reference."""
+"""Writer of the reference's preprocess output layout (clipcap/preprocess/writer.py:10-100), so a dataset encoded with
+the B200 ViT engine is read by the reference's training dataloader unchanged:
+
+    <out>/encoder_config.yaml                      EncoderConfig.to_dict()
+    <out>/embeddings/embeds_<id>.npy               [N, E] array, dtype as the encoder produced it
+    <out>/captions/captions_<id>.parquet           one column `caption`, row i belongs to embedding row i
+
+`<id>` is the partition number zero-padded to the digit count of the partition total. Paths go through fsspec (local
+paths, s3://, ...), as in the reference. `NumpyWriter` keeps the reference's constructor and call protocol
+(`writer(batch)` per encoded batch, `writer.flush()` once per partition)."""
 from __future__ import annotations
 
+import io
 import math
-from io import BytesIO
+from typing import List
 
 import fsspec
 import yaml
 
-from clipcap_b200.encoders.config import EncoderConfig
+from clipcap_b200.configs import EncoderConfig
 
 
 def save_config(config: EncoderConfig, output_folder: str) -> None:
-    fs, output_folder = fsspec.core.url_to_fs(output_folder)
-    fs.makedirs(output_folder, exist_ok=True)
-    with fs.open(output_folder + "/encoder_config.yaml", "w") as f:
-        yaml.dump(config.to_dict(), f, default_flow_style=False)
+    fs, root = fsspec.core.url_to_fs(output_folder)
+    fs.makedirs(root, exist_ok=True)
+    with fs.open(f"{root}/encoder_config.yaml", "w") as handle:
+        yaml.dump(config.to_dict(), handle, default_flow_style=False)
 
 
-class OutputSink:
-    def __init__(self, output_folder, partition_id, output_partition_count):
-        self.fs, output_folder = fsspec.core.url_to_fs(output_folder)
-        self.output_folder = output_folder
-        self.embed_folder = output_folder + "/embeddings"
-        self.captions_folder = output_folder + "/captions"
-        self.batch_num = partition_id
-        self.oom_partition_count = int(math.log10(output_partition_count)) + 1
-        self.fs.makedirs(self.embed_folder, exist_ok=True)
-        self.fs.makedirs(self.captions_folder, exist_ok=True)
-        self._reset()
-
-    def _reset(self):
-        self.embeddings, self.captions, self.batch_count = [], [], 0
-
-    def add(self, sample):
-        self.batch_count += sample["embeddings"].shape[0]
-        self.embeddings.append(sample["embeddings"])
-        self.captions.extend(sample["text"])
-
-    def flush(self):
-        if self.batch_count == 0:
-            return
-        import numpy as np
-        import pandas as pd
-        batch_num_str = str(self.batch_num).zfill(self.oom_partition_count)
-        with self.fs.open(self.embed_folder + "/embeds_" + batch_num_str + ".npy", "wb") as f:
-            buf = BytesIO()
-            np.save(buf, np.concatenate(self.embeddings))
-            f.write(buf.getbuffer())
-        df = pd.DataFrame(data=list(zip(self.captions)), columns=["caption"])
-        with self.fs.open(self.captions_folder + "/captions_" + batch_num_str + ".parquet", "wb") as f:
-            df.to_parquet(f)
-        self._reset()
+def _partition_tag(partition_id: int, partition_total: int) -> str:
+    return str(partition_id).zfill(int(math.log10(partition_total)) + 1)
 
 
 class NumpyWriter:
+    """Accumulates the (embeddings, text) batches of one partition in memory and writes the pair of files on flush()."""
+
     def __init__(self, partition_id, output_folder, output_partition_count):
-        self.sink = OutputSink(output_folder, partition_id, output_partition_count)
+        self._fs, root = fsspec.core.url_to_fs(output_folder)
+        self._tag = _partition_tag(partition_id, output_partition_count)
+        self._embed_path = f"{root}/embeddings/embeds_{self._tag}.npy"
+        self._caption_path = f"{root}/captions/captions_{self._tag}.parquet"
+        for sub in ("embeddings", "captions"):
+            self._fs.makedirs(f"{root}/{sub}", exist_ok=True)
+        self._chunks: List = []
+        self._texts: List[str] = []
 
-    def __call__(self, batch):
-        self.sink.add(batch)
+    def __call__(self, batch) -> None:
+        self._chunks.append(batch["embeddings"])
+        self._texts.extend(batch["text"])
 
-    def flush(self):
-        self.sink.flush()
+    def flush(self) -> None:
+        if not self._chunks or sum(c.shape[0] for c in self._chunks) == 0:
+            return
+        import numpy as np
+        import pandas as pd
+        raw = io.BytesIO()
+        np.save(raw, np.concatenate(self._chunks))
+        with self._fs.open(self._embed_path, "wb") as handle:
+            handle.write(raw.getbuffer())
+        with self._fs.open(self._caption_path, "wb") as handle:
+            pd.DataFrame({"caption": self._texts}).to_parquet(handle)
+        self._chunks, self._texts = [], []

@@ -140,3 +140,23 @@ def test_training_surface_matches_reference():
     assert tokens.tolist() == [[4, 9, 0]]  # padding rewritten in place before anything else, like the reference (model.py:104)
     with pytest.raises(NotImplementedError):  # fine-tuning the language model is not built
         ClipCapModel(cfg).training_step((tokens, torch.zeros(1, 64)), 0)
+
+
+def test_logit_filters_equal_the_reference_functions():
+    """clipcap_b200.inference.utils (tensor versions of the decode filters) against clipcap/inference/utils.py itself."""
+    import pytest
+    import torch
+    from oracle import ref_runner as RR
+    if not RR.available():
+        pytest.skip("needs /root/reference (build container only)")
+    RR.import_reference()
+    import clipcap.inference.utils as U
+    from clipcap_b200.inference import utils as V
+    g = torch.Generator().manual_seed(0)
+    for k, p in [(0, 0.9), (5, 0.0), (7, 0.5), (0, 0.0), (1, 0.3), (200, 0.99)]:
+        x = torch.randn(101, generator=g)
+        assert torch.equal(V.top_k_top_p_filtering(x.clone(), k, p), U.top_k_top_p_filtering(x.clone(), k, p)), (k, p)
+    x, t = torch.randn(50, generator=g), torch.tensor([3, 7, 7, 11])
+    assert torch.equal(V.repetition_penalty_apply(x.clone(), t, 1.3), U.repetition_penalty_apply(x.clone(), t, 1.3))
+    assert torch.equal(V.sentence_length_penalty_apply(x.clone(), t, 13, 5, 50, 1.0),
+                       U.sentence_length_penalty_apply(x.clone(), t, 13, 5, 50, 1.0))
