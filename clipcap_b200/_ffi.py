@@ -40,6 +40,12 @@ class cc_vit_cfg(C.Structure):
                 ("heads", C.c_int32), ("mlp_dim", C.c_int32), ("out_dim", C.c_int32), ("eps", C.c_float)]
 
 
+class cc_clap_cfg(C.Structure):
+    _fields_ = [("num_mel_bins", C.c_int32), ("spec_size", C.c_int32), ("patch", C.c_int32), ("embed", C.c_int32),
+                ("depths", C.c_int32 * 4), ("heads", C.c_int32 * 4), ("window", C.c_int32),
+                ("projection_dim", C.c_int32), ("eps", C.c_float)]
+
+
 class cc_mapper_cfg(C.Structure):
     _fields_ = [("kind", C.c_int32), ("E", C.c_int32), ("d", C.c_int32), ("P", C.c_int32), ("K", C.c_int32),
                 ("H", C.c_int32), ("L", C.c_int32), ("W", C.c_int32), ("use_pos", C.c_int32), ("eps", C.c_float)]
@@ -68,6 +74,10 @@ PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {
     "cc_vit_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "cc_vit_last_launches": (_i, [_vp]),
     "cc_vit_destroy": (None, [_vp]),
+    "cc_clap_create": (_i, [_pp, C.POINTER(cc_clap_cfg), C.POINTER(cc_tensor), _i, _i]),
+    "cc_clap_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "cc_clap_last_launches": (_i, [_vp]),
+    "cc_clap_destroy": (None, [_vp]),
     "cc_mapper_create": (_i, [_pp, C.POINTER(cc_mapper_cfg), C.POINTER(cc_tensor), _i, _i]),
     "cc_mapper_forward": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp]),
     "cc_mapper_last_launches": (_i, [_vp]),

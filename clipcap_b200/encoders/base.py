@@ -1,6 +1,6 @@
 """Encoder factories of the drop-in surface — `get_encoder`, `get_encoder_from_config`, `get_encoder_from_model` with the
 reference's names, arguments, return value `(encoder module, transform)` and error for an unknown encoder name
-(clipcap/encoders/base.py:10-39). Dispatch is a table of builders; only the CLIP image tower is built here."""
+(clipcap/encoders/base.py:10-39). Dispatch is a table of builders: the CLIP image towers and the CLAP audio tower."""
 from typing import Callable, Dict, Optional, Tuple
 
 from torch.nn import Module
@@ -15,9 +15,10 @@ def _build_clip(variant: str, **options) -> Encoder:
     return get_clip_encoder(variant, **options)
 
 
-def _build_clap(variant: str, **options) -> Encoder:
-    # the CLAP path is broken in the reference as committed (clap.py:136,152) and is a "next" row.
-    raise NotImplementedError("the CLAP audio encoder is not part of the clipcap_b200 hot path yet")
+def _build_clap(variant: str, normalize_embeddings: bool = False, device: str = "cuda", **_unused) -> Encoder:
+    # the reference's get_clap_encoder takes no variant / window options (clap.py:133); HTSAT-tiny is the only tower
+    from clipcap_b200.encoders.clap import get_clap_encoder
+    return get_clap_encoder(normalize_embeddings=normalize_embeddings, device=device)
 
 
 _BUILDERS: Dict[str, Callable[..., Encoder]] = {"clip": _build_clip, "clap": _build_clap}

@@ -70,6 +70,59 @@ class VitEngine(_Handle):
         return _ffi.lib().cc_vit_last_launches(self._h)
 
 
+class ClapEngine(_Handle):
+    """cc_clap_* — CLAP audio tower (HTSAT Swin encoder + audio projection). `weights`: tensors under the state_dict keys
+    of transformers' ClapAudioModelWithProjection (`audio_model.audio_encoder.*`, `audio_projection.*`)."""
+    _destroy_name = "cc_clap_destroy"
+
+    def __init__(self, weights: Dict[str, torch.Tensor], num_mel_bins=64, spec_size=256, patch=4, embed=96,
+                 depths=(2, 2, 6, 2), heads=(4, 8, 16, 32), window=8, projection_dim=512, eps=1e-5, max_batch=64,
+                 device="cuda"):
+        super().__init__()
+        if len(depths) != 4 or len(heads) != 4:
+            raise ValueError("the CLAP audio tower has 4 stages")
+        self.device = torch.device(device)
+        self.cfg = _ffi.cc_clap_cfg(num_mel_bins, spec_size, patch, embed, (C.c_int32 * 4)(*depths),
+                                    (C.c_int32 * 4)(*heads), window, projection_dim, eps)
+        self.max_batch = max_batch
+        self.stage_shapes = [((spec_size // patch >> i) ** 2, embed << i) for i in range(4)]  # (tokens, channels)
+        wanted = ("audio_model.audio_encoder.", "audio_projection.")
+        skip = ("fusion_model", "mel_conv2d", "relative_position_index", "num_batches_tracked")
+        weights = {k: v for k, v in weights.items() if k.startswith(wanted) and not any(x in k for x in skip)}
+        with torch.cuda.device(self.device):
+            arr, keep = _ffi.make_tensor_table(_named(weights, self.device))
+            _ffi.check(_ffi.lib().cc_clap_create(C.byref(self._h), C.byref(self.cfg), arr, len(keep), max_batch))
+            torch.cuda.synchronize()
+
+    def forward(self, mel: torch.Tensor, normalize: bool = False, out_dtype: Optional[torch.dtype] = None,
+                stop_after_stage: int = -1):
+        """mel: [B, channels, T, num_mel_bins] fp32 / fp16 (channel 0 = the global view). Returns [B, projection_dim]; with
+        `stop_after_stage` = s >= 0, the fp32 token stream [B, tokens_s, channels_s] after stage s instead."""
+        _require_cuda(mel, "mel")
+        if mel.dim() != 4 or mel.shape[3] != self.cfg.num_mel_bins:
+            raise ValueError(f"mel must be [B, channels, T, {self.cfg.num_mel_bins}], got {tuple(mel.shape)}")
+        if mel.dtype not in (torch.float32, torch.float16):
+            mel = mel.float()
+        mel = mel.contiguous()
+        B = mel.shape[0]
+        out = torch.empty(B, self.cfg.projection_dim, device=mel.device, dtype=out_dtype or mel.dtype)
+        dump = None
+        if stop_after_stage >= 0:
+            tokens, ch = self.stage_shapes[stop_after_stage]
+            dump = torch.empty(B, tokens, ch, device=mel.device, dtype=torch.float32)
+        with torch.cuda.device(mel.device):
+            _ffi.check(_ffi.lib().cc_clap_forward(self._h, mel.data_ptr(), _ffi.torch_dtype_code(mel), B, mel.shape[1],
+                                                  mel.shape[2], int(bool(normalize)), out.data_ptr(),
+                                                  _ffi.torch_dtype_code(out), stop_after_stage,
+                                                  dump.data_ptr() if dump is not None else None,
+                                                  _ffi.current_stream_ptr()))
+        return dump if dump is not None else out
+
+    @property
+    def last_launches(self) -> int:
+        return _ffi.lib().cc_clap_last_launches(self._h)
+
+
 class MapperEngine(_Handle):
     """cc_mapper_* — TransformerMapper / TransformerMapperWindowed / MLP mapper. Keys relative to `transformer_mapper.`"""
     _destroy_name = "cc_mapper_destroy"

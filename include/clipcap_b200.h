@@ -181,6 +181,36 @@ int cc_gpt2_last_launches(cc_gpt2* h);
 void cc_gpt2_destroy(cc_gpt2* h);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Stage 1 (audio) — CLAP audio tower (HTSAT-tiny Swin encoder + audio projection), BASELINE configs[4].
+ * Replaces: CLAPModel.forward -> clap_model.get_audio_embedding_from_data (clipcap/encoders/clap.py:105-131; laion_clap
+ * is not installed, the arithmetic is transformers' ClapAudioModelWithProjection, modeling_clap.py:1725-1775 with
+ * ClapAudioEncoder.forward :814-918). Weight names are that module's state_dict keys (audio_model.audio_encoder.*,
+ * audio_projection.linear{1,2}.*). Only the `is_longer == False` path (clips no longer than the 10 s window: the global
+ * mel channel alone feeds the patch embedding) is implemented; fused long-clip inputs are rejected by the Python wrapper.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct cc_clap_cfg {
+  int32_t num_mel_bins;   /* 64 */
+  int32_t spec_size;      /* 256: side of the folded spectrogram image */
+  int32_t patch;          /* 4 (size == stride) */
+  int32_t embed;          /* 96: channels of stage 0; stage i has embed << i */
+  int32_t depths[4];      /* 2 2 6 2 */
+  int32_t heads[4];       /* 4 8 16 32 (head dim must be 24) */
+  int32_t window;         /* 8 */
+  int32_t projection_dim; /* 512 */
+  float eps;              /* 1e-5 */
+} cc_clap_cfg;
+typedef struct cc_clap cc_clap;
+
+int cc_clap_create(cc_clap** h, const cc_clap_cfg* cfg, const cc_tensor* weights, int n_weights, int max_batch);
+/* mel: [B, channels, T <= spec_size * spec_size / num_mel_bins, num_mel_bins] log-mel features (channel 0 is used), dtype
+ * mel_dtype; out: [B, projection_dim]. stop_after_stage >= 0 with dump != NULL copies the fp32 token stream after that
+ * stage's blocks ([B * tokens, channels] of the stage) into `dump` and returns without producing `out` (debug / tests). */
+int cc_clap_forward(cc_clap* h, const void* mel, int mel_dtype, int B, int channels, int T, int normalize, void* out,
+                    int out_dtype, int stop_after_stage, float* dump, void* stream);
+int cc_clap_last_launches(cc_clap* h);
+void cc_clap_destroy(cc_clap* h);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Training step of the prefix mapper with the language model frozen.
  * Replaces: ClipCapModel.forward + training_step (clipcap/model/model.py:43-58, 94-113) followed by loss.backward() for
  * ClipCapModelPrefixOnly (model.py:116-123: only transformer_mapper parameters train, the LM stays in eval mode):

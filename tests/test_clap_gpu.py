@@ -1,0 +1,104 @@
+"""CLAP audio tower (cc_clap_*, SURVEY §8f rank 4 / BASELINE configs[4]) against oracle/restate_clap.py, which is itself
+pinned to transformers' ClapAudioModelWithProjection (tests/test_clap_oracle_cpu.py). Tolerances: the CUDA path feeds
+fp16 operands to the tensor cores and keeps the residual stream, LayerNorm statistics and softmax in fp32 — relative L2
+error of the [B, 512] embedding <= 1e-2 and cosine >= 0.9999 per sample, written below."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import restate_clap as RC
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-2
+COS = 0.9999
+
+
+def _weights(cfg, seed):
+    m = RC.hf_clap(cfg, seed=seed)
+    return {k: v.detach() for k, v in m.state_dict().items()}
+
+
+def _oracle_stages(w, mel, cfg):
+    """clap_audio_embed unrolled so the token stream after every stage's blocks is returned too."""
+    x = RC._bn_eval(mel.float().transpose(1, 3), w, RC.ENC + "batch_norm.").transpose(1, 3)
+    img = RC.reshape_mel2img(x, cfg)
+    x = RC.patch_embed(w, img, torch.zeros(mel.shape[0], 1, dtype=torch.bool), cfg)
+    grid = cfg.spec_size // cfg.patch
+    streams = []
+    for i, (depth, heads) in enumerate(zip(cfg.depths, cfg.heads)):
+        res = (grid >> i, grid >> i)
+        for j in range(depth):
+            x = RC.swin_block(w, f"{RC.ENC}layers.{i}.blocks.{j}.", x, res, heads, 0 if j % 2 == 0 else cfg.window // 2, cfg)
+        streams.append(x)
+        if i < len(cfg.depths) - 1:
+            x = RC.patch_merge(w, f"{RC.ENC}layers.{i}.downsample.", x, res, cfg)
+    return streams
+
+
+def _engine(w, cfg, max_batch, device):
+    from clipcap_b200.engine import ClapEngine
+    return ClapEngine(w, cfg.num_mel_bins, cfg.spec_size, cfg.patch, cfg.embed, cfg.depths, cfg.heads, cfg.window,
+                      cfg.projection_dim, cfg.eps, max_batch=max_batch, device=device)
+
+
+@pytest.mark.parametrize("frames", [1001, 1024, 313])
+def test_clap_embedding_matches_oracle(cuda_device, frames):
+    """HTSAT-tiny at full depth; 1001 frames is the 10 s clip of BASELINE configs[4] (bicubic stretch to 1024)."""
+    cfg = RC.ClapCfg()
+    w = _weights(cfg, seed=0)
+    B = 3
+    mel = torch.randn(B, 4, frames, 64, generator=torch.Generator().manual_seed(frames))
+    with torch.no_grad():
+        want = RC.clap_audio_embed(w, mel, torch.zeros(B, 1, dtype=torch.bool), cfg)
+    eng = _engine(w, cfg, 4, cuda_device)
+    got = eng.forward(mel.to(cuda_device)).float().cpu()
+    assert tuple(got.shape) == (B, 512)
+    assert rel_err(got, want) < REL
+    assert torch.nn.functional.cosine_similarity(got, want, dim=-1).min() > COS
+    assert eng.last_launches > 0
+    # fp16 features at the boundary, fused L2 normalisation, a batch of one through the same handle
+    got16 = eng.forward(mel[:1].half().to(cuda_device), normalize=True).float().cpu()
+    ref = want[:1] / want[:1].norm(dim=-1, keepdim=True)
+    assert rel_err(got16, ref) < REL
+
+
+def test_clap_stage_streams_match_oracle(cuda_device):
+    """Token stream after each Swin stage (shifted windows, region masks and patch merging are all index arithmetic in the
+    CUDA path): every stage must agree with the roll / partition / reverse formulation of the oracle."""
+    cfg = RC.ClapCfg(depths=(2, 2, 2, 2))
+    w = _weights(cfg, seed=2)
+    mel = torch.randn(2, 1, 1001, 64, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        want = _oracle_stages(w, mel, cfg)
+    eng = _engine(w, cfg, 2, cuda_device)
+    for s, ref in enumerate(want):
+        got = eng.forward(mel.to(cuda_device), stop_after_stage=s).cpu()
+        assert got.shape == ref.shape
+        assert rel_err(got, ref) < REL, f"stage {s}"
+
+
+def test_clap_wrapper_and_errors(cuda_device):
+    from clipcap_b200._ffi import CCError
+    from clipcap_b200.encoders import get_encoder
+    from clipcap_b200.encoders.clap import CLAPModel, ClapAudioTower
+    torch.manual_seed(0)
+    model, transform = get_encoder("clap", "", normalize_embeddings=True, device=cuda_device)
+    assert isinstance(model, CLAPModel) and isinstance(model.model, ClapAudioTower)
+    mel = torch.randn(2, 4, 1001, 64)
+    out = model(transform(mel).to(cuda_device))
+    assert tuple(out.shape) == (2, 512)
+    assert torch.allclose(out.float().norm(dim=-1).cpu(), torch.ones(2), atol=1e-3)
+    sd = {k: v.detach().cpu() for k, v in model.model.clap.state_dict().items()}
+    with torch.no_grad():
+        want = RC.clap_audio_embed(sd, mel, torch.zeros(2, 1, dtype=torch.bool), RC.ClapCfg())
+    want = want / want.norm(dim=-1, keepdim=True)
+    assert rel_err(out.float().cpu(), want) < REL
+    with pytest.raises(NotImplementedError):                  # long-clip feature fusion is not built
+        model.model.get_audio_embedding_from_mel(mel.to(cuda_device), is_longer=torch.tensor([[True], [False]]))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model.model._get_engine((2,)).forward(mel)
+    with pytest.raises(CCError, match="CC_ESHAPE"):           # more frames than the folded image holds
+        model.model._get_engine((2,)).forward(torch.randn(1, 1, 1025, 64, device=cuda_device))
+    with pytest.raises(CCError, match="CC_ESHAPE"):           # head dim other than 24
+        _engine(sd, RC.ClapCfg(heads=(2, 8, 16, 32)), 2, cuda_device)
