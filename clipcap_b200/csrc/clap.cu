@@ -9,7 +9,7 @@
 //         4x4/4 patch gather: ONE kernel]--> cols [B*4096, 16] --tcgen05 GEMM--> tokens [B*4096, 96] fp32 --LayerNorm-->
 //   4 stages of Swin blocks (depths 2/2/6/2, 96..768 channels, heads 4..32 => head dim 24, 8x8 windows, odd blocks shifted
 //   by 4): LN -> QKV GEMM (q, k, v weights concatenated) -> window attention -> out-proj GEMM (fp32 residual, TMA
-//   reduce-add) -> LN -> fc1 GEMM -> exact GELU -> fc2 GEMM (residual); between stages 2x2 patch merging (gather ->
+//   reduce-add) -> LN -> fc1 GEMM with the exact (erf) GELU in its epilogue -> fc2 GEMM (residual); between stages 2x2 patch merging (gather ->
 //   LN(4C) -> GEMM 4C -> 2C);  final LN + mean over the 64 tokens -> Linear + ReLU -> Linear.
 // Tokens stay in image order the whole time: the cyclic shift and the window partition / reverse of the reference are
 // index arithmetic inside the attention kernel (it gathers its window's rows of the QKV matrix and scatters its output
@@ -29,7 +29,8 @@ struct cc_clap {
   struct Block {
     const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqkv, *bo, *b1, *b2;
     const __half *wqkv, *wo, *w1, *w2;
-    const float* rel_bias;  // [heads][64][64] gathered from relative_position_bias_table
+    const float* rel_bias;     // [heads][64][64] gathered from relative_position_bias_table
+    const __half* rel_bias16;  // the same in fp16 (what the tensor-core window attention keeps in shared memory)
     cc::GemmPlan p_qkv, p_o, p_1, p_2;
   };
   struct Stage {
@@ -192,18 +193,176 @@ clap_window_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out
   for (int c = 0; c < CW_HD; c += 2) *reinterpret_cast<__half2*>(dst + c) = __floats2half2_rn(o[c] * inv, o[c + 1] * inv);
 }
 
-// ---------------------------------------------------------------- exact GELU, patch merging gather, final LN + mean pool
-__global__ void gelu_erf_kernel(__half2* __restrict__ x, long long n2) {
+// ---------------------------------------------------------------- window attention on mma.sync (the one that runs)
+// CTA = 16 warps = 4 window slots x 4 heads: a slot's 4 warps own one (window, group of 4 heads) at a time — the 96 q, 96 k
+// and 96 v columns of those heads for the window's 64 tokens (36 KB of shared memory), each warp one head: S = Q K^T as
+// 4 row strips of 16 x 64 (k = 24 = one m16n8k16 + one m16n8k8 step), softmax on the accumulator registers, O = P V with P
+// re-used from those registers as the A operand. Slots synchronise on their own named barrier, so one slot's cp.async
+// gather overlaps the others' math. The relative-position bias of the CTA's head group sits in shared memory as fp16
+// for the CTA's lifetime; a CTA walks the windows of one head group.
+constexpr int CW_LD = 104;       // row pitch of the q / k / v tiles in halves: 208 B, conflict-free ldmatrix
+constexpr int CW_BLD = 72;       // row pitch of the bias tile in halves
+constexpr int CW_SLOTS = 4;
+constexpr int CW_TILE = 64 * CW_LD;  // halves per q / k / v tile
+constexpr size_t CW_SMEM = static_cast<size_t>(4 * 64 * CW_BLD + CW_SLOTS * 3 * CW_TILE) * sizeof(__half) + CW_SLOTS * 64 * sizeof(int);
+
+__device__ __forceinline__ void slot_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
+
+__global__ void __launch_bounds__(CW_SLOTS * 128, 1)
+clap_window_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, const __half* __restrict__ rel_bias16,
+                            int res, int shift, int C, int n_windows, int ctas_per_group, float scale_log2e) {
+  extern __shared__ __align__(16) unsigned char cw_smem[];
+  __half* bias_s = reinterpret_cast<__half*>(cw_smem);                     // [4 heads][64][CW_BLD]
+  __half* tiles = bias_s + 4 * 64 * CW_BLD;                                // [slot][q, k, v][64][CW_LD]
+  int* region_s = reinterpret_cast<int*>(tiles + CW_SLOTS * 3 * CW_TILE);  // [slot][64]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slot = warp >> 2, head_l = warp & 3, st = tid & 127;  // st: thread index inside the slot
+  const int group = blockIdx.x / ctas_per_group, cta_in_group = blockIdx.x - group * ctas_per_group;
+  const int wpr = res >> 3, wps = wpr * wpr;  // windows per row / per sample
+  // bias of this head group (constant weights: may be read before the predecessor kernel has finished)
+  for (int i = tid; i < 4 * 64 * 8; i += blockDim.x) {  // 16-byte pieces: [head][row][8 pieces]
+    const int piece = i & 7, row = (i >> 3) & 63, h = i >> 9;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(rel_bias16 + ((static_cast<long long>(group) * 4 + h) * 64 + row) * 64) + piece);
+    *reinterpret_cast<uint4*>(bias_s + (h * 64 + row) * CW_BLD + piece * 8) = v;
+  }
   pdl_launch_dependents();
   pdl_wait();
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n2;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float2 v = __half22float2(x[i]);
-    x[i] = __floats2half2_rn(0.5f * v.x * (1.f + erff(v.x * 0.70710678118654752f)),
-                             0.5f * v.y * (1.f + erff(v.y * 0.70710678118654752f)));
+  __syncthreads();
+  __half* qs = tiles + slot * 3 * CW_TILE;
+  __half* ks = qs + CW_TILE;
+  __half* vs = ks + CW_TILE;
+  int* regs = region_s + slot * 64;
+  const uint32_t qs_u = smem_u32(qs), ks_u = smem_u32(ks), vs_u = smem_u32(vs);
+  const int g = lane >> 2, q4 = lane & 3;
+  const __half* bias_h = bias_s + head_l * 64 * CW_BLD;
+  const float kLog2e = 1.4426950408889634f;
+
+  for (int w = cta_in_group * CW_SLOTS + slot; w < n_windows; w += ctas_per_group * CW_SLOTS) {
+    const long long b = w / wps;
+    const int win = w - static_cast<int>(b) * wps;
+    const int wy = win / wpr, wx = win - wy * wpr;
+    const long long sample_row0 = b * res * res;
+    slot_barrier(slot);  // the previous window's output tile has been stored
+    // ---- gather: 64 tokens x {q, k, v} x 12 pieces of 16 B
+#pragma unroll 3
+    for (int m = 0; m < 18; ++m) {
+      const int k = st + 128 * m;
+      const int tok = k / 36, rem = k - tok * 36, which = rem / 12, piece = rem - which * 12;
+      int oy = wy * 8 + (tok >> 3) + shift, ox = wx * 8 + (tok & 7) + shift;
+      oy -= oy >= res ? res : 0;
+      ox -= ox >= res ? res : 0;
+      const __half* src = qkv + (sample_row0 + static_cast<long long>(oy) * res + ox) * (3LL * C) + which * C + group * 96 + piece * 8;
+      cp_async_16(qs_u + static_cast<uint32_t>((which * CW_TILE + tok * CW_LD + piece * 8) * 2), src, true);
+    }
+    cp_async_commit();
+    if (st < 64) {
+      int region = 0;
+      if (shift > 0) {
+        const int sy = wy * 8 + (st >> 3), sx = wx * 8 + (st & 7);
+        const int ry = sy < res - 8 ? 0 : (sy < res - shift ? 1 : 2);
+        const int rx = sx < res - 8 ? 0 : (sx < res - shift ? 1 : 2);
+        region = ry * 3 + rx;
+      }
+      regs[st] = region;
+    }
+    cp_async_wait<0>();
+    slot_barrier(slot);
+    // ---- this warp's head: the K fragments stay in registers for the four row strips
+    const int hc = head_l * CW_HD;  // first column of the head inside the tiles
+    uint32_t kf[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int mi = lane >> 3;
+      ldmatrix_x4(kf[nt], ks_u + static_cast<uint32_t>(((nt * 8 + (lane & 7)) * CW_LD + hc + (mi < 2 ? mi : 2) * 8) * 2));
+    }
+#pragma unroll 1
+    for (int mt = 0; mt < 4; ++mt) {
+      uint32_t qa[4], qb[2];
+      {
+        const int mi = lane >> 3;
+        ldmatrix_x4(qa, qs_u + static_cast<uint32_t>(((mt * 16 + (lane & 7) + (mi & 1) * 8) * CW_LD + hc + (mi >> 1) * 8) * 2));
+        ldmatrix_x2(qb, qs_u + static_cast<uint32_t>(((mt * 16 + (lane & 15)) * CW_LD + hc + 16) * 2));
+      }
+      float sacc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+        mma_16816(sacc[nt], qa, kf[nt][0], kf[nt][1]);
+        mma_1688(sacc[nt], qb, kf[nt][2]);
+      }
+      // scores in the log2 domain: (q.k * scale + bias + mask) * log2(e); rows r0 = mt*16 + g and r0 + 8
+      const int r0 = mt * 16 + g;
+      const int reg_r0 = regs[r0], reg_r1 = regs[r0 + 8];
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(bias_h + r0 * CW_BLD + nt * 8 + 2 * q4));
+        const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(bias_h + (r0 + 8) * CW_BLD + nt * 8 + 2 * q4));
+        const int2 rc = *reinterpret_cast<const int2*>(regs + nt * 8 + 2 * q4);  // regions of this thread's two columns
+        sacc[nt][0] = sacc[nt][0] * scale_log2e + (b0.x + (rc.x != reg_r0 ? -100.f : 0.f)) * kLog2e;
+        sacc[nt][1] = sacc[nt][1] * scale_log2e + (b0.y + (rc.y != reg_r0 ? -100.f : 0.f)) * kLog2e;
+        sacc[nt][2] = sacc[nt][2] * scale_log2e + (b1.x + (rc.x != reg_r1 ? -100.f : 0.f)) * kLog2e;
+        sacc[nt][3] = sacc[nt][3] * scale_log2e + (b1.y + (rc.y != reg_r1 ? -100.f : 0.f)) * kLog2e;
+        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pa[4][4];  // P as the A operand of the four 16-token k-steps
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float p0 = fast_exp2(sacc[nt][0] - mx0), p1 = fast_exp2(sacc[nt][1] - mx0);
+        const float p2 = fast_exp2(sacc[nt][2] - mx1), p3 = fast_exp2(sacc[nt][3] - mx1);
+        sum0 += p0 + p1;
+        sum1 += p2 + p3;
+        pa[nt >> 1][(nt & 1) * 2] = pack_half2(p0, p1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_half2(p2, p3);
+      }
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      float oacc[3][4];
+#pragma unroll
+      for (int n3 = 0; n3 < 3; ++n3) oacc[n3][0] = oacc[n3][1] = oacc[n3][2] = oacc[n3][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {  // V fragments of 16 tokens: (tokens, hd 0-7 | 8-15) transposed x4, hd 16-23 x2
+        const int mi = lane >> 3;
+        uint32_t t4[4], t2[2];
+        ldmatrix_x4_trans(t4, vs_u + static_cast<uint32_t>(((kk * 16 + (lane & 7) + (mi & 1) * 8) * CW_LD + hc + (mi >> 1) * 8) * 2));
+        ldmatrix_x2_trans(t2, vs_u + static_cast<uint32_t>(((kk * 16 + (lane & 15)) * CW_LD + hc + 16) * 2));
+        mma_16816(oacc[0], pa[kk], t4[0], t4[1]);
+        mma_16816(oacc[1], pa[kk], t4[2], t4[3]);
+        mma_16816(oacc[2], pa[kk], t2[0], t2[1]);
+      }
+      // O over this head's q columns of the strip (its fragments are in registers already; no other warp reads them)
+      const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+      __syncwarp();
+#pragma unroll
+      for (int n3 = 0; n3 < 3; ++n3) {
+        *reinterpret_cast<uint32_t*>(qs + r0 * CW_LD + hc + n3 * 8 + 2 * q4) = pack_half2(oacc[n3][0] * inv0, oacc[n3][1] * inv0);
+        *reinterpret_cast<uint32_t*>(qs + (r0 + 8) * CW_LD + hc + n3 * 8 + 2 * q4) = pack_half2(oacc[n3][2] * inv1, oacc[n3][3] * inv1);
+      }
+    }
+    slot_barrier(slot);
+    // ---- scatter the 64 x 96 output tile: 12 pieces of 16 B per token
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+      const int k = st + 128 * m;
+      const int tok = k / 12, piece = k - tok * 12;
+      int oy = wy * 8 + (tok >> 3) + shift, ox = wx * 8 + (tok & 7) + shift;
+      oy -= oy >= res ? res : 0;
+      ox -= ox >= res ? res : 0;
+      const uint4 v = *reinterpret_cast<const uint4*>(qs + tok * CW_LD + piece * 8);
+      *reinterpret_cast<uint4*>(out + (sample_row0 + static_cast<long long>(oy) * res + ox) * C + group * 96 + piece * 8) = v;
+    }
   }
 }
 
+// ---------------------------------------------------------------- patch merging gather, final LN + mean pool
 // out[b, y2 * (res/2) + x2, q * C + c] = x[b, (2 y2 + dy_q) * res + 2 x2 + dx_q, c], q = 0..3 <-> (dy, dx) = (0,0), (1,0), (0,1), (1,1)
 __global__ void clap_merge_gather_kernel(const float4* __restrict__ x, float4* __restrict__ out, int res, int C4, long long n) {
   pdl_launch_dependents();
@@ -371,6 +530,7 @@ int clap_build(cc_clap* m, const cc_tensor* w, int nw) {
     st.C = C0 << si;
     st.heads = c.heads[si];
     st.res = m->grid0 >> si;
+    CC_REQUIRE(st.heads % 4 == 0, CC_ESHAPE, "clap: stage %d has %d heads (kernels take groups of 4)", si, st.heads);
     CC_REQUIRE(st.C % st.heads == 0 && st.C / st.heads == CW_HD, CC_ESHAPE, "clap: stage %d head dim %d (kernels need %d)", si,
                st.C / st.heads, CW_HD);
     CC_REQUIRE(st.res >= ws && st.res % ws == 0, CC_ESHAPE, "clap: stage %d resolution %d vs window %d", si, st.res, ws);
@@ -435,10 +595,16 @@ int clap_build(cc_clap* m, const cc_tensor* w, int nw) {
         CC_TRY(A.alloc_t(&d, bias.size()));
         CC_CUDA(cudaMemcpy(d, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
         bk.rel_bias = d;
+        std::vector<__half> bias16(bias.size());
+        for (size_t i = 0; i < bias.size(); ++i) bias16[i] = __float2half(bias[i]);
+        __half* d16 = nullptr;
+        CC_TRY(A.alloc_t(&d16, bias16.size()));
+        CC_CUDA(cudaMemcpy(d16, bias16.data(), bias16.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        bk.rel_bias16 = d16;
       }
       CC_TRY(gemm_plan(&bk.p_qkv, m->ln16, C, rows, bk.wqkv, 3 * C, C, EPI_F16_NONE, bk.bqkv, m->qkv16, 3 * C));
       CC_TRY(gemm_plan(&bk.p_o, m->att16, C, rows, bk.wo, C, C, EPI_RESID_F32, bk.bo, m->x, C));
-      CC_TRY(gemm_plan(&bk.p_1, m->ln16, C, rows, bk.w1, 4 * C, C, EPI_F16_NONE, bk.b1, m->mlp16, 4 * C));
+      CC_TRY(gemm_plan(&bk.p_1, m->ln16, C, rows, bk.w1, 4 * C, C, EPI_F16_GELU_ERF, bk.b1, m->mlp16, 4 * C));
       CC_TRY(gemm_plan(&bk.p_2, m->mlp16, 4 * C, rows, bk.w2, C, 4 * C, EPI_RESID_F32, bk.b2, m->x, C));
       stage.release();
     }
@@ -522,6 +688,10 @@ int cc_clap_forward(cc_clap* m, const void* mel, int mel_dtype, int B, int chann
              T, S * ratio);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   m->launches = 0;
+  static const bool scalar_attn = getenv("CLIPCAP_B200_CLAP_SCALAR_ATTN") != nullptr;  // development A/B switch
+  static const cudaError_t smem_attr = cudaFuncSetAttribute(clap_window_attn_mma_kernel,
+                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CW_SMEM));
+  CC_CUDA(smem_attr);
   const int g0 = m->grid0;
   const long long tokens0 = static_cast<long long>(B) * g0 * g0;
   const long long sample_stride = static_cast<long long>(channels) * T * F;
@@ -552,16 +722,24 @@ int cc_clap_forward(cc_clap* m, const void* mel, int mel_dtype, int B, int chann
       const int shift = (bi % 2 == 1 && res > c.window) ? c.window / 2 : 0;
       CC_TRY(layernorm_run(m->x, C, bk.ln1_g, bk.ln1_b, m->ln16, C, rows, C, c.eps, s));
       CC_TRY(gemm_run(bk.p_qkv, rows, s));
-      CC_CUDA(launch_pdl(clap_window_attn_kernel, dim3(windows, st.heads), dim3(64), 0, s,
-                         static_cast<const __half*>(m->qkv16), m->att16, bk.rel_bias, res, ws, shift, C, st.heads,
-                         1.0f / sqrtf(static_cast<float>(CW_HD))));
+      if (scalar_attn) {
+        CC_CUDA(launch_pdl(clap_window_attn_kernel, dim3(windows, st.heads), dim3(64), 0, s,
+                           static_cast<const __half*>(m->qkv16), m->att16, bk.rel_bias, res, ws, shift, C, st.heads,
+                           1.0f / sqrtf(static_cast<float>(CW_HD))));
+      } else {
+        const int groups = st.heads / 4;
+        int per = num_sms() / groups;
+        per = per < 1 ? 1 : per;
+        per = per > (windows + CW_SLOTS - 1) / CW_SLOTS ? (windows + CW_SLOTS - 1) / CW_SLOTS : per;
+        CC_CUDA(launch_pdl(clap_window_attn_mma_kernel, dim3(groups * per), dim3(CW_SLOTS * 128), CW_SMEM, s,
+                           static_cast<const __half*>(m->qkv16), m->att16, bk.rel_bias16, res, shift, C, windows, per,
+                           1.4426950408889634f / sqrtf(static_cast<float>(CW_HD))));
+      }
       CC_TRY(gemm_run(bk.p_o, rows, s));
       CC_TRY(layernorm_run(m->x, C, bk.ln2_g, bk.ln2_b, m->ln16, C, rows, C, c.eps, s));
       CC_TRY(gemm_run(bk.p_1, rows, s));
-      const long long n2 = static_cast<long long>(rows) * 4 * C / 2;
-      CC_CUDA(launch_pdl(gelu_erf_kernel, dim3(grid_for(n2, 256)), dim3(256), 0, s, reinterpret_cast<__half2*>(m->mlp16), n2));
       CC_TRY(gemm_run(bk.p_2, rows, s));
-      m->launches += 8;
+      m->launches += 7;
     }
     if (static_cast<int>(si) == stop_after_stage && dump != nullptr) {
       CC_CUDA(cudaMemcpyAsync(dump, m->x, static_cast<size_t>(rows) * C * sizeof(float), cudaMemcpyDeviceToDevice, s));

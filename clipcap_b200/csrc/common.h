@@ -119,6 +119,7 @@ enum Epi {
   EPI_ARGMAX,         // keys[m] = max over n of pack(acc, n)   (fused greedy LM head; no logits written)
   EPI_PARTIAL_F32,    // split-K: partial[split][m][n] = acc over this split's k-range (summed by layernorm_reduce)
   EPI_F16_HEADS,      // packed QKV projection written head-major: out[((b*3 + which)*H + h)*S + tok][64] = acc + bias
+  EPI_F16_GELU_ERF,   // C16 = 0.5 x (1 + erf(x / sqrt 2)): the exact GELU of the Swin MLP (CLAP audio tower)
   EPI_COUNT
 };
 

@@ -84,6 +84,7 @@ __device__ __forceinline__ float apply_act(float x) {
   if constexpr (EPI == EPI_F16_QUICKGELU) return act_quickgelu(x);
   if constexpr (EPI == EPI_F16_GELU_NEW) return act_gelu_new(x);
   if constexpr (EPI == EPI_F16_TANH) return act_tanh(x);
+  if constexpr (EPI == EPI_F16_GELU_ERF) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
   return x;
 }
 
@@ -95,7 +96,8 @@ __device__ __forceinline__ uint32_t float_order_key(float x) {
 template <int EPI>
 struct EpiTraits {
   static constexpr bool kTma =
-      EPI <= EPI_F16_TANH || EPI == EPI_RESID_F32 || EPI == EPI_PARTIAL_F32 || EPI == EPI_F16_HEADS;
+      EPI <= EPI_F16_TANH || EPI == EPI_F16_GELU_ERF || EPI == EPI_RESID_F32 || EPI == EPI_PARTIAL_F32 ||
+      EPI == EPI_F16_HEADS;
   static constexpr bool kF32 = EPI == EPI_RESID_F32 || EPI == EPI_PARTIAL_F32;
 };
 
@@ -603,6 +605,7 @@ int launch_epi(const GemmPlan& p, int bn_idx, int M, cudaStream_t s, int row0) {
     case EPI_ARGMAX: return launch<BN, EPI_ARGMAX, CG>(p, bn_idx, M, s, row0);
     case EPI_PARTIAL_F32: return launch<BN, EPI_PARTIAL_F32, CG>(p, bn_idx, M, s, row0);
     case EPI_F16_HEADS: return launch<BN, EPI_F16_HEADS, CG>(p, bn_idx, M, s, row0);
+    case EPI_F16_GELU_ERF: return launch<BN, EPI_F16_GELU_ERF, CG>(p, bn_idx, M, s, row0);
   }
   set_error("unknown GEMM epilogue %d", p.epi);
   return CC_EINVAL;
@@ -694,7 +697,7 @@ int gemm_plan(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __h
   // groups are written); fp32 logits and argmax keys use direct stores and get a copy of map_a as a placeholder.
   CC_REQUIRE(epi != EPI_PARTIAL_F32 && epi != EPI_F16_HEADS, CC_EINVAL,
              "gemm_plan: split-K / head-major plans are built with gemm_plan_partial / gemm_plan_heads");
-  if (epi <= EPI_F16_TANH || epi == EPI_RESID_F32)
+  if (epi <= EPI_F16_TANH || epi == EPI_F16_GELU_ERF || epi == EPI_RESID_F32)
     CC_TRY(encode_out_map(&p->map_c, out, epi == EPI_RESID_F32, max_rows, N, ldc));
   else
     p->map_c = p->map_a;

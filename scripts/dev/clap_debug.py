@@ -19,7 +19,7 @@ for s, ref in enumerate(stages):
     print("stage", s, "rel", rel_err(got, ref), "finite", bool(torch.isfinite(got).all()), flush=True)
 got = eng.forward(mel.cuda()).cpu()
 print("embed rel", rel_err(got, want), "launches", eng.last_launches, flush=True)
-big = torch.randn(64, 1, 1001, 64, device="cuda")
+big = torch.randn(64, 4, 1001, 64, device="cuda")
 for _ in range(3):
     eng.forward(big)
 torch.cuda.synchronize()
