@@ -29,8 +29,7 @@ struct cc_clap {
   struct Block {
     const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqkv, *bo, *b1, *b2;
     const __half *wqkv, *wo, *w1, *w2;
-    const float* rel_bias;     // [heads][64][64] gathered from relative_position_bias_table
-    const __half* rel_bias16;  // the same in fp16 (what the tensor-core window attention keeps in shared memory)
+    const __half* rel_bias16;  // [heads][64][64] fp16, gathered from relative_position_bias_table through the index
     cc::GemmPlan p_qkv, p_o, p_1, p_2;
   };
   struct Stage {
@@ -109,91 +108,8 @@ __global__ void clap_patches_kernel(const SRC* __restrict__ mel, long long sampl
   }
 }
 
-// ---------------------------------------------------------------- window attention (8x8 windows, head dim 24)
-// One CTA per (sample, window, head), one thread per query token. The window is defined in the cyclically shifted frame;
-// its tokens are gathered from / scattered to image order: shifted (sy, sx) <-> original ((sy + shift) % res, ...).
+// ---------------------------------------------------------------- window attention (8x8 windows, head dim 24) on mma.sync
 constexpr int CW_HD = 24;
-__global__ void __launch_bounds__(64)
-clap_window_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, const float* __restrict__ rel_bias,
-                        int res, int ws, int shift, int C, int heads, float scale) {
-  __shared__ float ks[64][CW_HD + 1], vs[64][CW_HD + 1];
-  const int n_tok = ws * ws;  // 64 (or res * res when the image is a single window)
-  const int wpr = res / ws;
-  const int head = blockIdx.y;
-  const int win = blockIdx.x % (wpr * wpr);
-  const long long b = blockIdx.x / (wpr * wpr);
-  const int wy = win / wpr, wx = win - wy * wpr;
-  const int i = threadIdx.x;
-  pdl_launch_dependents();
-  pdl_wait();
-  const int ty = i / ws, tx = i - ty * ws;
-  const int sy = wy * ws + ty, sx = wx * ws + tx;
-  const int oy = (sy + shift) % res, ox = (sx + shift) % res;
-  const long long row = b * res * res + static_cast<long long>(oy) * res + ox;
-  // region id of the token in the shifted frame (modeling_clap.py:525-550)
-  int region = 0;
-  if (shift > 0) {
-    const int ry = sy < res - ws ? 0 : (sy < res - shift ? 1 : 2);
-    const int rx = sx < res - ws ? 0 : (sx < res - shift ? 1 : 2);
-    region = ry * 3 + rx;
-  }
-  __shared__ int regions[64];
-  float q[CW_HD];
-  if (i < n_tok) {
-    const __half* base = qkv + row * (3LL * C) + head * CW_HD;
-#pragma unroll
-    for (int c = 0; c < CW_HD; c += 2) {
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(base + c));
-      const float2 kk = __half22float2(*reinterpret_cast<const __half2*>(base + C + c));
-      const float2 vv = __half22float2(*reinterpret_cast<const __half2*>(base + 2 * C + c));
-      q[c] = a.x;
-      q[c + 1] = a.y;
-      ks[i][c] = kk.x;
-      ks[i][c + 1] = kk.y;
-      vs[i][c] = vv.x;
-      vs[i][c + 1] = vv.y;
-    }
-    regions[i] = region;
-  }
-  __syncthreads();
-  if (i >= n_tok) return;
-  float p[64];
-  float mx = -INFINITY;
-  const float* bias = rel_bias + (static_cast<long long>(head) * 64 + i) * 64;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    float s = -INFINITY;
-    if (j < n_tok) {
-      float d = 0.f;
-#pragma unroll
-      for (int c = 0; c < CW_HD; ++c) d += q[c] * ks[j][c];
-      s = d * scale + bias[j] + (regions[j] != region ? -100.f : 0.f);
-    }
-    p[j] = s;
-    mx = fmaxf(mx, s);
-  }
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    p[j] = __expf(p[j] - mx);
-    sum += p[j];
-  }
-  const float inv = 1.f / sum;
-  float o[CW_HD];
-#pragma unroll
-  for (int c = 0; c < CW_HD; ++c) o[c] = 0.f;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    const float pj = p[j];  // exp(-inf) = 0 beyond n_tok
-#pragma unroll
-    for (int c = 0; c < CW_HD; ++c) o[c] += pj * vs[j][c];
-  }
-  __half* dst = out + row * C + head * CW_HD;
-#pragma unroll
-  for (int c = 0; c < CW_HD; c += 2) *reinterpret_cast<__half2*>(dst + c) = __floats2half2_rn(o[c] * inv, o[c + 1] * inv);
-}
-
-// ---------------------------------------------------------------- window attention on mma.sync (the one that runs)
 // CTA = 16 warps = 4 window slots x 4 heads: a slot's 4 warps own one (window, group of 4 heads) at a time — the 96 q, 96 k
 // and 96 v columns of those heads for the window's 64 tokens (36 KB of shared memory), each warp one head: S = Q K^T as
 // 4 row strips of 16 x 64 (k = 24 = one m16n8k16 + one m16n8k8 step), softmax on the accumulator registers, O = P V with P
@@ -591,10 +507,6 @@ int clap_build(cc_clap* m, const cc_tensor* w, int nw) {
           for (int i = 0; i < nt; ++i)
             for (int j = 0; j < nt; ++j)
               bias[(static_cast<size_t>(h) * 64 + i) * 64 + j] = table[static_cast<size_t>(rel_index[static_cast<size_t>(i) * nt + j]) * st.heads + h];
-        float* d = nullptr;
-        CC_TRY(A.alloc_t(&d, bias.size()));
-        CC_CUDA(cudaMemcpy(d, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
-        bk.rel_bias = d;
         std::vector<__half> bias16(bias.size());
         for (size_t i = 0; i < bias.size(); ++i) bias16[i] = __float2half(bias[i]);
         __half* d16 = nullptr;
@@ -688,7 +600,6 @@ int cc_clap_forward(cc_clap* m, const void* mel, int mel_dtype, int B, int chann
              T, S * ratio);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   m->launches = 0;
-  static const bool scalar_attn = getenv("CLIPCAP_B200_CLAP_SCALAR_ATTN") != nullptr;  // development A/B switch
   static const cudaError_t smem_attr = cudaFuncSetAttribute(clap_window_attn_mma_kernel,
                                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CW_SMEM));
   CC_CUDA(smem_attr);
@@ -722,11 +633,7 @@ int cc_clap_forward(cc_clap* m, const void* mel, int mel_dtype, int B, int chann
       const int shift = (bi % 2 == 1 && res > c.window) ? c.window / 2 : 0;
       CC_TRY(layernorm_run(m->x, C, bk.ln1_g, bk.ln1_b, m->ln16, C, rows, C, c.eps, s));
       CC_TRY(gemm_run(bk.p_qkv, rows, s));
-      if (scalar_attn) {
-        CC_CUDA(launch_pdl(clap_window_attn_kernel, dim3(windows, st.heads), dim3(64), 0, s,
-                           static_cast<const __half*>(m->qkv16), m->att16, bk.rel_bias, res, ws, shift, C, st.heads,
-                           1.0f / sqrtf(static_cast<float>(CW_HD))));
-      } else {
+      {  // one CTA walks the windows of one group of 4 heads; about one CTA per SM over all groups
         const int groups = st.heads / 4;
         int per = num_sms() / groups;
         per = per < 1 ? 1 : per;

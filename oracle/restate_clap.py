@@ -1,7 +1,7 @@
 """CPU restatement of the CLAP audio tower (BASELINE configs[4]) in plain fp32 torch ops.
 
-TEST INFRASTRUCTURE for a row that is NOT BUILT yet: there is no CUDA path for CLAP in clipcap_b200 — this file only
-fixes what such a path will have to reproduce. PARITY UNPINNED by the reference: its CLAP wrapper does not run as
+TEST INFRASTRUCTURE: the checker of clipcap_b200's CUDA path for CLAP (`csrc/clap.cu`, `tests/test_clap_gpu.py`); nothing
+in the product imports it. PARITY UNPINNED by the reference: its CLAP wrapper does not run as
 committed (`clipcap/encoders/clap.py:136,152` — undefined names) and its arithmetic lives in `laion_clap` (unpinned,
 `requirements-clap.txt:1`, not installed). The stand-in named by SURVEY §8c is
 `transformers.ClapAudioModelWithProjection(ClapAudioConfig(enable_fusion=True))` (5.5.0 installed): HTSAT-tiny, a Swin

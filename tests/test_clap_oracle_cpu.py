@@ -1,4 +1,4 @@
-"""Pins oracle/restate_clap.py (the CLAP audio tower of BASELINE configs[4] — a row with no CUDA path yet) against
+"""Pins oracle/restate_clap.py (the CLAP audio tower of BASELINE configs[4]; its CUDA path is checked against it in tests/test_clap_gpu.py) against
 transformers.ClapAudioModelWithProjection, the stand-in SURVEY §8c names for the un-installed `laion_clap`."""
 import pytest
 import torch

@@ -160,3 +160,18 @@ def test_logit_filters_equal_the_reference_functions():
     assert torch.equal(V.repetition_penalty_apply(x.clone(), t, 1.3), U.repetition_penalty_apply(x.clone(), t, 1.3))
     assert torch.equal(V.sentence_length_penalty_apply(x.clone(), t, 13, 5, 50, 1.0),
                        U.sentence_length_penalty_apply(x.clone(), t, 13, 5, 50, 1.0))
+
+
+def test_clap_surface_has_no_cpu_path():
+    """get_encoder("clap", ...) returns the reference's (CLAPModel, transform) pair; on a CPU device the forward refuses."""
+    from clipcap_b200.encoders import get_encoder
+    from clipcap_b200.encoders.clap import CLAPModel, ClapAudioTower
+    model, transform = get_encoder("clap", "", normalize_embeddings=True, device="cpu")
+    assert isinstance(model, CLAPModel) and model.normalize_embeddings and isinstance(model.model, ClapAudioTower)
+    assert sum(p.numel() for p in model.model.clap.parameters()) > 28e6          # HTSAT-tiny + projection
+    mel = torch.zeros(1, 4, 1001, 64)
+    assert transform(mel) is mel
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(mel)
+    with pytest.raises(NotImplementedError):                                      # long-clip feature fusion is not built
+        model.model.get_audio_embedding_from_mel(mel, is_longer=torch.tensor([[True]]))
