@@ -75,7 +75,7 @@ PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {
     "cc_vit_last_launches": (_i, [_vp]),
     "cc_vit_destroy": (None, [_vp]),
     "cc_clap_create": (_i, [_pp, C.POINTER(cc_clap_cfg), C.POINTER(cc_tensor), _i, _i]),
-    "cc_clap_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "cc_clap_forward": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "cc_clap_last_launches": (_i, [_vp]),
     "cc_clap_destroy": (None, [_vp]),
     "cc_mapper_create": (_i, [_pp, C.POINTER(cc_mapper_cfg), C.POINTER(cc_tensor), _i, _i]),

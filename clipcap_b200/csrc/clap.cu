@@ -48,6 +48,14 @@ struct cc_clap {
          *hid16 = nullptr;
   float *x = nullptr, *merge32 = nullptr, *out32 = nullptr;
   cc::GemmPlan p_embed, p_proj1, p_proj2;
+  // feature fusion of the patch embedding (samples flagged is_longer): 4x12 / (4,12) conv of the three local views and the
+  // AFF block with its BatchNorms folded into the 1x1 convolutions. All fp32.
+  bool has_fusion = false;
+  int aff_hidden = 0, local_w = 0;  // C0 / r; output columns of the local conv per view ((S - 3p) / 3p + 1 = 21)
+  const float *mel_w = nullptr, *mel_b = nullptr;                                          // [C0][p * 3p], [C0]
+  const float *lw1 = nullptr, *lb1 = nullptr, *lw2 = nullptr, *lb2 = nullptr;              // local attention branch
+  const float *gw1 = nullptr, *gb1 = nullptr, *gw2 = nullptr, *gb2 = nullptr;              // global attention branch
+  float *local32 = nullptr, *gvec = nullptr;  // [g0][3 * local_w][C0] of one sample; [C0]
   int launches = 0;
 };
 
@@ -64,47 +72,156 @@ __device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {  // PyTor
   c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
 }
 
-// one thread per (sample, token): 16 patch values. img[y][x] = stretched[t = (y / F) * (S / ratio ...)]: see reshape_mel2img.
+// Value of the folded spectrogram image at (y, x) for one [T][F] mel channel: BatchNorm over the mel bin, bicubic stretch of
+// the time axis to ratio * S frames (align_corners), time chunk y / F laid along frequency (reshape_mel2img).
+template <typename SRC>
+__device__ __forceinline__ float mel_image_value(const SRC* __restrict__ src, int T, int F, int S, int y, int x,
+                                                 const float* __restrict__ bn_scale, const float* __restrict__ bn_shift) {
+  const int Tw = S * (S / F);
+  const int f = y % F, t = (y / F) * S + x;
+  float v;
+  if (T == Tw) {
+    v = static_cast<float>(src[static_cast<long long>(t) * F + f]);
+  } else {
+    const float scale = Tw > 1 ? static_cast<float>(T - 1) / static_cast<float>(Tw - 1) : 0.f;
+    const float real = scale * static_cast<float>(t);
+    const int i0 = static_cast<int>(floorf(real));
+    float c[4];
+    cubic_coeffs(real - static_cast<float>(i0), c);
+    v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int idx = i0 - 1 + k;
+      idx = idx < 0 ? 0 : (idx > T - 1 ? T - 1 : idx);
+      v += c[k] * static_cast<float>(src[static_cast<long long>(idx) * F + f]);
+    }
+  }
+  return v * bn_scale[f] + bn_shift[f];
+}
+
+// one thread per (sample, token): the patch x patch values of the global view (channel 0) as one row of the GEMM operand
 template <typename SRC>
 __global__ void clap_patches_kernel(const SRC* __restrict__ mel, long long sample_stride, int T, int F, int S, int patch,
                                     const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
                                     __half* __restrict__ cols, int B) {
-  const int g = S / patch;                       // tokens per side
+  const int g = S / patch;  // tokens per side
   const long long n = static_cast<long long>(B) * g * g;
-  const int ratio = S / F;                       // time chunks stacked along frequency
-  const int Tw = S * ratio;                      // stretched time length (1024)
-  const int chunk = Tw / ratio;                  // = S
-  const float scale = Tw > 1 ? static_cast<float>(T - 1) / static_cast<float>(Tw - 1) : 0.f;  // align_corners = True
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int px = static_cast<int>(i % g), py = static_cast<int>((i / g) % g);
-    const long long b = i / (static_cast<long long>(g) * g);
-    const SRC* src = mel + b * sample_stride;  // channel 0: [T][F]
+    const SRC* src = mel + (i / (static_cast<long long>(g) * g)) * sample_stride;  // channel 0: [T][F]
     __half* dst = cols + i * (patch * patch);
-    for (int ky = 0; ky < patch; ++ky) {
-      const int y = py * patch + ky;
-      const int f = y % F, r = y / F;
-      for (int kx = 0; kx < patch; ++kx) {
-        const int t = r * chunk + px * patch + kx;
-        float v;
-        if (T == Tw) {
-          v = static_cast<float>(src[static_cast<long long>(t) * F + f]);
-        } else {
-          const float real = scale * static_cast<float>(t);
-          const int i0 = static_cast<int>(floorf(real));
-          float c[4];
-          cubic_coeffs(real - static_cast<float>(i0), c);
-          v = 0.f;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            int idx = i0 - 1 + k;
-            idx = idx < 0 ? 0 : (idx > T - 1 ? T - 1 : idx);
-            v += c[k] * static_cast<float>(src[static_cast<long long>(idx) * F + f]);
-          }
-        }
-        dst[ky * patch + kx] = __float2half_rn(v * bn_scale[f] + bn_shift[f]);
-      }
+    for (int ky = 0; ky < patch; ++ky)
+      for (int kx = 0; kx < patch; ++kx)
+        dst[ky * patch + kx] =
+            __float2half_rn(mel_image_value(src, T, F, S, py * patch + ky, px * patch + kx, bn_scale, bn_shift));
+  }
+}
+
+// ---------------------------------------------------------------- feature fusion of one long clip (ClapAudioPatchEmbed + AFF)
+// local[y][view * LW + xw][co] = bias[co] + sum_{ky,kx} w[co][ky][kx] * image_{view+1}[p y + ky][3p xw + kx]: the three local
+// views through the p x 3p / (p, 3p) convolution, laid side by side along time. One CTA per output position, thread = co.
+template <typename SRC>
+__global__ void clap_fusion_local_kernel(const SRC* __restrict__ mel_sample, int T, int F, int S, int patch, int LW, int C0,
+                                         const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                                         const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ local) {
+  extern __shared__ float patch_s[];  // [patch][3 patch]
+  const int kw = 3 * patch, kn = patch * kw;
+  const int xw = blockIdx.x % LW, y = blockIdx.x / LW, view = blockIdx.y;
+  const SRC* src = mel_sample + static_cast<long long>(view + 1) * T * F;
+  for (int k = threadIdx.x; k < kn; k += blockDim.x)
+    patch_s[k] = mel_image_value(src, T, F, S, y * patch + k / kw, xw * kw + k % kw, bn_scale, bn_shift);
+  __syncthreads();
+  for (int co = threadIdx.x; co < C0; co += blockDim.x) {
+    float acc = bias[co];
+    for (int k = 0; k < kn; ++k) acc += w[co * kn + k] * patch_s[k];
+    local[(static_cast<long long>(y) * (3 * LW) + view * LW + xw) * C0 + co] = acc;
+  }
+}
+
+// gvec[c] = global-attention branch of the AFF block on mean over all positions of (global + local): one CTA.
+__global__ void __launch_bounds__(1024)
+clap_fusion_global_kernel(const float* __restrict__ glob, const float* __restrict__ local, int g0, int LW3, int C0, int hid,
+                          const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                          const float* __restrict__ b2, float* __restrict__ gvec) {
+  extern __shared__ float fs[];  // [groups][C0] partial sums, then mean[C0], hidden[hid]
+  const int groups = blockDim.x / C0;
+  const int c = threadIdx.x % C0, grp = threadIdx.x / C0;
+  pdl_launch_dependents();
+  pdl_wait();
+  float acc = 0.f;
+  if (grp < groups)
+    for (int p = grp; p < g0 * g0; p += groups) {
+      const int y = p / g0, x = p - y * g0;
+      acc += glob[static_cast<long long>(p) * C0 + c] + (x < LW3 ? local[(static_cast<long long>(y) * LW3 + x) * C0 + c] : 0.f);
     }
+  if (grp < groups) fs[grp * C0 + c] = acc;
+  __syncthreads();
+  float* mean = fs + groups * C0;
+  float* hidden = mean + C0;
+  if (threadIdx.x < C0) {
+    float t = 0.f;
+    for (int k = 0; k < groups; ++k) t += fs[k * C0 + threadIdx.x];
+    mean[threadIdx.x] = t / static_cast<float>(g0 * g0);
+  }
+  __syncthreads();
+  if (threadIdx.x < hid) {
+    float t = b1[threadIdx.x];
+    for (int k = 0; k < C0; ++k) t += w1[threadIdx.x * C0 + k] * mean[k];
+    hidden[threadIdx.x] = fmaxf(t, 0.f);
+  }
+  __syncthreads();
+  if (threadIdx.x < C0) {
+    float t = b2[threadIdx.x];
+    for (int k = 0; k < hid; ++k) t += w2[threadIdx.x * hid + k] * hidden[k];
+    gvec[threadIdx.x] = t;
+  }
+}
+
+// glob[p][c] <- 2 glob gate + 2 local (1 - gate), gate = sigmoid(local_att(glob + local)[c] + gvec[c]); thread = position.
+constexpr int CF_MAXHID = 48;
+__global__ void __launch_bounds__(128)
+clap_fusion_apply_kernel(float* __restrict__ glob, const float* __restrict__ local, int g0, int LW3, int C0, int hid,
+                         const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                         const float* __restrict__ b2, const float* __restrict__ gvec) {
+  extern __shared__ float ws_[];  // w1 [hid][C0], w2 [C0][hid], b1 [hid], b2 + gvec [C0]
+  float* w1s = ws_;
+  float* w2s = w1s + hid * C0;
+  float* b1s = w2s + C0 * hid;
+  float* b2s = b1s + hid;
+  for (int i = threadIdx.x; i < hid * C0; i += blockDim.x) {
+    w1s[i] = w1[i];
+    w2s[i] = w2[i];
+  }
+  for (int i = threadIdx.x; i < hid; i += blockDim.x) b1s[i] = b1[i];
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int i = threadIdx.x; i < C0; i += blockDim.x) b2s[i] = b2[i] + gvec[i];
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= g0 * g0) return;
+  const int y = p / g0, x = p - y * g0;
+  float* gp = glob + static_cast<long long>(p) * C0;
+  const float* lp = x < LW3 ? local + (static_cast<long long>(y) * LW3 + x) * C0 : nullptr;
+  float hidden[CF_MAXHID];
+#pragma unroll
+  for (int j = 0; j < CF_MAXHID; ++j) hidden[j] = j < hid ? b1s[j] : 0.f;
+  for (int c = 0; c < C0; ++c) {
+    const float xa = gp[c] + (lp ? lp[c] : 0.f);
+#pragma unroll
+    for (int j = 0; j < CF_MAXHID; ++j)
+      if (j < hid) hidden[j] += w1s[j * C0 + c] * xa;
+  }
+#pragma unroll
+  for (int j = 0; j < CF_MAXHID; ++j) hidden[j] = fmaxf(hidden[j], 0.f);
+  for (int c = 0; c < C0; ++c) {
+    float l = b2s[c];
+#pragma unroll
+    for (int j = 0; j < CF_MAXHID; ++j)
+      if (j < hid) l += w2s[c * hid + j] * hidden[j];
+    const float gate = 1.f / (1.f + __expf(-l));
+    const float xg = gp[c], xl = lp ? lp[c] : 0.f;
+    gp[c] = 2.f * xg * gate + 2.f * xl * (1.f - gate);
   }
 }
 
@@ -432,6 +549,75 @@ int clap_build(cc_clap* m, const cc_tensor* w, int nw) {
     // conv output goes to merge32 (scratch), its LayerNorm into the residual stream x
     CC_TRY(gemm_plan(&m->p_embed, m->cols16, pp, static_cast<int>(rows0), m->pe_w, C0, pp, EPI_F32, m->pe_b, m->merge32, C0));
   }
+  // feature fusion (present when the checkpoint was built with enable_fusion): fold every eval-mode BatchNorm into the
+  // 1x1 convolution in front of it, on the host (a few thousand values)
+  {
+    const std::string pe = enc + "patch_embed.";
+    bool present = false;
+    int64_t hid_numel = 0;
+    for (int i = 0; i < nw; ++i)
+      if (w[i].name != nullptr && pe + "fusion_model.local_att.0.weight" == w[i].name) {
+        present = true;
+        hid_numel = 1;
+        for (int k = 0; k < w[i].ndim; ++k) hid_numel *= w[i].shape[k];
+      }
+    if (present) {
+      const int hid = static_cast<int>(hid_numel / C0);
+      CC_REQUIRE(hid >= 1 && hid <= CF_MAXHID && static_cast<int64_t>(hid) * C0 == hid_numel, CC_ESHAPE,
+                 "clap: AFF hidden width %d (max %d)", hid, CF_MAXHID);
+      CC_REQUIRE(S >= 3 * c.patch, CC_ESHAPE, "clap: spec_size %d too small for the fusion convolution", S);
+      m->aff_hidden = hid;
+      m->local_w = (S - 3 * c.patch) / (3 * c.patch) + 1;
+      auto fetch = [&](const std::string& name, int64_t numel, std::vector<float>& out) -> int {
+        const float* d = nullptr;
+        CC_TRY(get(w, nw, name, numel, stage, &d));
+        out.resize(static_cast<size_t>(numel));
+        CC_CUDA(cudaMemcpy(out.data(), d, out.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        return CC_OK;
+      };
+      auto upload = [&](const std::vector<float>& v, const float** out) -> int {
+        float* d = nullptr;
+        CC_TRY(A.alloc_t(&d, v.size()));
+        CC_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+        *out = d;
+        return CC_OK;
+      };
+      // conv [out, in, 1, 1] + BatchNorm(out)  ->  W' = s W, b' = s (b - mean) + beta, s = gamma / sqrt(var + 1e-5)
+      auto folded = [&](const std::string& conv, const std::string& bn, int out_ch, int in_ch, const float** wd,
+                        const float** bd) -> int {
+        std::vector<float> cw, cb, g, b, rm, rv;
+        CC_TRY(fetch(conv + "weight", static_cast<int64_t>(out_ch) * in_ch, cw));
+        CC_TRY(fetch(conv + "bias", out_ch, cb));
+        CC_TRY(fetch(bn + "weight", out_ch, g));
+        CC_TRY(fetch(bn + "bias", out_ch, b));
+        CC_TRY(fetch(bn + "running_mean", out_ch, rm));
+        CC_TRY(fetch(bn + "running_var", out_ch, rv));
+        for (int o = 0; o < out_ch; ++o) {
+          const float sc = g[o] / sqrtf(rv[o] + 1e-5f);
+          for (int i = 0; i < in_ch; ++i) cw[static_cast<size_t>(o) * in_ch + i] *= sc;
+          cb[o] = sc * (cb[o] - rm[o]) + b[o];
+        }
+        CC_TRY(upload(cw, wd));
+        CC_TRY(upload(cb, bd));
+        return CC_OK;
+      };
+      const std::string fm = pe + "fusion_model.";
+      CC_TRY(folded(fm + "local_att.0.", fm + "local_att.1.", hid, C0, &m->lw1, &m->lb1));
+      CC_TRY(folded(fm + "local_att.3.", fm + "local_att.4.", C0, hid, &m->lw2, &m->lb2));
+      CC_TRY(folded(fm + "global_att.1.", fm + "global_att.2.", hid, C0, &m->gw1, &m->gb1));
+      CC_TRY(folded(fm + "global_att.4.", fm + "global_att.5.", C0, hid, &m->gw2, &m->gb2));
+      const float *mw, *mb;
+      CC_TRY(get(w, nw, pe + "mel_conv2d.weight", static_cast<int64_t>(C0) * pp * 3, stage, &mw));
+      CC_TRY(get(w, nw, pe + "mel_conv2d.bias", C0, stage, &mb));
+      CC_TRY(keep_f32(A, mw, static_cast<size_t>(C0) * pp * 3, &m->mel_w));
+      CC_TRY(keep_f32(A, mb, C0, &m->mel_b));
+      CC_TRY(A.alloc_t(&m->local32, static_cast<size_t>(m->grid0) * 3 * m->local_w * C0));
+      CC_TRY(A.alloc_t(&m->gvec, static_cast<size_t>(C0)));
+      CC_REQUIRE(3 * m->local_w <= m->grid0, CC_ESHAPE, "clap: %d local columns exceed the %d global ones", 3 * m->local_w, m->grid0);
+      m->has_fusion = true;
+      stage.release();
+    }
+  }
   // relative position index of an 8x8 window (modeling_clap.py:427-438)
   const int ws = c.window, nt = ws * ws;
   std::vector<int> rel_index(static_cast<size_t>(nt) * nt);
@@ -589,8 +775,8 @@ int cc_clap_create(cc_clap** h, const cc_clap_cfg* cfg, const cc_tensor* weights
   return CC_OK;
 }
 
-int cc_clap_forward(cc_clap* m, const void* mel, int mel_dtype, int B, int channels, int T, int normalize, void* out,
-                    int out_dtype, int stop_after_stage, float* dump, void* stream) {
+int cc_clap_forward(cc_clap* m, const void* mel, int mel_dtype, const unsigned char* is_longer, int B, int channels, int T,
+                    int normalize, void* out, int out_dtype, int stop_after_stage, float* dump, void* stream) {
   using namespace cc;
   CC_REQUIRE(m != nullptr && mel != nullptr && out != nullptr, CC_EINVAL, "cc_clap_forward: null argument");
   CC_REQUIRE(B > 0 && B <= m->max_batch, CC_ESHAPE, "cc_clap_forward: batch %d outside 1..%d", B, m->max_batch);
@@ -618,6 +804,32 @@ int cc_clap_forward(cc_clap* m, const void* mel, int mel_dtype, int B, int chann
   }
   CC_CUDA(cudaGetLastError());
   CC_TRY(gemm_run(m->p_embed, static_cast<int>(tokens0), s));  // conv as GEMM -> merge32 (scratch)
+  if (is_longer != nullptr) {  // modeling_clap.py:310-338: the flagged samples' global map is fused with their local views
+    const int C0 = c.embed, LW = m->local_w, hid = m->aff_hidden;
+    for (int b = 0; b < B; ++b) {
+      if (!is_longer[b]) continue;
+      CC_REQUIRE(m->has_fusion, CC_EINVAL, "cc_clap_forward: sample %d is flagged is_longer but the handle has no fusion weights", b);
+      CC_REQUIRE(channels == 4, CC_ESHAPE, "cc_clap_forward: feature fusion needs 4 mel views per sample, got %d", channels);
+      float* glob = m->merge32 + static_cast<size_t>(b) * g0 * g0 * C0;
+      const size_t psm = static_cast<size_t>(c.patch) * 3 * c.patch * sizeof(float);
+      if (mel_dtype == CC_F32)
+        clap_fusion_local_kernel<float><<<dim3(LW * g0, 3), 96, psm, s>>>(static_cast<const float*>(mel) + b * sample_stride, T, F, S, c.patch,
+                                                                          LW, C0, m->bn_scale, m->bn_shift, m->mel_w, m->mel_b, m->local32);
+      else
+        clap_fusion_local_kernel<__half><<<dim3(LW * g0, 3), 96, psm, s>>>(static_cast<const __half*>(mel) + b * sample_stride, T, F, S,
+                                                                           c.patch, LW, C0, m->bn_scale, m->bn_shift, m->mel_w, m->mel_b,
+                                                                           m->local32);
+      CC_CUDA(cudaGetLastError());
+      const int gthreads = (1024 / C0) * C0 > 0 ? (1024 / C0) * C0 : C0;
+      CC_CUDA(launch_pdl(clap_fusion_global_kernel, dim3(1), dim3(gthreads), static_cast<size_t>(gthreads + C0 + hid) * sizeof(float),
+                         s, static_cast<const float*>(glob), static_cast<const float*>(m->local32), g0, 3 * LW, C0, hid, m->gw1,
+                         m->gb1, m->gw2, m->gb2, m->gvec));
+      CC_CUDA(launch_pdl(clap_fusion_apply_kernel, dim3((g0 * g0 + 127) / 128), dim3(128),
+                         static_cast<size_t>(2 * hid * C0 + hid + C0) * sizeof(float), s, glob, static_cast<const float*>(m->local32),
+                         g0, 3 * LW, C0, hid, m->lw1, m->lb1, m->lw2, m->lb2, static_cast<const float*>(m->gvec)));
+      m->launches += 3;
+    }
+  }
   // patch LayerNorm, fp32 -> the fp32 residual stream
   CC_CUDA(launch_pdl(clap_ln_f32_kernel, dim3(grid_for(tokens0 * 32, 256)), dim3(256), 0, s,
                      static_cast<const float*>(m->merge32), m->pe_g, m->pe_beta, m->x, tokens0, c.embed, c.eps));

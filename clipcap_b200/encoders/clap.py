@@ -5,8 +5,8 @@ installed here and whose wrapper does not run as committed (clap.py:136 reads `m
 unknown keyword). What is built here is the tower that call ends in: HTSAT-tiny + the audio projection, with the arithmetic
 and parameter names of transformers' `ClapAudioModelWithProjection` (the stand-in SURVEY §8c names), running in
 libclipcap_b200's cc_clap_forward. Its input is the log-mel feature tensor `[B, channels, T <= 1024, 64]` (what
-`ClapFeatureExtractor` / laion_clap's `get_mel` produce); the waveform -> mel front end is host-side feature extraction
-and stays with the caller. Clips longer than the 10 s window (`is_longer`, the feature-fusion branch) are rejected.
+`ClapFeatureExtractor` / laion_clap's `get_mel` produce) plus the per-sample `is_longer` flags that select the
+feature-fusion patch embedding; the waveform -> mel front end is host-side feature extraction and stays with the caller.
 """
 from __future__ import annotations
 
@@ -50,9 +50,7 @@ class ClapAudioTower(EngineModule):
     @torch.no_grad()
     def get_audio_embedding_from_mel(self, mel: torch.Tensor, is_longer: Optional[torch.Tensor] = None,
                                      normalize: bool = False) -> torch.Tensor:
-        if is_longer is not None and bool(torch.as_tensor(is_longer).any()):
-            raise NotImplementedError("clipcap_b200: CLAP feature fusion of clips longer than the 10 s window is not built")
-        return self._get_engine((max(8, mel.shape[0]),)).forward(mel, normalize=normalize)
+        return self._get_engine((max(8, mel.shape[0]),)).forward(mel, normalize=normalize, is_longer=is_longer)
 
     forward = get_audio_embedding_from_mel
 
@@ -66,8 +64,9 @@ class CLAPModel(nn.Module):
         self.normalize_embeddings = normalize_embeddings
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.model.get_audio_embedding_from_mel(x, normalize=self.normalize_embeddings)  # fused L2 normalisation
+    def forward(self, x: torch.Tensor, is_longer: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.model.get_audio_embedding_from_mel(x, is_longer=is_longer,
+                                                       normalize=self.normalize_embeddings)  # fused L2 normalisation
 
 
 def get_clap_encoder(normalize_embeddings: bool = False, device: str = "cuda",

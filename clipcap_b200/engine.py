@@ -87,7 +87,7 @@ class ClapEngine(_Handle):
         self.max_batch = max_batch
         self.stage_shapes = [((spec_size // patch >> i) ** 2, embed << i) for i in range(4)]  # (tokens, channels)
         wanted = ("audio_model.audio_encoder.", "audio_projection.")
-        skip = ("fusion_model", "mel_conv2d", "relative_position_index", "num_batches_tracked")
+        skip = ("relative_position_index", "num_batches_tracked")
         weights = {k: v for k, v in weights.items() if k.startswith(wanted) and not any(x in k for x in skip)}
         with torch.cuda.device(self.device):
             arr, keep = _ffi.make_tensor_table(_named(weights, self.device))
@@ -95,9 +95,11 @@ class ClapEngine(_Handle):
             torch.cuda.synchronize()
 
     def forward(self, mel: torch.Tensor, normalize: bool = False, out_dtype: Optional[torch.dtype] = None,
-                stop_after_stage: int = -1):
-        """mel: [B, channels, T, num_mel_bins] fp32 / fp16 (channel 0 = the global view). Returns [B, projection_dim]; with
-        `stop_after_stage` = s >= 0, the fp32 token stream [B, tokens_s, channels_s] after stage s instead."""
+                stop_after_stage: int = -1, is_longer=None):
+        """mel: [B, channels, T, num_mel_bins] fp32 / fp16 (channel 0 = the global view, 1..3 = local views of clips longer
+        than the window). `is_longer`: per-sample flags (tensor / sequence, any shape with B elements) selecting the
+        feature-fusion patch embedding. Returns [B, projection_dim]; with `stop_after_stage` = s >= 0, the fp32 token stream
+        [B, tokens_s, channels_s] after stage s instead."""
         _require_cuda(mel, "mel")
         if mel.dim() != 4 or mel.shape[3] != self.cfg.num_mel_bins:
             raise ValueError(f"mel must be [B, channels, T, {self.cfg.num_mel_bins}], got {tuple(mel.shape)}")
@@ -105,13 +107,21 @@ class ClapEngine(_Handle):
             mel = mel.float()
         mel = mel.contiguous()
         B = mel.shape[0]
+        flags = None
+        if is_longer is not None:
+            host = torch.as_tensor(is_longer).reshape(-1).to("cpu")
+            if host.numel() != B:
+                raise ValueError(f"is_longer must hold one flag per sample ({B}), got {host.numel()}")
+            if bool(host.any()):
+                flags = (C.c_ubyte * B)(*[1 if v else 0 for v in host.tolist()])
         out = torch.empty(B, self.cfg.projection_dim, device=mel.device, dtype=out_dtype or mel.dtype)
         dump = None
         if stop_after_stage >= 0:
             tokens, ch = self.stage_shapes[stop_after_stage]
             dump = torch.empty(B, tokens, ch, device=mel.device, dtype=torch.float32)
         with torch.cuda.device(mel.device):
-            _ffi.check(_ffi.lib().cc_clap_forward(self._h, mel.data_ptr(), _ffi.torch_dtype_code(mel), B, mel.shape[1],
+            _ffi.check(_ffi.lib().cc_clap_forward(self._h, mel.data_ptr(), _ffi.torch_dtype_code(mel),
+                                                  C.cast(flags, C.c_void_p) if flags is not None else None, B, mel.shape[1],
                                                   mel.shape[2], int(bool(normalize)), out.data_ptr(),
                                                   _ffi.torch_dtype_code(out), stop_after_stage,
                                                   dump.data_ptr() if dump is not None else None,

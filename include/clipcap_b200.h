@@ -185,8 +185,9 @@ void cc_gpt2_destroy(cc_gpt2* h);
  * Replaces: CLAPModel.forward -> clap_model.get_audio_embedding_from_data (clipcap/encoders/clap.py:105-131; laion_clap
  * is not installed, the arithmetic is transformers' ClapAudioModelWithProjection, modeling_clap.py:1725-1775 with
  * ClapAudioEncoder.forward :814-918). Weight names are that module's state_dict keys (audio_model.audio_encoder.*,
- * audio_projection.linear{1,2}.*). Only the `is_longer == False` path (clips no longer than the 10 s window: the global
- * mel channel alone feeds the patch embedding) is implemented; fused long-clip inputs are rejected by the Python wrapper.
+ * audio_projection.linear{1,2}.*). Samples flagged `is_longer` (clips longer than the 10 s window; 4 mel views: the
+ * global one and three local crops) go through the feature-fusion patch embedding (mel_conv2d + AFF block,
+ * modeling_clap.py:296-344, :238-245); it needs the `patch_embed.mel_conv2d.*` / `patch_embed.fusion_model.*` tensors.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct cc_clap_cfg {
   int32_t num_mel_bins;   /* 64 */
@@ -202,11 +203,12 @@ typedef struct cc_clap_cfg {
 typedef struct cc_clap cc_clap;
 
 int cc_clap_create(cc_clap** h, const cc_clap_cfg* cfg, const cc_tensor* weights, int n_weights, int max_batch);
-/* mel: [B, channels, T <= spec_size * spec_size / num_mel_bins, num_mel_bins] log-mel features (channel 0 is used), dtype
- * mel_dtype; out: [B, projection_dim]. stop_after_stage >= 0 with dump != NULL copies the fp32 token stream after that
+/* mel: [B, channels, T <= spec_size * spec_size / num_mel_bins, num_mel_bins] log-mel features, dtype mel_dtype (channel 0 =
+ * global view; channels 1..3 = local views, read for flagged samples only); is_longer: HOST array of B bytes (non-zero =
+ * fuse the local views of that sample) or NULL for none; out: [B, projection_dim]. stop_after_stage >= 0 with dump != NULL copies the fp32 token stream after that
  * stage's blocks ([B * tokens, channels] of the stage) into `dump` and returns without producing `out` (debug / tests). */
-int cc_clap_forward(cc_clap* h, const void* mel, int mel_dtype, int B, int channels, int T, int normalize, void* out,
-                    int out_dtype, int stop_after_stage, float* dump, void* stream);
+int cc_clap_forward(cc_clap* h, const void* mel, int mel_dtype, const unsigned char* is_longer, int B, int channels, int T,
+                    int normalize, void* out, int out_dtype, int stop_after_stage, float* dump, void* stream);
 int cc_clap_last_launches(cc_clap* h);
 void cc_clap_destroy(cc_clap* h);
 

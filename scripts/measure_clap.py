@@ -77,6 +77,14 @@ def main():
                   "p50_ms": p50, "launches": eng.last_launches, "rel_err_vs_host_module": rel,
                   "tflops": 11.8e9 * B / (ms * 1e-3) / 1e12})
 
+    one = torch.zeros(B, dtype=torch.bool)
+    one[B // 2] = True   # ClapFeatureExtractor flags one random sample when no clip of the batch is longer than the window
+    ms1, _ = timed(lambda: eng.forward(mel, is_longer=one), a.iters)
+    every = torch.ones(B, dtype=torch.bool)
+    msa, _ = timed(lambda: eng.forward(mel, is_longer=every), a.iters)
+    lines.append({"config": f"CLAP audio tower, {B} clips, feature fusion on 1 / on all {B} samples", "ms_one": ms1, "ms_all": msa,
+                  "clips_per_s_one": B / (ms1 * 1e-3), "clips_per_s_all": B / (msa * 1e-3)})
+
     mapper = MapperEngine(mapper_w, E=512, d=1024, P=10, K=40, H=8, L=8, max_batch=B, device=dev)
     lm = Gpt2Engine(lm_w, 1024, 24, 16, 50257, 1024, max_seqs=B, max_len=40 + 20, device=dev)
 

@@ -19,11 +19,13 @@ def _weights(cfg, seed):
     return {k: v.detach() for k, v in m.state_dict().items()}
 
 
-def _oracle_stages(w, mel, cfg):
+def _oracle_stages(w, mel, cfg, is_longer=None):
     """clap_audio_embed unrolled so the token stream after every stage's blocks is returned too."""
     x = RC._bn_eval(mel.float().transpose(1, 3), w, RC.ENC + "batch_norm.").transpose(1, 3)
     img = RC.reshape_mel2img(x, cfg)
-    x = RC.patch_embed(w, img, torch.zeros(mel.shape[0], 1, dtype=torch.bool), cfg)
+    if is_longer is None:
+        is_longer = torch.zeros(mel.shape[0], 1, dtype=torch.bool)
+    x = RC.patch_embed(w, img, is_longer, cfg)
     grid = cfg.spec_size // cfg.patch
     streams = []
     for i, (depth, heads) in enumerate(zip(cfg.depths, cfg.heads)):
@@ -63,6 +65,31 @@ def test_clap_embedding_matches_oracle(cuda_device, frames):
     assert rel_err(got16, ref) < REL
 
 
+@pytest.mark.parametrize("longer,frames,dtype", [([1, 0, 1], 1001, torch.float32), ([1, 1, 1, 1], 1024, torch.float32),
+                                                 ([0, 1], 1001, torch.float16)])
+def test_clap_feature_fusion_matches_oracle(cuda_device, longer, frames, dtype):
+    """Samples flagged is_longer: the three local mel views go through the 4x12 convolution and the AFF block
+    (modeling_clap.py:296-344) before the Swin stages; unflagged samples of the same batch are untouched."""
+    cfg = RC.ClapCfg()
+    w = _weights(cfg, seed=4)
+    B = len(longer)
+    mel = torch.randn(B, 4, frames, 64, generator=torch.Generator().manual_seed(17)).to(dtype)
+    flags = torch.tensor(longer, dtype=torch.bool).view(B, 1)
+    with torch.no_grad():
+        want = RC.clap_audio_embed(w, mel.float(), flags, cfg)
+        plain = RC.clap_audio_embed(w, mel.float(), torch.zeros(B, 1, dtype=torch.bool), cfg)
+        stage0 = _oracle_stages(w, mel.float(), cfg, flags)[0]
+    assert rel_err(want, plain) > 5e-2                       # the fusion branch matters on these inputs
+    eng = _engine(w, cfg, 4, cuda_device)
+    got0 = eng.forward(mel.to(cuda_device), stop_after_stage=0, is_longer=flags).cpu()
+    assert rel_err(got0, stage0) < REL
+    got = eng.forward(mel.to(cuda_device), is_longer=flags).float().cpu()
+    assert rel_err(got, want) < REL
+    assert torch.nn.functional.cosine_similarity(got, want, dim=-1).min() > COS
+    none = eng.forward(mel.to(cuda_device), is_longer=torch.zeros(B, dtype=torch.bool)).float().cpu()
+    assert rel_err(none, plain) < REL
+
+
 def test_clap_stage_streams_match_oracle(cuda_device):
     """Token stream after each Swin stage (shifted windows, region masks and patch merging are all index arithmetic in the
     CUDA path): every stage must agree with the roll / partition / reverse formulation of the oracle."""
@@ -94,8 +121,19 @@ def test_clap_wrapper_and_errors(cuda_device):
         want = RC.clap_audio_embed(sd, mel, torch.zeros(2, 1, dtype=torch.bool), RC.ClapCfg())
     want = want / want.norm(dim=-1, keepdim=True)
     assert rel_err(out.float().cpu(), want) < REL
-    with pytest.raises(NotImplementedError):                  # long-clip feature fusion is not built
-        model.model.get_audio_embedding_from_mel(mel.to(cuda_device), is_longer=torch.tensor([[True], [False]]))
+    fused = model(mel.to(cuda_device), is_longer=torch.tensor([[True], [False]]))   # HF convention: [B, 1] flags
+    with torch.no_grad():
+        want_f = RC.clap_audio_embed(sd, mel, torch.tensor([[True], [False]]), RC.ClapCfg())
+    assert rel_err(fused.float().cpu(), want_f / want_f.norm(dim=-1, keepdim=True)) < REL
+    with pytest.raises(CCError, match="CC_ESHAPE"):           # flagged sample without its three local views
+        model.model._get_engine((2,)).forward(mel[:, :1].contiguous().to(cuda_device), is_longer=[True, False])
+    with pytest.raises(ValueError):                           # one flag per sample
+        model.model._get_engine((2,)).forward(mel.to(cuda_device), is_longer=[True])
+    plain_cfg = RC.ClapCfg(enable_fusion=False)
+    plain = _engine(_weights(plain_cfg, 1), plain_cfg, 2, cuda_device)              # checkpoint without fusion weights
+    assert tuple(plain.forward(mel[:, :1].contiguous().to(cuda_device)).shape) == (2, 512)
+    with pytest.raises(CCError, match="CC_EINVAL"):
+        plain.forward(mel.to(cuda_device), is_longer=[True, False])
     with pytest.raises(RuntimeError, match="no CPU path"):
         model.model._get_engine((2,)).forward(mel)
     with pytest.raises(CCError, match="CC_ESHAPE"):           # more frames than the folded image holds

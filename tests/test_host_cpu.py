@@ -173,5 +173,3 @@ def test_clap_surface_has_no_cpu_path():
     assert transform(mel) is mel
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model(mel)
-    with pytest.raises(NotImplementedError):                                      # long-clip feature fusion is not built
-        model.model.get_audio_embedding_from_mel(mel, is_longer=torch.tensor([[True]]))
