@@ -55,7 +55,8 @@ struct cc_clap {
   const float *mel_w = nullptr, *mel_b = nullptr;                                          // [C0][p * 3p], [C0]
   const float *lw1 = nullptr, *lb1 = nullptr, *lw2 = nullptr, *lb2 = nullptr;              // local attention branch
   const float *gw1 = nullptr, *gb1 = nullptr, *gw2 = nullptr, *gb2 = nullptr;              // global attention branch
-  float *local32 = nullptr, *gvec = nullptr;  // [g0][3 * local_w][C0] of one sample; [C0]
+  float *local32 = nullptr, *gvec = nullptr;  // per fused sample (slot): [g0][3 * local_w][C0]; [C0]
+  int* slots = nullptr;                       // [max_batch]: slot of a flagged sample, -1 otherwise (uploaded per call)
   int launches = 0;
 };
 
@@ -118,17 +119,22 @@ __global__ void clap_patches_kernel(const SRC* __restrict__ mel, long long sampl
   }
 }
 
-// ---------------------------------------------------------------- feature fusion of one long clip (ClapAudioPatchEmbed + AFF)
+// ---------------------------------------------------------------- feature fusion of the long clips (ClapAudioPatchEmbed + AFF)
+// Every kernel runs over all samples of the batch; CTAs of samples without a slot (not flagged is_longer) leave at once.
 // local[y][view * LW + xw][co] = bias[co] + sum_{ky,kx} w[co][ky][kx] * image_{view+1}[p y + ky][3p xw + kx]: the three local
 // views through the p x 3p / (p, 3p) convolution, laid side by side along time. One CTA per output position, thread = co.
 template <typename SRC>
-__global__ void clap_fusion_local_kernel(const SRC* __restrict__ mel_sample, int T, int F, int S, int patch, int LW, int C0,
-                                         const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
-                                         const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ local) {
+__global__ void clap_fusion_local_kernel(const SRC* __restrict__ mel, long long sample_stride, const int* __restrict__ slots,
+                                         int T, int F, int S, int patch, int LW, int C0, const float* __restrict__ bn_scale,
+                                         const float* __restrict__ bn_shift, const float* __restrict__ w,
+                                         const float* __restrict__ bias, float* __restrict__ local_all) {
   extern __shared__ float patch_s[];  // [patch][3 patch]
+  const int slot = slots[blockIdx.z];
+  if (slot < 0) return;
   const int kw = 3 * patch, kn = patch * kw;
   const int xw = blockIdx.x % LW, y = blockIdx.x / LW, view = blockIdx.y;
-  const SRC* src = mel_sample + static_cast<long long>(view + 1) * T * F;
+  const SRC* src = mel + blockIdx.z * sample_stride + static_cast<long long>(view + 1) * T * F;
+  float* local = local_all + static_cast<long long>(slot) * (S / patch) * (3 * LW) * C0;
   for (int k = threadIdx.x; k < kn; k += blockDim.x)
     patch_s[k] = mel_image_value(src, T, F, S, y * patch + k / kw, xw * kw + k % kw, bn_scale, bn_shift);
   __syncthreads();
@@ -141,14 +147,20 @@ __global__ void clap_fusion_local_kernel(const SRC* __restrict__ mel_sample, int
 
 // gvec[c] = global-attention branch of the AFF block on mean over all positions of (global + local): one CTA.
 __global__ void __launch_bounds__(1024)
-clap_fusion_global_kernel(const float* __restrict__ glob, const float* __restrict__ local, int g0, int LW3, int C0, int hid,
-                          const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                          const float* __restrict__ b2, float* __restrict__ gvec) {
+clap_fusion_global_kernel(const float* __restrict__ glob_all, const float* __restrict__ local_all,
+                          const int* __restrict__ slots, int g0, int LW3, int C0, int hid, const float* __restrict__ w1,
+                          const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                          float* __restrict__ gvec_all) {
   extern __shared__ float fs[];  // [groups][C0] partial sums, then mean[C0], hidden[hid]
   const int groups = blockDim.x / C0;
   const int c = threadIdx.x % C0, grp = threadIdx.x / C0;
   pdl_launch_dependents();
+  const int slot = slots[blockIdx.x];  // uploaded before the predecessor kernel was launched
+  if (slot < 0) return;
   pdl_wait();
+  const float* glob = glob_all + static_cast<long long>(blockIdx.x) * g0 * g0 * C0;
+  const float* local = local_all + static_cast<long long>(slot) * g0 * LW3 * C0;
+  float* gvec = gvec_all + static_cast<long long>(slot) * C0;
   float acc = 0.f;
   if (grp < groups)
     for (int p = grp; p < g0 * g0; p += groups) {
@@ -181,10 +193,18 @@ clap_fusion_global_kernel(const float* __restrict__ glob, const float* __restric
 // glob[p][c] <- 2 glob gate + 2 local (1 - gate), gate = sigmoid(local_att(glob + local)[c] + gvec[c]); thread = position.
 constexpr int CF_MAXHID = 48;
 __global__ void __launch_bounds__(128)
-clap_fusion_apply_kernel(float* __restrict__ glob, const float* __restrict__ local, int g0, int LW3, int C0, int hid,
-                         const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                         const float* __restrict__ b2, const float* __restrict__ gvec) {
+clap_fusion_apply_kernel(float* __restrict__ glob_all, const float* __restrict__ local_all, const int* __restrict__ slots,
+                         int g0, int LW3, int C0, int hid, const float* __restrict__ w1, const float* __restrict__ b1,
+                         const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ gvec_all) {
   extern __shared__ float ws_[];  // w1 [hid][C0], w2 [C0][hid], b1 [hid], b2 + gvec [C0]
+  const int slot = slots[blockIdx.y];
+  if (slot < 0) {
+    pdl_launch_dependents();
+    return;
+  }
+  float* glob = glob_all + static_cast<long long>(blockIdx.y) * g0 * g0 * C0;
+  const float* local = local_all + static_cast<long long>(slot) * g0 * LW3 * C0;
+  const float* gvec = gvec_all + static_cast<long long>(slot) * C0;
   float* w1s = ws_;
   float* w2s = w1s + hid * C0;
   float* b1s = w2s + C0 * hid;
@@ -611,8 +631,9 @@ int clap_build(cc_clap* m, const cc_tensor* w, int nw) {
       CC_TRY(get(w, nw, pe + "mel_conv2d.bias", C0, stage, &mb));
       CC_TRY(keep_f32(A, mw, static_cast<size_t>(C0) * pp * 3, &m->mel_w));
       CC_TRY(keep_f32(A, mb, C0, &m->mel_b));
-      CC_TRY(A.alloc_t(&m->local32, static_cast<size_t>(m->grid0) * 3 * m->local_w * C0));
-      CC_TRY(A.alloc_t(&m->gvec, static_cast<size_t>(C0)));
+      CC_TRY(A.alloc_t(&m->local32, static_cast<size_t>(B) * m->grid0 * 3 * m->local_w * C0));
+      CC_TRY(A.alloc_t(&m->gvec, static_cast<size_t>(B) * C0));
+      CC_TRY(A.alloc_t(&m->slots, static_cast<size_t>(B)));
       CC_REQUIRE(3 * m->local_w <= m->grid0, CC_ESHAPE, "clap: %d local columns exceed the %d global ones", 3 * m->local_w, m->grid0);
       m->has_fusion = true;
       stage.release();
@@ -804,31 +825,35 @@ int cc_clap_forward(cc_clap* m, const void* mel, int mel_dtype, const unsigned c
   }
   CC_CUDA(cudaGetLastError());
   CC_TRY(gemm_run(m->p_embed, static_cast<int>(tokens0), s));  // conv as GEMM -> merge32 (scratch)
-  if (is_longer != nullptr) {  // modeling_clap.py:310-338: the flagged samples' global map is fused with their local views
+  int n_fused = 0;
+  if (is_longer != nullptr)
+    for (int b = 0; b < B; ++b) n_fused += is_longer[b] != 0;
+  if (n_fused > 0) {  // modeling_clap.py:310-338: the flagged samples' global map is fused with their local views
+    CC_REQUIRE(m->has_fusion, CC_EINVAL, "cc_clap_forward: %d samples are flagged is_longer but the handle has no fusion weights", n_fused);
+    CC_REQUIRE(channels == 4, CC_ESHAPE, "cc_clap_forward: feature fusion needs 4 mel views per sample, got %d", channels);
     const int C0 = c.embed, LW = m->local_w, hid = m->aff_hidden;
-    for (int b = 0; b < B; ++b) {
-      if (!is_longer[b]) continue;
-      CC_REQUIRE(m->has_fusion, CC_EINVAL, "cc_clap_forward: sample %d is flagged is_longer but the handle has no fusion weights", b);
-      CC_REQUIRE(channels == 4, CC_ESHAPE, "cc_clap_forward: feature fusion needs 4 mel views per sample, got %d", channels);
-      float* glob = m->merge32 + static_cast<size_t>(b) * g0 * g0 * C0;
-      const size_t psm = static_cast<size_t>(c.patch) * 3 * c.patch * sizeof(float);
-      if (mel_dtype == CC_F32)
-        clap_fusion_local_kernel<float><<<dim3(LW * g0, 3), 96, psm, s>>>(static_cast<const float*>(mel) + b * sample_stride, T, F, S, c.patch,
-                                                                          LW, C0, m->bn_scale, m->bn_shift, m->mel_w, m->mel_b, m->local32);
-      else
-        clap_fusion_local_kernel<__half><<<dim3(LW * g0, 3), 96, psm, s>>>(static_cast<const __half*>(mel) + b * sample_stride, T, F, S,
-                                                                           c.patch, LW, C0, m->bn_scale, m->bn_shift, m->mel_w, m->mel_b,
-                                                                           m->local32);
-      CC_CUDA(cudaGetLastError());
-      const int gthreads = (1024 / C0) * C0 > 0 ? (1024 / C0) * C0 : C0;
-      CC_CUDA(launch_pdl(clap_fusion_global_kernel, dim3(1), dim3(gthreads), static_cast<size_t>(gthreads + C0 + hid) * sizeof(float),
-                         s, static_cast<const float*>(glob), static_cast<const float*>(m->local32), g0, 3 * LW, C0, hid, m->gw1,
-                         m->gb1, m->gw2, m->gb2, m->gvec));
-      CC_CUDA(launch_pdl(clap_fusion_apply_kernel, dim3((g0 * g0 + 127) / 128), dim3(128),
-                         static_cast<size_t>(2 * hid * C0 + hid + C0) * sizeof(float), s, glob, static_cast<const float*>(m->local32),
-                         g0, 3 * LW, C0, hid, m->lw1, m->lb1, m->lw2, m->lb2, static_cast<const float*>(m->gvec)));
-      m->launches += 3;
-    }
+    std::vector<int> slots(static_cast<size_t>(B));
+    for (int b = 0, k = 0; b < B; ++b) slots[b] = is_longer[b] ? k++ : -1;
+    // pageable source: the copy is staged before the call returns, so the vector may die with this scope
+    CC_CUDA(cudaMemcpyAsync(m->slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    const size_t psm = static_cast<size_t>(c.patch) * 3 * c.patch * sizeof(float);
+    const dim3 lgrid(LW * g0, 3, B);
+    if (mel_dtype == CC_F32)
+      clap_fusion_local_kernel<float><<<lgrid, 96, psm, s>>>(static_cast<const float*>(mel), sample_stride, m->slots, T, F, S, c.patch, LW,
+                                                             C0, m->bn_scale, m->bn_shift, m->mel_w, m->mel_b, m->local32);
+    else
+      clap_fusion_local_kernel<__half><<<lgrid, 96, psm, s>>>(static_cast<const __half*>(mel), sample_stride, m->slots, T, F, S, c.patch,
+                                                              LW, C0, m->bn_scale, m->bn_shift, m->mel_w, m->mel_b, m->local32);
+    CC_CUDA(cudaGetLastError());
+    const int gthreads = (1024 / C0) * C0 > 0 ? (1024 / C0) * C0 : C0;
+    CC_CUDA(launch_pdl(clap_fusion_global_kernel, dim3(B), dim3(gthreads), static_cast<size_t>(gthreads + C0 + hid) * sizeof(float), s,
+                       static_cast<const float*>(m->merge32), static_cast<const float*>(m->local32),
+                       static_cast<const int*>(m->slots), g0, 3 * LW, C0, hid, m->gw1, m->gb1, m->gw2, m->gb2, m->gvec));
+    CC_CUDA(launch_pdl(clap_fusion_apply_kernel, dim3((g0 * g0 + 127) / 128, B), dim3(128),
+                       static_cast<size_t>(2 * hid * C0 + hid + C0) * sizeof(float), s, m->merge32,
+                       static_cast<const float*>(m->local32), static_cast<const int*>(m->slots), g0, 3 * LW, C0, hid, m->lw1,
+                       m->lb1, m->lw2, m->lb2, static_cast<const float*>(m->gvec)));
+    m->launches += 3;
   }
   // patch LayerNorm, fp32 -> the fp32 residual stream
   CC_CUDA(launch_pdl(clap_ln_f32_kernel, dim3(grid_for(tokens0 * 32, 256)), dim3(256), 0, s,

@@ -1,4 +1,4 @@
-"""Two B=64 forwards of the CLAP tower for an ncu launch list (development aid)."""
+"""Two forwards of the CLAP tower at 128 clips (the second with one fused sample) for an ncu launch list."""
 import sys
 sys.path.insert(0, ".")
 sys.path.insert(0, "tests")
@@ -7,11 +7,14 @@ from oracle import restate_clap as RC
 from test_clap_gpu import _weights, _engine
 
 cfg = RC.ClapCfg()
-eng = _engine(_weights(cfg, 0), cfg, 64, "cuda:0")
-big = torch.randn(64, 1, 1001, 64, device="cuda")
+eng = _engine(_weights(cfg, 0), cfg, 128, "cuda:0")
+big = torch.randn(128, 4, 1001, 64, device="cuda")
+flags = torch.zeros(128, dtype=torch.bool)
+flags[5] = True
+eng.forward(big, is_longer=flags)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-for _ in range(2):
-    eng.forward(big)
+eng.forward(big)
+eng.forward(big, is_longer=flags)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
