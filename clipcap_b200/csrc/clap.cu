@@ -55,8 +55,8 @@ struct cc_clap {
   const float *mel_w = nullptr, *mel_b = nullptr;                                          // [C0][p * 3p], [C0]
   const float *lw1 = nullptr, *lb1 = nullptr, *lw2 = nullptr, *lb2 = nullptr;              // local attention branch
   const float *gw1 = nullptr, *gb1 = nullptr, *gw2 = nullptr, *gb2 = nullptr;              // global attention branch
-  float *local32 = nullptr, *gvec = nullptr;  // per fused sample (slot): [g0][3 * local_w][C0]; [C0]
-  int* slots = nullptr;                       // [max_batch]: slot of a flagged sample, -1 otherwise (uploaded per call)
+  float *local32 = nullptr, *gvec = nullptr;  // per fused sample (slot): [g0][3 * local_w][C0]; partial sums [CF_CHUNKS][C0]
+  int* slots = nullptr;                       // [max_batch]: sample index of each slot (uploaded per call)
   int launches = 0;
 };
 
@@ -120,95 +120,87 @@ __global__ void clap_patches_kernel(const SRC* __restrict__ mel, long long sampl
 }
 
 // ---------------------------------------------------------------- feature fusion of the long clips (ClapAudioPatchEmbed + AFF)
-// Every kernel runs over all samples of the batch; CTAs of samples without a slot (not flagged is_longer) leave at once.
+// Every kernel runs over the flagged samples of the batch at once: fused[slot] = index of the slot-th flagged sample.
 // local[y][view * LW + xw][co] = bias[co] + sum_{ky,kx} w[co][ky][kx] * image_{view+1}[p y + ky][3p xw + kx]: the three local
-// views through the p x 3p / (p, 3p) convolution, laid side by side along time. One CTA per output position, thread = co.
+// views through the p x 3p / (p, 3p) convolution, laid side by side along time. One CTA per (output row y, view, sample):
+// the p image rows the row needs are built once in shared memory, thread = output channel with its filter in registers.
+constexpr int CF_P = 4;  // patch size the fusion kernels are written for
 template <typename SRC>
-__global__ void clap_fusion_local_kernel(const SRC* __restrict__ mel, long long sample_stride, const int* __restrict__ slots,
-                                         int T, int F, int S, int patch, int LW, int C0, const float* __restrict__ bn_scale,
+__global__ void clap_fusion_local_kernel(const SRC* __restrict__ mel, long long sample_stride, const int* __restrict__ fused,
+                                         int T, int F, int S, int LW, int C0, const float* __restrict__ bn_scale,
                                          const float* __restrict__ bn_shift, const float* __restrict__ w,
                                          const float* __restrict__ bias, float* __restrict__ local_all) {
-  extern __shared__ float patch_s[];  // [patch][3 patch]
-  const int slot = slots[blockIdx.z];
-  if (slot < 0) return;
-  const int kw = 3 * patch, kn = patch * kw;
-  const int xw = blockIdx.x % LW, y = blockIdx.x / LW, view = blockIdx.y;
-  const SRC* src = mel + blockIdx.z * sample_stride + static_cast<long long>(view + 1) * T * F;
-  float* local = local_all + static_cast<long long>(slot) * (S / patch) * (3 * LW) * C0;
-  for (int k = threadIdx.x; k < kn; k += blockDim.x)
-    patch_s[k] = mel_image_value(src, T, F, S, y * patch + k / kw, xw * kw + k % kw, bn_scale, bn_shift);
+  extern __shared__ float rows_s[];  // [CF_P][LW * 3 * CF_P]
+  constexpr int KW = 3 * CF_P, KN = CF_P * KW;
+  const int y = blockIdx.x, view = blockIdx.y, slot = blockIdx.z, b = fused[slot];
+  const int width = LW * KW;
+  const SRC* src = mel + b * sample_stride + static_cast<long long>(view + 1) * T * F;
+  for (int i = threadIdx.x; i < CF_P * width; i += blockDim.x)
+    rows_s[i] = mel_image_value(src, T, F, S, y * CF_P + i / width, i % width, bn_scale, bn_shift);
   __syncthreads();
+  float* local = local_all + (static_cast<long long>(slot) * (S / CF_P) + y) * (3 * LW) * C0;
   for (int co = threadIdx.x; co < C0; co += blockDim.x) {
-    float acc = bias[co];
-    for (int k = 0; k < kn; ++k) acc += w[co * kn + k] * patch_s[k];
-    local[(static_cast<long long>(y) * (3 * LW) + view * LW + xw) * C0 + co] = acc;
+    float wr[KN];
+#pragma unroll
+    for (int k = 0; k < KN; ++k) wr[k] = w[co * KN + k];
+    const float bco = bias[co];
+    for (int xw = 0; xw < LW; ++xw) {
+      float acc = bco;
+#pragma unroll
+      for (int k = 0; k < KN; ++k) acc += wr[k] * rows_s[(k / KW) * width + xw * KW + (k % KW)];
+      local[(view * LW + xw) * C0 + co] = acc;
+    }
   }
 }
 
-// gvec[c] = global-attention branch of the AFF block on mean over all positions of (global + local): one CTA.
+// partial[slot][chunk][c] = sum over the chunk's positions of (global + local)[c]  (the mean feeding the global-attention branch)
+constexpr int CF_CHUNKS = 32;
 __global__ void __launch_bounds__(1024)
-clap_fusion_global_kernel(const float* __restrict__ glob_all, const float* __restrict__ local_all,
-                          const int* __restrict__ slots, int g0, int LW3, int C0, int hid, const float* __restrict__ w1,
-                          const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
-                          float* __restrict__ gvec_all) {
-  extern __shared__ float fs[];  // [groups][C0] partial sums, then mean[C0], hidden[hid]
+clap_fusion_sum_kernel(const float* __restrict__ glob_all, const float* __restrict__ local_all, const int* __restrict__ fused,
+                       int g0, int LW3, int C0, float* __restrict__ partial) {
+  extern __shared__ float fs[];  // [groups][C0]
   const int groups = blockDim.x / C0;
   const int c = threadIdx.x % C0, grp = threadIdx.x / C0;
   pdl_launch_dependents();
-  const int slot = slots[blockIdx.x];  // uploaded before the predecessor kernel was launched
-  if (slot < 0) return;
+  const int slot = blockIdx.y, b = fused[slot];  // uploaded before the predecessor kernel was launched
   pdl_wait();
-  const float* glob = glob_all + static_cast<long long>(blockIdx.x) * g0 * g0 * C0;
+  const float* glob = glob_all + static_cast<long long>(b) * g0 * g0 * C0;
   const float* local = local_all + static_cast<long long>(slot) * g0 * LW3 * C0;
-  float* gvec = gvec_all + static_cast<long long>(slot) * C0;
+  const int per = (g0 * g0 + CF_CHUNKS - 1) / CF_CHUNKS;
+  const int p0 = blockIdx.x * per, p1 = min(g0 * g0, p0 + per);
   float acc = 0.f;
-  if (grp < groups)
-    for (int p = grp; p < g0 * g0; p += groups) {
-      const int y = p / g0, x = p - y * g0;
-      acc += glob[static_cast<long long>(p) * C0 + c] + (x < LW3 ? local[(static_cast<long long>(y) * LW3 + x) * C0 + c] : 0.f);
-    }
-  if (grp < groups) fs[grp * C0 + c] = acc;
+  for (int p = p0 + grp; p < p1; p += groups) {
+    const int y = p / g0, x = p - y * g0;
+    acc += glob[static_cast<long long>(p) * C0 + c] + (x < LW3 ? local[(static_cast<long long>(y) * LW3 + x) * C0 + c] : 0.f);
+  }
+  fs[grp * C0 + c] = acc;
   __syncthreads();
-  float* mean = fs + groups * C0;
-  float* hidden = mean + C0;
   if (threadIdx.x < C0) {
     float t = 0.f;
     for (int k = 0; k < groups; ++k) t += fs[k * C0 + threadIdx.x];
-    mean[threadIdx.x] = t / static_cast<float>(g0 * g0);
-  }
-  __syncthreads();
-  if (threadIdx.x < hid) {
-    float t = b1[threadIdx.x];
-    for (int k = 0; k < C0; ++k) t += w1[threadIdx.x * C0 + k] * mean[k];
-    hidden[threadIdx.x] = fmaxf(t, 0.f);
-  }
-  __syncthreads();
-  if (threadIdx.x < C0) {
-    float t = b2[threadIdx.x];
-    for (int k = 0; k < hid; ++k) t += w2[threadIdx.x * hid + k] * hidden[k];
-    gvec[threadIdx.x] = t;
+    partial[(static_cast<long long>(slot) * CF_CHUNKS + blockIdx.x) * C0 + threadIdx.x] = t;
   }
 }
 
-// glob[p][c] <- 2 glob gate + 2 local (1 - gate), gate = sigmoid(local_att(glob + local)[c] + gvec[c]); thread = position.
+// glob[p][c] <- 2 glob gate + 2 local (1 - gate), gate = sigmoid(local_att(glob + local)[c] + global_att(mean)[c]); thread =
+// position. Every CTA first finishes the global-attention branch for its sample (sum of the 32 partials -> 96 -> hid -> 96).
 constexpr int CF_MAXHID = 48;
 __global__ void __launch_bounds__(128)
-clap_fusion_apply_kernel(float* __restrict__ glob_all, const float* __restrict__ local_all, const int* __restrict__ slots,
+clap_fusion_apply_kernel(float* __restrict__ glob_all, const float* __restrict__ local_all, const int* __restrict__ fused,
                          int g0, int LW3, int C0, int hid, const float* __restrict__ w1, const float* __restrict__ b1,
-                         const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ gvec_all) {
-  extern __shared__ float ws_[];  // w1 [hid][C0], w2 [C0][hid], b1 [hid], b2 + gvec [C0]
-  const int slot = slots[blockIdx.y];
-  if (slot < 0) {
-    pdl_launch_dependents();
-    return;
-  }
-  float* glob = glob_all + static_cast<long long>(blockIdx.y) * g0 * g0 * C0;
+                         const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ gw1,
+                         const float* __restrict__ gb1, const float* __restrict__ gw2, const float* __restrict__ gb2,
+                         const float* __restrict__ partial) {
+  extern __shared__ float ws_[];  // w1 [hid][C0], w2 [C0][hid], b1 [hid], b2 + global branch [C0], mean [C0], ghid [hid]
+  const int slot = blockIdx.y, b = fused[slot];
+  float* glob = glob_all + static_cast<long long>(b) * g0 * g0 * C0;
   const float* local = local_all + static_cast<long long>(slot) * g0 * LW3 * C0;
-  const float* gvec = gvec_all + static_cast<long long>(slot) * C0;
   float* w1s = ws_;
   float* w2s = w1s + hid * C0;
   float* b1s = w2s + C0 * hid;
   float* b2s = b1s + hid;
+  float* mean = b2s + C0;
+  float* ghid = mean + C0;
   for (int i = threadIdx.x; i < hid * C0; i += blockDim.x) {
     w1s[i] = w1[i];
     w2s[i] = w2[i];
@@ -216,7 +208,23 @@ clap_fusion_apply_kernel(float* __restrict__ glob_all, const float* __restrict__
   for (int i = threadIdx.x; i < hid; i += blockDim.x) b1s[i] = b1[i];
   pdl_launch_dependents();
   pdl_wait();
-  for (int i = threadIdx.x; i < C0; i += blockDim.x) b2s[i] = b2[i] + gvec[i];
+  for (int i = threadIdx.x; i < C0; i += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < CF_CHUNKS; ++k) t += partial[(static_cast<long long>(slot) * CF_CHUNKS + k) * C0 + i];
+    mean[i] = t / static_cast<float>(g0 * g0);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < hid; j += blockDim.x) {
+    float t = gb1[j];
+    for (int k = 0; k < C0; ++k) t += gw1[j * C0 + k] * mean[k];
+    ghid[j] = fmaxf(t, 0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C0; i += blockDim.x) {
+    float t = gb2[i] + b2[i];
+    for (int k = 0; k < hid; ++k) t += gw2[i * hid + k] * ghid[k];
+    b2s[i] = t;
+  }
   __syncthreads();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g0 * g0) return;
@@ -585,7 +593,8 @@ int clap_build(cc_clap* m, const cc_tensor* w, int nw) {
       const int hid = static_cast<int>(hid_numel / C0);
       CC_REQUIRE(hid >= 1 && hid <= CF_MAXHID && static_cast<int64_t>(hid) * C0 == hid_numel, CC_ESHAPE,
                  "clap: AFF hidden width %d (max %d)", hid, CF_MAXHID);
-      CC_REQUIRE(S >= 3 * c.patch, CC_ESHAPE, "clap: spec_size %d too small for the fusion convolution", S);
+      CC_REQUIRE(S >= 3 * c.patch && c.patch == CF_P && C0 <= 1024, CC_ESHAPE,
+                 "clap: the fusion kernels take patch %d (got %d), spec_size %d, embed %d", CF_P, c.patch, S, C0);
       m->aff_hidden = hid;
       m->local_w = (S - 3 * c.patch) / (3 * c.patch) + 1;
       auto fetch = [&](const std::string& name, int64_t numel, std::vector<float>& out) -> int {
@@ -632,7 +641,7 @@ int clap_build(cc_clap* m, const cc_tensor* w, int nw) {
       CC_TRY(keep_f32(A, mw, static_cast<size_t>(C0) * pp * 3, &m->mel_w));
       CC_TRY(keep_f32(A, mb, C0, &m->mel_b));
       CC_TRY(A.alloc_t(&m->local32, static_cast<size_t>(B) * m->grid0 * 3 * m->local_w * C0));
-      CC_TRY(A.alloc_t(&m->gvec, static_cast<size_t>(B) * C0));
+      CC_TRY(A.alloc_t(&m->gvec, static_cast<size_t>(B) * CF_CHUNKS * C0));
       CC_TRY(A.alloc_t(&m->slots, static_cast<size_t>(B)));
       CC_REQUIRE(3 * m->local_w <= m->grid0, CC_ESHAPE, "clap: %d local columns exceed the %d global ones", 3 * m->local_w, m->grid0);
       m->has_fusion = true;
@@ -832,27 +841,28 @@ int cc_clap_forward(cc_clap* m, const void* mel, int mel_dtype, const unsigned c
     CC_REQUIRE(m->has_fusion, CC_EINVAL, "cc_clap_forward: %d samples are flagged is_longer but the handle has no fusion weights", n_fused);
     CC_REQUIRE(channels == 4, CC_ESHAPE, "cc_clap_forward: feature fusion needs 4 mel views per sample, got %d", channels);
     const int C0 = c.embed, LW = m->local_w, hid = m->aff_hidden;
-    std::vector<int> slots(static_cast<size_t>(B));
-    for (int b = 0, k = 0; b < B; ++b) slots[b] = is_longer[b] ? k++ : -1;
+    std::vector<int> slots;  // slot -> sample
+    for (int b = 0; b < B; ++b)
+      if (is_longer[b]) slots.push_back(b);
     // pageable source: the copy is staged before the call returns, so the vector may die with this scope
     CC_CUDA(cudaMemcpyAsync(m->slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-    const size_t psm = static_cast<size_t>(c.patch) * 3 * c.patch * sizeof(float);
-    const dim3 lgrid(LW * g0, 3, B);
+    const size_t psm = static_cast<size_t>(CF_P) * LW * 3 * CF_P * sizeof(float);
+    const dim3 lgrid(g0, 3, n_fused);
     if (mel_dtype == CC_F32)
-      clap_fusion_local_kernel<float><<<lgrid, 96, psm, s>>>(static_cast<const float*>(mel), sample_stride, m->slots, T, F, S, c.patch, LW,
-                                                             C0, m->bn_scale, m->bn_shift, m->mel_w, m->mel_b, m->local32);
+      clap_fusion_local_kernel<float><<<lgrid, 96, psm, s>>>(static_cast<const float*>(mel), sample_stride, m->slots, T, F, S, LW, C0,
+                                                             m->bn_scale, m->bn_shift, m->mel_w, m->mel_b, m->local32);
     else
-      clap_fusion_local_kernel<__half><<<lgrid, 96, psm, s>>>(static_cast<const __half*>(mel), sample_stride, m->slots, T, F, S, c.patch,
-                                                              LW, C0, m->bn_scale, m->bn_shift, m->mel_w, m->mel_b, m->local32);
+      clap_fusion_local_kernel<__half><<<lgrid, 96, psm, s>>>(static_cast<const __half*>(mel), sample_stride, m->slots, T, F, S, LW, C0,
+                                                              m->bn_scale, m->bn_shift, m->mel_w, m->mel_b, m->local32);
     CC_CUDA(cudaGetLastError());
     const int gthreads = (1024 / C0) * C0 > 0 ? (1024 / C0) * C0 : C0;
-    CC_CUDA(launch_pdl(clap_fusion_global_kernel, dim3(B), dim3(gthreads), static_cast<size_t>(gthreads + C0 + hid) * sizeof(float), s,
+    CC_CUDA(launch_pdl(clap_fusion_sum_kernel, dim3(CF_CHUNKS, n_fused), dim3(gthreads), static_cast<size_t>(gthreads) * sizeof(float), s,
                        static_cast<const float*>(m->merge32), static_cast<const float*>(m->local32),
-                       static_cast<const int*>(m->slots), g0, 3 * LW, C0, hid, m->gw1, m->gb1, m->gw2, m->gb2, m->gvec));
-    CC_CUDA(launch_pdl(clap_fusion_apply_kernel, dim3((g0 * g0 + 127) / 128, B), dim3(128),
-                       static_cast<size_t>(2 * hid * C0 + hid + C0) * sizeof(float), s, m->merge32,
+                       static_cast<const int*>(m->slots), g0, 3 * LW, C0, m->gvec));
+    CC_CUDA(launch_pdl(clap_fusion_apply_kernel, dim3((g0 * g0 + 127) / 128, n_fused), dim3(128),
+                       static_cast<size_t>(2 * hid * C0 + 2 * hid + 2 * C0) * sizeof(float), s, m->merge32,
                        static_cast<const float*>(m->local32), static_cast<const int*>(m->slots), g0, 3 * LW, C0, hid, m->lw1,
-                       m->lb1, m->lw2, m->lb2, static_cast<const float*>(m->gvec)));
+                       m->lb1, m->lw2, m->lb2, m->gw1, m->gb1, m->gw2, m->gb2, static_cast<const float*>(m->gvec)));
     m->launches += 3;
   }
   // patch LayerNorm, fp32 -> the fp32 residual stream
