@@ -13,8 +13,9 @@
 //   LN(4C) -> GEMM 4C -> 2C);  final LN + mean over the 64 tokens -> Linear + ReLU -> Linear.
 // Tokens stay in image order the whole time: the cyclic shift and the window partition / reverse of the reference are
 // index arithmetic inside the attention kernel (it gathers its window's rows of the QKV matrix and scatters its output
-// rows), not data movement. Only `is_longer == False` samples are supported (the fusion branch of the patch embedding
-// only acts on clips longer than the 10 s window; BASELINE configs[4] feeds 10 s clips): channel 0 of the input is used.
+// rows), not data movement. Samples flagged is_longer (clips longer than the 10 s window) additionally run the feature
+// fusion of the patch embedding: the three local mel views through a 4x12 / (4,12) convolution, then the AFF block that gates
+// between the global map and the local one (modeling_clap.py:296-344, :238-245) — three fp32 kernels on the conv output.
 #include <string>
 #include <vector>
 
