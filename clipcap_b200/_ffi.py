@@ -19,6 +19,7 @@ STATUS_NAMES = {0: "CC_OK", -1: "CC_EINVAL", -2: "CC_ESHAPE", -3: "CC_EALIGN", -
 
 # GEMM epilogues (csrc/common.h `enum Epi`)
 EPI_F16_NONE, EPI_F16_RELU, EPI_F16_QUICKGELU, EPI_F16_GELU_NEW, EPI_F16_TANH, EPI_F32, EPI_RESID_F32, EPI_ARGMAX = range(8)
+EPI_F16_GELU_ERF = 10  # after the two internal plan kinds (split-K partials, head-major QKV)
 
 CC_MAPPER_TRANSFORMER, CC_MAPPER_WINDOWED, CC_MAPPER_MLP = 0, 1, 2
 CC_GEN_GREEDY, CC_GEN_BEAM, CC_GEN_NUCLEUS, CC_GEN_SAMPLE = 0, 1, 2, 3

@@ -244,7 +244,7 @@ int cc_op_adamw(float* p, const float* g, float* m, float* v, int64_t n, float l
  * ------------------------------------------------------------------------------------------------------------------ */
 /* C[M,N] = A[M,K] (fp16, row stride lda) x W[N,K]^T (fp16, row stride K) with epilogue `epi` (see csrc/common.h):
  * 0..4 fp16 out with none/relu/quickgelu/gelu_new/tanh, 5 fp32 out, 6 fp32 in-place residual add, 7 fused argmax
- * (out = uint64 keys[M], must be zeroed). bn = 0 picks BLOCK_N heuristically. */
+ * (out = uint64 keys[M], must be zeroed), 10 fp16 out with the exact (erf) GELU. bn = 0 picks BLOCK_N heuristically. */
 int cc_op_gemm(const void* a, int64_t lda, const void* w, const float* bias, void* out, int64_t ldc, int M, int N, int K,
                int epi, int bn, void* stream);
 int cc_op_layernorm(const float* x, int64_t x_ld, const float* gamma, const float* beta, void* y, int64_t y_ld, int rows,

@@ -37,7 +37,8 @@ def test_gemm_epilogues(cuda_device, shape, bn):
     cases = [(_ffi.EPI_F16_NONE, torch.half, lambda r: r), (_ffi.EPI_F16_RELU, torch.half, torch.relu),
              (_ffi.EPI_F16_QUICKGELU, torch.half, lambda r: r * torch.sigmoid(1.702 * r)),
              (_ffi.EPI_F16_GELU_NEW, torch.half, lambda r: torch.nn.functional.gelu(r, approximate="tanh")),
-             (_ffi.EPI_F16_TANH, torch.half, torch.tanh), (_ffi.EPI_F32, torch.float, lambda r: r)]
+             (_ffi.EPI_F16_TANH, torch.half, torch.tanh), (_ffi.EPI_F32, torch.float, lambda r: r),
+             (_ffi.EPI_F16_GELU_ERF, torch.half, torch.nn.functional.gelu)]   # exact (erf) GELU of the Swin MLP
     for epi, dt, fn in cases:
         out = torch.zeros(M, N, device=cuda_device, dtype=dt)
         _ffi.check(lib.cc_op_gemm(a.data_ptr(), K, w.data_ptr(), bias.data_ptr(), out.data_ptr(), N, M, N, K, epi, bn,
@@ -57,6 +58,32 @@ def test_gemm_epilogues(cuda_device, shape, bn):
     raw = a.float() @ w.float().t()
     got, best = raw.gather(1, idx.view(-1, 1)).squeeze(1), raw.max(1).values
     assert ((best - got).abs().max() / best.abs().max()).item() < GEMM_TOL
+
+
+@pytest.mark.parametrize("shape,epi", [((8192, 96, 16), "f32"), ((8192, 288, 96), "none"), ((8192, 384, 96), "gelu_erf"),
+                                       ((8192, 96, 384), "resid"), ((2048, 576, 192), "none"), ((40, 512, 768), "relu")])
+def test_gemm_swin_shapes(cuda_device, shape, epi):
+    """The narrow shapes of the CLAP audio tower: K = 16 (4x4 patch embedding: one TMA box wider than the matrix), N and K
+    that are multiples of 96, the exact-GELU and residual epilogues on them."""
+    lib = _ffi.lib()
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    a = (torch.randn(M, K, device=cuda_device, generator=g) * 0.5).half()
+    w = (torch.randn(N, K, device=cuda_device, generator=g) * 0.1).half()
+    bias = torch.randn(N, device=cuda_device, generator=g)
+    ref = a.float() @ w.float().t() + bias
+    code, dt, fn = {"f32": (_ffi.EPI_F32, torch.float, lambda r: r), "none": (_ffi.EPI_F16_NONE, torch.half, lambda r: r),
+                    "gelu_erf": (_ffi.EPI_F16_GELU_ERF, torch.half, torch.nn.functional.gelu),
+                    "relu": (_ffi.EPI_F16_RELU, torch.half, torch.relu),
+                    "resid": (_ffi.EPI_RESID_F32, torch.float, lambda r: r)}[epi]
+    if epi == "resid":
+        out = torch.randn(M, N, device=cuda_device, generator=g)
+        ref = ref + out
+    else:
+        out = torch.zeros(M, N, device=cuda_device, dtype=dt)
+    _ffi.check(lib.cc_op_gemm(a.data_ptr(), K, w.data_ptr(), bias.data_ptr(), out.data_ptr(), N, M, N, K, code, 0, _stream()))
+    torch.cuda.synchronize()
+    assert _rel(out, fn(ref)) < GEMM_TOL, (shape, epi)
 
 
 def test_gemm_odd_vocabulary_fp32(cuda_device):
