@@ -793,6 +793,8 @@ int cc_clap_create(cc_clap** h, const cc_clap_cfg* cfg, const cc_tensor* weights
     CC_REQUIRE(cfg->depths[i] > 0 && cfg->heads[i] > 0, CC_ESHAPE, "clap: stage %d depth %d heads %d", i, cfg->depths[i], cfg->heads[i]);
   CC_REQUIRE((cfg->spec_size / cfg->patch) % 64 == 0, CC_ESHAPE, "clap: %d tokens per side must be a multiple of 64",
              cfg->spec_size / cfg->patch);
+  // per device: the handle's device is the one current now
+  CC_CUDA(cudaFuncSetAttribute(clap_window_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CW_SMEM)));
   cc_clap* m = new cc_clap();
   m->cfg = *cfg;
   if (m->cfg.eps <= 0.f) m->cfg.eps = 1e-5f;
@@ -817,9 +819,6 @@ int cc_clap_forward(cc_clap* m, const void* mel, int mel_dtype, const unsigned c
              T, S * ratio);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   m->launches = 0;
-  static const cudaError_t smem_attr = cudaFuncSetAttribute(clap_window_attn_mma_kernel,
-                                                            cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CW_SMEM));
-  CC_CUDA(smem_attr);
   const int g0 = m->grid0;
   const long long tokens0 = static_cast<long long>(B) * g0 * g0;
   const long long sample_stride = static_cast<long long>(channels) * T * F;

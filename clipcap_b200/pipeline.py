@@ -1,6 +1,6 @@
-"""Host-side serving loop around the hot path: pinned host pixels in, token ids in pinned host memory out, with the
-host->device copy of batch i+1 running on a copy stream while batch i is on the compute stream (double-buffered device
-staging). This is what `bench.py`'s end-to-end number measures; the reference moves one image at a time with a blocking
+"""Host-side serving loop around the hot path: pinned host pixels (or, with `input_shape`, any encoder input such as the
+[4, 1001, 64] mel features of the CLAP tower) in, token ids in pinned host memory out, with the host->device copy of
+batch i+1 running on a copy stream while batch i is on the compute stream (double-buffered device staging). This is what `bench.py`'s end-to-end number measures; the reference moves one image at a time with a blocking
 `.to(device)` (docs/inference.md:22-27, preprocess/mapper.py:17).
 """
 from __future__ import annotations
@@ -15,13 +15,13 @@ from clipcap_b200.distributed import caption_step
 class CaptionPipeline:
     def __init__(self, encode_fn: Callable, model, batch: int, image_size: int = 224, entry_length: int = 20,
                  stop_token: int = 50256, device="cuda", pixel_dtype: torch.dtype = torch.float32,
-                 prefix_all: Optional[torch.Tensor] = None):
+                 prefix_all: Optional[torch.Tensor] = None, input_shape: Optional[Tuple[int, ...]] = None):
         self.encode_fn, self.model = encode_fn, model
         self.entry_length, self.stop_token = entry_length, stop_token
         self.device = torch.device(device)
         self.prefix_all = prefix_all
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        shape = (batch, 3, image_size, image_size)
+        shape = (batch, *input_shape) if input_shape is not None else (batch, 3, image_size, image_size)
         self._px = [torch.empty(shape, device=self.device, dtype=pixel_dtype) for _ in range(2)]
         self._copied = [torch.cuda.Event() for _ in range(2)]     # staging buffer i holds its batch
         self._consumed = [torch.cuda.Event() for _ in range(2)]   # the compute stream no longer reads buffer i

@@ -48,6 +48,36 @@ def test_pipeline_equals_direct_calls(cuda_device):
     assert list(pipe.run([])) == []
 
 
+def test_pipeline_with_audio_encoder(cuda_device):
+    """BASELINE configs[4] through the same serving loop: mel features -> CLAP tower -> mapper (E = 512) -> greedy decode."""
+    from clipcap_b200.encoders import get_encoder
+    from clipcap_b200.encoders.config import EncoderConfig
+    from clipcap_b200.inference.base import generate_greedy_tokens
+    from clipcap_b200.model import ClipCapModelPrefixOnly, Config
+    from clipcap_b200.pipeline import CaptionPipeline
+    spec, gcfg, mcfg, _, lm_w, g = load_lm_case("tiny_a")
+    torch.manual_seed(3)
+    encode_fn, transform = get_encoder("clap", "", device=cuda_device)
+    cfg = Config(language_model=spec, prefix_length=mcfg.K, projection_length=mcfg.P, transformer_layers=mcfg.L,
+                 transformer_attention_heads=mcfg.H, encoder_config=EncoderConfig(encoder_model_name="clap",
+                                                                                 encoder_embedding_size=512))
+    model = ClipCapModelPrefixOnly(cfg)
+    model.load_state_dict({f"language_model.{k}": v for k, v in lm_w.items()}, strict=False)
+    model = model.eval().to(cuda_device)
+    EL, stop = 6, int(g["stop_token"])
+    gen = torch.Generator().manual_seed(8)
+    batches = [transform(torch.randn(n, 4, 1001, 64, generator=gen)).pin_memory() for n in (3, 3, 2)]
+    pipe = CaptionPipeline(encode_fn, model, 3, entry_length=EL, stop_token=stop, device=cuda_device, input_shape=(4, 1001, 64))
+    assert pipe.h2d_bytes_per_batch == 3 * 4 * 1001 * 64 * 4
+    got = [(t.clone(), l.clone()) for t, l in pipe.run(batches)]
+    assert len(got) == 3
+    for mel, (toks, lens) in zip(batches, got):
+        emb = encode_fn(mel.to(cuda_device))
+        assert tuple(emb.shape) == (mel.shape[0], 512)
+        want_t, want_l, _ = generate_greedy_tokens(model, model.transformer_mapper(emb), EL, stop)
+        assert torch.equal(toks, want_t.cpu()) and torch.equal(lens, want_l.cpu())
+
+
 def test_encoder_mapper_and_writer(cuda_device, tmp_path):
     from clipcap_b200.preprocess import EncoderMapper, NumpyWriter
     encode_fn, model, vcfg, _ = _build(cuda_device)
