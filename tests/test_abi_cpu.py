@@ -52,3 +52,32 @@ def test_no_device_is_an_error_not_a_fallback():
     x = (C.c_float * 8)()
     st = lib.cc_op_layernorm(x, 8, x, x, x, 8, 1, 8, 1e-5, None)
     assert st in (-4, -6), _ffi.last_error()  # CC_ECUDA / CC_EARCH
+
+
+def test_struct_layouts_match_the_header_compiled_as_c(tmp_path):
+    """include/clipcap_b200.h is plain C: gcc compiles it, and the sizes and field offsets it gives every struct are the
+    ones the ctypes mirrors in clipcap_b200/_ffi.py have (so a cgo / JNI / ctypes binding sees the same layout)."""
+    import shutil
+    import subprocess
+    import pytest
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = {n: getattr(_ffi, n) for n in ("cc_tensor", "cc_vit_cfg", "cc_clap_cfg", "cc_mapper_cfg", "cc_gpt2_cfg",
+                                             "cc_gen_cfg")}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "clipcap_b200.h"', 'int main(void) {']
+    for name, st in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in st._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True,
+                                                       text=True).stdout.splitlines())
+    for name, st in structs.items():
+        assert int(got[name]) == C.sizeof(st), name
+        for field, _ in st._fields_:
+            assert int(got[f"{name}.{field}"]) == getattr(st, field).offset, f"{name}.{field}"
