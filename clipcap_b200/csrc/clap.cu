@@ -445,17 +445,20 @@ __global__ void clap_merge_gather_kernel(const float4* __restrict__ x, float4* _
   }
 }
 
-// pooled[b, :] = mean over the `tokens` rows of LayerNorm(x[b, t, :])  (fp32 statistics and mean; one CTA per sample)
-__global__ void __launch_bounds__(256)
+// pooled[b, :] = mean over the `tokens` rows of LayerNorm(x[b, t, :])  (fp32 statistics and mean; one CTA per sample). Every
+// warp sums its tokens (t = warp, warp + 8, ...) into its own row of shared memory, the rows are then added in warp order:
+// the result does not depend on scheduling.
+constexpr int CP_WARPS = 8;
+__global__ void __launch_bounds__(CP_WARPS * 32)
 clap_ln_meanpool_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bta,
                         __half* __restrict__ pooled, int tokens, int C, float eps) {
-  extern __shared__ float acc[];  // [C]
+  extern __shared__ float acc[];  // [CP_WARPS][C]
   pdl_launch_dependents();
   pdl_wait();
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) acc[c] = 0.f;
-  __syncthreads();
-  for (int t = warp; t < tokens; t += nw) {
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* mine = acc + warp * C;
+  for (int c = lane; c < C; c += 32) mine[c] = 0.f;
+  for (int t = warp; t < tokens; t += CP_WARPS) {
     const float* row = x + (static_cast<long long>(b) * tokens + t) * C;
     float s = 0.f;
     for (int c = lane; c < C; c += 32) s += row[c];
@@ -470,10 +473,15 @@ clap_ln_meanpool_kernel(const float* __restrict__ x, const float* __restrict__ g
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q / C + eps);
-    for (int c = lane; c < C; c += 32) atomicAdd(&acc[c], (row[c] - mean) * rstd * g[c] + bta[c]);
+    for (int c = lane; c < C; c += 32) mine[c] += (row[c] - mean) * rstd * g[c] + bta[c];  // channel c belongs to this lane
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) pooled[static_cast<long long>(b) * C + c] = __float2half_rn(acc[c] / tokens);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < CP_WARPS; ++w) t += acc[w * C + c];
+    pooled[static_cast<long long>(b) * C + c] = __float2half_rn(t / tokens);
+  }
 }
 
 // fp32 -> fp32 LayerNorm, one warp per row (the patch-embedding norm, whose output is the residual stream itself)
@@ -559,6 +567,7 @@ int clap_build(cc_clap* m, const cc_tensor* w, int nw) {
   CC_TRY(A.alloc_t(&m->mlp16, rows0 * 4 * C0));
   const int n_stages = 4;
   const int Cl = C0 << (n_stages - 1);
+  CC_REQUIRE(static_cast<size_t>(CP_WARPS) * Cl * sizeof(float) <= 48 * 1024, CC_ESHAPE, "clap: final width %d too large for the pool kernel", Cl);
   const size_t Bp = (static_cast<size_t>(B) + 31) / 32 * 32;  // GEMM epilogues write whole 32-row groups
   CC_TRY(A.alloc_t(&m->pool16, Bp * Cl));
   CC_TRY(A.alloc_t(&m->hid16, Bp * c.projection_dim));
@@ -910,7 +919,7 @@ int cc_clap_forward(cc_clap* m, const void* mel, int mel_dtype, const unsigned c
   }
   const cc_clap::Stage& last = m->stages.back();
   const int tok = last.res * last.res;
-  CC_CUDA(launch_pdl(clap_ln_meanpool_kernel, dim3(B), dim3(256), static_cast<size_t>(last.C) * sizeof(float), s,
+  CC_CUDA(launch_pdl(clap_ln_meanpool_kernel, dim3(B), dim3(CP_WARPS * 32), static_cast<size_t>(CP_WARPS) * last.C * sizeof(float), s,
                      static_cast<const float*>(m->x), m->norm_g, m->norm_b, m->pool16, tok, last.C, c.eps));
   CC_TRY(gemm_run(m->p_proj1, B, s));
   CC_TRY(gemm_run(m->p_proj2, B, s));
