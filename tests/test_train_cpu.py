@@ -8,6 +8,7 @@ from conftest import rel_err
 from golden_util import LM_CASES, load_train_case
 from oracle import ref_runner as RR
 from oracle import restate as R
+from oracle import synth
 
 TOL = 5e-5  # fp32 re-association between the restatement's autograd graph and the reference's
 
@@ -72,3 +73,26 @@ def test_schedule_matches_transformers():
     for _ in range(45):
         assert abs(sa.get_last_lr()[0] - sb.get_last_lr()[0]) < 1e-12
         a.step(); b.step(); sa.step(); sb.step()
+
+
+@pytest.mark.skipif(not RR.available(), reason="needs /root/reference (build container only)")
+@pytest.mark.parametrize("use_pos", [True, False])
+def test_windowed_mapper_training_restatement_vs_live_reference(use_pos):
+    """SURVEY §8f rank 3, not built on the GPU yet: training_step + backward with TransformerMapperWindowed
+    (clipcap/model/mapper.py:133-160) — the oracle side of that row, pinned against the reference itself."""
+    gcfg = R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64)
+    mcfg = R.MapperCfg(kind="windowed", E=64, d=128, P=3, K=5, H=2, L=2, W=3, use_pos=use_pos)
+    map_w, lm_w = synth.mapper_weights(mcfg, seed=61), synth.gpt2_weights(gcfg, seed=62, wte_std=0.1)
+    model = RR.build_reference_model("tiny:128:2:2:1003:64", 64, 5, 3, 2, 2, map_w, lm_w, windowed=True, window_size=2,
+                                     use_pos=use_pos)
+    emb = synth.embeddings(9, 64, seed=63).view(3, 3, 64)
+    g = torch.Generator().manual_seed(64)
+    tokens = torch.randint(1, gcfg.V, (3, 9), generator=g)
+    tokens[1, 6:] = -1
+    tokens[2, 2:] = -1
+    ref_loss, ref_grads = RR.reference_training_step(model, tokens, emb)
+    loss, grads = R.training_loss_and_grads(map_w, lm_w, mcfg, gcfg, tokens, emb)
+    assert abs(loss - ref_loss) < TOL * abs(ref_loss)
+    assert set(grads) == set(ref_grads)
+    for k in grads:
+        assert rel_err(grads[k], ref_grads[k]) < TOL, k
