@@ -1,7 +1,9 @@
 """Per-stage error of the CLAP CUDA path against the oracle + a timing of the full tower (development aid)."""
-import sys, time
-sys.path.insert(0, ".")
-sys.path.insert(0, "tests")
+import os
+import sys
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import torch
 from oracle import restate_clap as RC
 from test_clap_gpu import _weights, _oracle_stages, _engine

@@ -1,7 +1,9 @@
 """Two forwards of the CLAP tower at 128 clips (the second with one fused sample) for an ncu launch list."""
+import os
 import sys
-sys.path.insert(0, ".")
-sys.path.insert(0, "tests")
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, "tests"))
 import torch
 from oracle import restate_clap as RC
 from test_clap_gpu import _weights, _engine

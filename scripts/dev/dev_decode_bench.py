@@ -1,7 +1,7 @@
 """Developer timing of the decode-path kernels at the benchmark shape (GPU box only): rotates over 24 layers' worth of
 weights / KV cache so every launch streams from HBM like the real step."""
 import ctypes as C, sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from clipcap_b200 import _ffi
 

@@ -1,5 +1,5 @@
 import ctypes as C, sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from clipcap_b200 import _ffi
 h = C.CDLL(_ffi.LIB_PATH)

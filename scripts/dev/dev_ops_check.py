@@ -1,6 +1,6 @@
 """Developer smoke check of the kernel-level hooks against torch (GPU box only)."""
 import ctypes as C, sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from clipcap_b200 import _ffi
 
