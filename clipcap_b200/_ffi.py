@@ -87,8 +87,16 @@ PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {
     "cc_gpt2_logits": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "cc_gpt2_embed": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
     "cc_generate": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(cc_gen_cfg), _vp, _vp, _vp, _vp]),
+    "cc_generate_prefill": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(cc_gen_cfg), _vp]),
+    "cc_generate_decode": (_i, [_vp, _i, _i, C.POINTER(cc_gen_cfg), _vp, _vp, _vp, _vp]),
     "cc_gpt2_last_launches": (_i, [_vp]),
     "cc_gpt2_destroy": (None, [_vp]),
+    "cc_partition_create": (_i, [_pp, _i, _i]),
+    "cc_partition_stream": (_vp, [_vp, _i]),
+    "cc_partition_sms": (_i, [_vp, _i]),
+    "cc_partition_destroy": (None, [_vp]),
+    "cc_set_sm_budget": (None, [_i]),
+    "cc_get_sm_budget": (_i, []),
     "cc_prof_enable": (None, [_i]),
     "cc_prof_read": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "cc_op_gemm": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),

@@ -10,6 +10,10 @@ const char* cc_last_error(void) { return cc::get_error(); }
 
 const char* cc_version(void) { return "clipcap_b200 0.1.0 sm_100a"; }
 
+void cc_set_sm_budget(int n_sms) { cc::set_sm_budget(n_sms); }
+
+int cc_get_sm_budget(void) { return cc::sm_budget(); }
+
 void cc_prof_enable(int on) { cc::gemm_prof_enable(on != 0); }
 
 void cc_prof_read(double* ms, double* flops, long long* n) {

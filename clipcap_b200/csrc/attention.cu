@@ -226,11 +226,7 @@ template <int HD, bool CAUSAL>
 int launch_attn(const __half* q, const __half* k, const __half* v, int64_t ld, __half* o, int64_t ldo, int B, int S,
                 int H, float scale, cudaStream_t s) {
   auto kern = attn_fwd_kernel<HD, CAUSAL>;
-  static bool configured = false;
-  if (!configured) {
-    CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<HD>::kBytes));
-    configured = true;
-  }
+  CC_OPT_IN_SMEM(kern, AttnSmem<HD>::kBytes);
   const int tiles = (S + 15) / 16;
   const int nblk = (tiles + 7) / 8;
   const int nw = (tiles + nblk - 1) / nblk;
@@ -778,11 +774,7 @@ int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, cons
       return e != nullptr && e[0] == '1';
     }();
     if (!off) {
-      static bool configured = false;
-      if (!configured) {
-        CC_CUDA(cudaFuncSetAttribute(decode_attn_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        configured = true;
-      }
+      CC_OPT_IN_SMEM(decode_attn_beam_kernel, 64 * 1024);
       CC_CUDA(launch_pdl(decode_attn_beam_kernel, dim3((nseq / beam) * H), dim3(beam * 32),
                          static_cast<size_t>(shared_len) * 256, s, qkv, kcache, vcache, anc, o, beam, H, t_max, pos,
                          shared_len, scale * 1.4426950408889634f));
@@ -792,11 +784,7 @@ int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, cons
   // bulk-copy variant: no ancestry indirection, cache rows 16-byte aligned, staging fits beside two other CTAs
   const size_t bulk_smem = static_cast<size_t>(DEC_WARPS) * 2 * pos * 128;  // the pos cached rows of K and V per warp
   if (anc == nullptr && bulk_smem <= 72 * 1024) {
-    static bool configured = false;
-    if (!configured) {
-      CC_CUDA(cudaFuncSetAttribute(decode_attn_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-      configured = true;
-    }
+    CC_OPT_IN_SMEM(decode_attn_bulk_kernel, 72 * 1024);
     CC_CUDA(launch_pdl(decode_attn_bulk_kernel, dim3(grid), dim3(DEC_WARPS * 32), bulk_smem, s, qkv, kcache, vcache, o,
                        nseq, H, t_max, pos, scale * 1.4426950408889634f));
     return CC_OK;

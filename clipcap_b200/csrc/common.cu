@@ -3,6 +3,7 @@
 
 #include "common.h"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstring>
 
@@ -85,15 +86,28 @@ int check_device_sm100() {
   return CC_OK;
 }
 
-int num_sms() {
-  static int n = 0;
+namespace {
+std::atomic<int> g_sm_budget{0};
+}
+
+void set_sm_budget(int n) { g_sm_budget.store(n > 0 ? n : 0); }
+int sm_budget() { return g_sm_budget.load(); }
+
+int device_sms() {  // per device: a process may drive several GPUs
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load();
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev].store(n);
   }
   return n;
+}
+
+int num_sms() {
+  const int n = device_sms(), b = g_sm_budget.load();
+  return (b > 0 && b < n) ? b : n;
 }
 
 int find_weight(const cc_tensor* w, int n, const std::string& name, int64_t expect_numel, Arena& arena,

@@ -5,8 +5,10 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -38,6 +40,20 @@ const char* get_error();
       cc::set_error(__VA_ARGS__);   \
       return (code);                \
     }                               \
+  } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device (per-context) property of a kernel: opt in once per
+// (call site, device) — a process may drive several GPUs through handles created on different devices.
+#define CC_OPT_IN_SMEM(kern, bytes)                                                                          \
+  do {                                                                                                       \
+    static std::atomic<unsigned long long> done__{0};                                                        \
+    int dev__ = 0;                                                                                           \
+    CC_CUDA(cudaGetDevice(&dev__));                                                                          \
+    const unsigned long long bit__ = 1ull << (dev__ & 63);                                                   \
+    if (!(done__.load() & bit__)) {                                                                          \
+      CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));             \
+      done__.fetch_or(bit__);                                                                                \
+    }                                                                                                        \
   } while (0)
 
 // ------------------------------------------------------------------ device memory owned by an engine handle
@@ -99,7 +115,12 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 
 int check_device_sm100();  // CC_EARCH unless the current device is compute capability 10.x
+// SMs a launch may count on: the device's SM count, or the caller's SM budget (cc_set_sm_budget) when the stream it
+// enqueues on belongs to an SM partition (green context) smaller than the device.
 int num_sms();
+int device_sms();
+void set_sm_budget(int n);  // 0 = whole device
+int sm_budget();
 
 // ------------------------------------------------------------------ weights lookup
 // Finds `name` among the caller's tensors, checks the element count, and returns a device fp32 pointer. Host pointers
@@ -154,6 +175,7 @@ int gemm_plan_heads(GemmPlan* p, const __half* a, int64_t lda, int max_images, i
                     const float* bias, __half* out);
 int gemm_plan_partial(GemmPlan* p, const __half* a, int64_t lda, int max_rows, const __half* w, int N, int K,
                       float* partial, int split_rows, int splits, int bn);
+constexpr int kMaxSplitK = 16;  // largest split-K factor gemm_pick_split returns
 void gemm_pick_split(int M, int N, int K, int* bn_out, int* splits_out);
 // row0: first row of A / out covered (a multiple of 32); lets independent row groups of one plan run on different streams.
 int gemm_run(const GemmPlan& p, int M, cudaStream_t s, int row0 = 0);
@@ -287,7 +309,7 @@ struct Stack {
     std::vector<GemmPlan> o, p2;
   };
   float* part = nullptr;  // fp32 partial sums, sized in plan() for the largest splits * split_rows over all block counts
-  std::vector<DecPlans> dec_plans;  // index = row blocks - 1
+  std::map<std::pair<int, int>, DecPlans> dec_plans;  // key = (row blocks, SM budget the plan was made for)
   int dec_plans_for(int blocks, DecPlans** out);
   // true when a decode step of nseq rows runs on the skinny kernels (<= 16 rows, no partial sums pending)
   bool skinny_step(int nseq, int row0) const;
@@ -308,6 +330,11 @@ struct Stack {
   // Last block of a causal prefill whose only consumer is the last position (the LM head of the first generated token):
   // K, V of every position still go to the cache, everything after the attention scores runs for row S-1 of each sequence.
   int layer_last_row(int l, int B, int S, KvCache* kv, int slot_stride, cudaStream_t s);
+  struct LastRowPlans {
+    GemmPlan o, p2;
+    int rows = 0;
+  };
+  std::map<std::pair<int, int>, LastRowPlans> last_row_plans;  // key = (layer, S): encoded on first use, never per call
 
   int init(Arena& arena, int d_, int dff_, int H_, int act_epi_, bool causal_, float eps_, int max_rows_,
            int dec_rows_ = 0);

@@ -11,12 +11,13 @@ namespace cc {
 namespace {
 
 
-__global__ void gen_reset_kernel(int32_t* stopped, int32_t* lengths, unsigned long long* keys, int n) {
+__global__ void gen_reset_kernel(int32_t* stopped, int32_t* lengths, unsigned long long* keys, float* scores, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     stopped[i] = 0;
     lengths[i] = 0;
     keys[i] = 0ull;
+    scores[i] = 0.f;  // greedy / sampling modes return zero scores (never a previous beam call's)
   }
 }
 
@@ -309,8 +310,8 @@ __global__ void beam_final_kernel(BeamState st, int cur, int beam, int entry_len
 
 }  // namespace
 
-int gen_reset_run(int32_t* stopped, int32_t* lengths, unsigned long long* keys, int n, cudaStream_t s) {
-  gen_reset_kernel<<<(n + 255) / 256, 256, 0, s>>>(stopped, lengths, keys, n);
+int gen_reset_run(int32_t* stopped, int32_t* lengths, unsigned long long* keys, float* scores, int n, cudaStream_t s) {
+  gen_reset_kernel<<<(n + 255) / 256, 256, 0, s>>>(stopped, lengths, keys, scores, n);
   CC_CUDA(cudaGetLastError());
   return CC_OK;
 }

@@ -17,7 +17,7 @@ struct BeamState {
   int32_t* anc[2];     // ping-pong [rows, t_max]: cache slot holding position t of this row's history
 };
 
-int gen_reset_run(int32_t* stopped, int32_t* lengths, unsigned long long* keys, int n, cudaStream_t s);
+int gen_reset_run(int32_t* stopped, int32_t* lengths, unsigned long long* keys, float* scores, int n, cudaStream_t s);
 int greedy_select_run(unsigned long long* keys, int32_t* tokens, int entry_len, int step, int32_t* stopped,
                       int32_t* lengths, int stop_token, int n, cudaStream_t s);
 int row_topk_run(const float* logits, int64_t ldl, int V, float inv_temp, int beam, const int32_t* stopped,

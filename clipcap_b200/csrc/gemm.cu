@@ -568,12 +568,8 @@ int encode_out_map(CUtensorMap* m, void* base, bool f32, uint64_t rows, uint64_t
 template <int BN, int EPI, int CG>
 int launch(const GemmPlan& p, int bn_idx, int M, cudaStream_t s, int row0) {
   using Cfg = GemmCfg<BN, CG>;
-  static bool configured = false;
   auto kern = gemm_tn_kernel<BN, EPI, CG>;
-  if (!configured) {
-    CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-    configured = true;
-  }
+  CC_OPT_IN_SMEM(kern, Cfg::kSmem);
   const int num_kb = (p.K + BK - 1) / BK;
   const int splits = (EPI == EPI_PARTIAL_F32) ? p.splits : 1;
   const int kb_per = (num_kb + splits - 1) / splits;
@@ -582,11 +578,14 @@ int launch(const GemmPlan& p, int bn_idx, int M, cudaStream_t s, int row0) {
   const int tiles = ((M + BM * CG - 1) / (BM * CG)) * ((p.N + BN - 1) / BN) * splits;
   int units = num_sms() / CG;  // persistent: one CTA (pair) per SM (pair)
   if (CG == 2) {
-    // not every SM pair can host a cluster (GPC shapes): size the persistent grid to what is co-resident
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
+    // not every SM pair can host a cluster (GPC shapes): size the persistent grid to what is co-resident (per device)
+    static std::atomic<int> cluster_cache[64];
+    int dev = 0;
+    CC_CUDA(cudaGetDevice(&dev));
+    int max_clusters = cluster_cache[dev & 63].load();
+    if (max_clusters <= 0) {
       cudaLaunchConfig_t qc = {};
-      qc.gridDim = dim3(num_sms());
+      qc.gridDim = dim3(device_sms());
       qc.blockDim = dim3(GEMM_THREADS);
       qc.dynamicSmemBytes = Cfg::kSmem;
       cudaLaunchAttribute qa[1];
@@ -597,9 +596,10 @@ int launch(const GemmPlan& p, int bn_idx, int M, cudaStream_t s, int row0) {
       qc.attrs = qa;
       qc.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) != cudaSuccess || n <= 0) n = num_sms() / 2;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) != cudaSuccess || n <= 0) n = device_sms() / 2;
       max_clusters = n;
-      if (getenv("CLIPCAP_B200_VERBOSE")) fprintf(stderr, "clipcap_b200: %d co-resident CTA pairs\n", n);
+      cluster_cache[dev & 63].store(n);
+      if (getenv("CLIPCAP_B200_VERBOSE")) fprintf(stderr, "clipcap_b200: %d co-resident CTA pairs on device %d\n", n, dev);
     }
     if (units > max_clusters) units = max_clusters;
   }
@@ -674,21 +674,37 @@ int gemm_pick_bn(int M, int N, int K) {
 }
 
 void gemm_pick_split(int M, int N, int K, int* bn_out, int* splits_out) {
-  const int sms = num_sms();
+  // The split factor fixes the order in which an output element's partial sums are added, i.e. the result's bits: it is
+  // chosen for the WHOLE device whatever SM budget the caller runs under, so a decode step gives bit-identical results
+  // inside an SM partition and outside. The tile width only decides how the work is spread and follows the budget.
   const int num_kb = (K + BK - 1) / BK;
   static const int cand[4] = {256, 128, 64, 32};
   double best_c = 1e30;
   *bn_out = 32;
   *splits_out = 1;
+  const int dev_sms = device_sms();
   for (int i = 0; i < 4; ++i) {
     const int bn = cand[i];
     if (bn > 32 && bn / 2 >= N) continue;
-    for (int sp = 1; sp <= 16 && sp * 2 <= num_kb; sp *= 2) {
-      const double c = gemm_cost(M, N, K, bn, sp, sms);
+    for (int sp = 1; sp <= kMaxSplitK && sp * 2 <= num_kb; sp *= 2) {
+      const double c = gemm_cost(M, N, K, bn, sp, dev_sms);
       if (c < best_c) {
         best_c = c;
         *bn_out = bn;
         *splits_out = sp;
+      }
+    }
+  }
+  const int sms = num_sms();
+  if (sms != dev_sms) {
+    best_c = 1e30;
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cand[i];
+      if (bn > 32 && bn / 2 >= N) continue;
+      const double c = gemm_cost(M, N, K, bn, *splits_out, sms);
+      if (c < best_c) {
+        best_c = c;
+        *bn_out = bn;
       }
     }
   }

@@ -36,6 +36,8 @@ struct cc_gpt2 {
   cc::BeamState beam{};
   int max_entry = 0;
   cc::GemmPlan p_head_keys, p_head_logits;
+  cc::GemmPlan p_logits_out;           // cc_gpt2_logits: head writing into the caller's buffer `logits_plan_out`
+  const float* logits_plan_out = nullptr;
   cudaStream_t cap_stream = nullptr;
   // Greedy decode can run as independent row groups on parallel streams (parallel branches of the captured graph).
   // Measured on B200 at B=256 it loses (1 group 31.9 ms, 2 groups 36.2 ms, 4 groups 45.5 ms per generate call: the
@@ -45,13 +47,22 @@ struct cc_gpt2 {
   int decode_groups = 1;
   cudaStream_t grp_stream[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
-  using Key = std::tuple<int, int, int, int, int, int, uint32_t>;
-  std::map<Key, cudaGraphExec_t> graphs;
+  // (mode, B, Tp, beam, entry_length, stop_token, temperature bits, SM budget, capture stream, phase)
+  using Key = std::tuple<int, int, int, int, int, int, uint32_t, int, uintptr_t, int>;
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long last_use = 0;
+    int launches = 0;  // kernels inside the graph
+  };
+  std::map<Key, GraphEntry> graphs;  // bounded: least recently used entry evicted beyond kMaxGraphs
+  static constexpr size_t kMaxGraphs = 16;
+  unsigned long long use_clock = 0;
   bool use_graphs = true;
   int launches = 0;
+  int phase_launches = 0;  // kernels of the last prefill phase (cc_generate_prefill), added to the decode phase's count
 
   ~cc_gpt2() {
-    for (auto& kv_ : graphs) cudaGraphExecDestroy(kv_.second);
+    for (auto& kv_ : graphs) cudaGraphExecDestroy(kv_.second.exec);
     if (cap_stream) cudaStreamDestroy(cap_stream);
     for (int i = 0; i < kMaxGroups; ++i) {
       if (grp_stream[i]) cudaStreamDestroy(grp_stream[i]);
@@ -193,7 +204,9 @@ inline int nseq_of(int B, int beam) { return B * beam; }
 
 // Everything of one generate call after the prefix rows have been written into st.h; results land in g_tokens /
 // g_lengths / g_scores. Safe to capture into a graph: touches only handle-owned memory.
-int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_t s) {
+enum GenPhase { PHASE_ALL = 0, PHASE_PREFILL = 1, PHASE_DECODE = 2 };
+
+int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_t s, int phase = PHASE_ALL) {
   const cc_gpt2_cfg& c = m->cfg;
   const int d = c.d, EL = g.entry_length;
   const bool is_beam = g.mode == CC_GEN_BEAM;
@@ -212,8 +225,10 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
   const float inv_temp = 1.0f / (g.temperature > 0.f ? g.temperature : 1.0f);
   Stack& st = m->st;
   st.launches = 0;
+  st.pend_splits = 0;
   int extra = 0;
-
+  int cur = 0;  // ping-pong index of the beam token / ancestry tables
+  if (phase != PHASE_DECODE) {
   // ---- prefill: all Tp prefix positions at once; K,V go to slot img*beam
   // The first token needs only the last prefix position of the last block (LM head on row Tp-1): that block runs its
   // out-proj / MLP for those B rows alone (K, V of every position still go to the cache).
@@ -228,12 +243,12 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
                        m->lnf16, d, B, d, c.eps, s));
   extra += 1;
   if (is_sample) {
-    CC_TRY(gen_reset_run(m->g_stopped, m->g_lengths, m->keys, B, s));
+    CC_TRY(gen_reset_run(m->g_stopped, m->g_lengths, m->keys, m->g_scores, B, s));
     CC_TRY(gemm_run(m->p_head_logits, B, s));
     CC_TRY(sample_step(0));
     extra += 3;
   } else if (!is_beam) {
-    CC_TRY(gen_reset_run(m->g_stopped, m->g_lengths, m->keys, B, s));
+    CC_TRY(gen_reset_run(m->g_stopped, m->g_lengths, m->keys, m->g_scores, B, s));
     CC_TRY(gemm_run(m->p_head_keys, B, s));
     CC_TRY(greedy_select_run(m->keys, m->g_tokens, EL, 0, m->g_stopped, m->g_lengths, g.stop_token, B, s));
     extra += 3;
@@ -243,7 +258,11 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
     CC_TRY(beam_init_run(m->cand_val, m->cand_idx, m->beam, beam, EL, m->t_max, Tp, g.stop_token, B, s));
     extra += 3;
   }
-  int cur = 0;  // ping-pong index of the beam token / ancestry tables
+  }  // prefill phase
+  if (phase == PHASE_PREFILL) {
+    m->launches = st.launches + extra;
+    return CC_OK;
+  }
   if (is_sample) {
     for (int step = 1; step < EL; ++step) {
       const int pos = Tp + step - 1;
@@ -346,18 +365,19 @@ int cc_gpt2_logits(cc_gpt2* m, const void* embeds, int dtype, int B, int T, int 
   Stack& st = m->st;
   CC_TRY(gpt2_embed_prefix_run(embeds, dtype, m->wpe32, st.h, B, T, d, 0, s));
   for (int l = 0; l < c.L; ++l) CC_TRY(st.layer_full(l, B, T, nullptr, 0, s));
-  GemmPlan p;
-  if (all_positions) {
-    CC_TRY(layernorm_run(st.h, d, m->lnf_g, m->lnf_b, m->lnf16, d, B * T, d, c.eps, s));
-    CC_TRY(gemm_plan(&p, m->lnf16, d, B * T, m->wte16, c.V, d, EPI_F32, nullptr, logits, c.V));
-    CC_TRY(gemm_run(p, B * T, s));
-  } else {
-    CC_TRY(layernorm_run(st.h + static_cast<size_t>(T - 1) * d, static_cast<int64_t>(T) * d, m->lnf_g, m->lnf_b,
-                         m->lnf16, d, B, d, c.eps, s));
-    CC_TRY(gemm_plan(&p, m->lnf16, d, B, m->wte16, c.V, d, EPI_F32, nullptr, logits, c.V));
-    CC_TRY(gemm_run(p, B, s));
+  // The head writes straight into the caller's buffer: its plan is encoded once per output pointer and reused while the
+  // caller keeps handing in the same buffer (the tensor map itself does not depend on the row count).
+  const int rows = all_positions ? B * T : B;
+  if (m->logits_plan_out != logits) {
+    CC_TRY(gemm_plan(&m->p_logits_out, m->lnf16, d, m->max_rows, m->wte16, c.V, d, EPI_F32, nullptr, logits, c.V));
+    m->logits_plan_out = logits;
   }
-  return CC_OK;
+  if (all_positions)
+    CC_TRY(layernorm_run(st.h, d, m->lnf_g, m->lnf_b, m->lnf16, d, rows, d, c.eps, s));
+  else
+    CC_TRY(layernorm_run(st.h + static_cast<size_t>(T - 1) * d, static_cast<int64_t>(T) * d, m->lnf_g, m->lnf_b,
+                         m->lnf16, d, rows, d, c.eps, s));
+  return gemm_run(m->p_logits_out, rows, s);
 }
 
 int cc_gpt2_embed(cc_gpt2* m, const int32_t* ids, int n, void* out, int out_dtype, void* stream) {
@@ -366,11 +386,10 @@ int cc_gpt2_embed(cc_gpt2* m, const int32_t* ids, int n, void* out, int out_dtyp
   return gather_rows_run(ids, m->wte32, out, out_dtype, n, m->cfg.d, m->cfg.V, static_cast<cudaStream_t>(stream));
 }
 
-int cc_generate(cc_gpt2* m, const void* prefix, int dtype, int B, int Tp, const cc_gen_cfg* g, int32_t* tokens,
-                int32_t* lengths, float* scores, void* stream) {
-  using namespace cc;
-  CC_REQUIRE(m != nullptr && prefix != nullptr && g != nullptr && tokens != nullptr && lengths != nullptr, CC_EINVAL,
-             "cc_generate: null argument");
+namespace cc {
+namespace {
+
+int validate_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg* g) {
   CC_REQUIRE(g->mode >= CC_GEN_GREEDY && g->mode <= CC_GEN_SAMPLE, CC_EINVAL, "cc_generate: mode %d", g->mode);
   const bool sampling = g->mode == CC_GEN_NUCLEUS || g->mode == CC_GEN_SAMPLE;
   if (sampling) {
@@ -387,12 +406,74 @@ int cc_generate(cc_gpt2* m, const void* prefix, int dtype, int B, int Tp, const 
   CC_REQUIRE(Tp > 0 && Tp + g->entry_length - 1 <= m->max_len, CC_ESHAPE,
              "cc_generate: prefix %d + %d generated positions exceed max_len %d", Tp, g->entry_length - 1, m->max_len);
   CC_REQUIRE(beam <= m->cfg.V, CC_ESHAPE, "cc_generate: beam %d > vocabulary %d", beam, m->cfg.V);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int d = m->cfg.d, EL = g->entry_length;
+  return CC_OK;
+}
 
+// Runs one phase of a generate call on stream s: replayed from the handle's graph cache (greedy / beam) or enqueued
+// directly (sampling calls carry many free parameters and are not cached).
+int run_phase(cc_gpt2* m, int B, int Tp, const cc_gen_cfg* g, cudaStream_t s, int phase) {
+  const bool sampling = g->mode == CC_GEN_NUCLEUS || g->mode == CC_GEN_SAMPLE;
+  const int beam = g->mode == CC_GEN_BEAM ? g->beam : 1;
+  const int EL = g->entry_length;
+  if (!m->use_graphs || sampling) {
+    const int before = phase == PHASE_DECODE ? m->launches : 0;
+    CC_TRY(enqueue_generate(m, B, Tp, *g, s, phase));
+    m->launches += before;
+    return CC_OK;
+  }
+  uint32_t tbits;
+  const float temp = g->temperature > 0.f ? g->temperature : 1.0f;
+  memcpy(&tbits, &temp, 4);
+  // Kernel nodes run in the context of the stream they were captured on. A caller inside an SM partition (a green
+  // context stream, cc_set_sm_budget) must get nodes bound to ITS partition, so the capture happens on the caller's own
+  // stream and the graph is cached per (SM budget, stream); the legacy default stream cannot capture and uses the
+  // handle's private stream (whole device).
+  const bool own = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread && sm_budget() > 0;
+  cudaStream_t cs = own ? s : m->cap_stream;
+  const cc_gpt2::Key key{g->mode, B, Tp, beam, EL, g->stop_token, tbits, sm_budget(),
+                         own ? reinterpret_cast<uintptr_t>(s) : 0, phase};
+  auto it = m->graphs.find(key);
+  if (it == m->graphs.end()) {
+    if (m->graphs.size() >= cc_gpt2::kMaxGraphs) {  // evict the least recently used graph (ragged batches, prompt lengths ...)
+      auto victim = m->graphs.begin();
+      for (auto jt = m->graphs.begin(); jt != m->graphs.end(); ++jt)
+        if (jt->second.last_use < victim->second.last_use) victim = jt;
+      CC_CUDA(cudaStreamSynchronize(s));  // an evicted graph may still be running on this stream
+      cudaGraphExecDestroy(victim->second.exec);
+      m->graphs.erase(victim);
+    }
+    cudaGraph_t graph = nullptr;
+    CC_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    const int st = enqueue_generate(m, B, Tp, *g, cs, phase);
+    const cudaError_t e = cudaStreamEndCapture(cs, &graph);
+    if (st != CC_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+      return st;
+    }
+    CC_REQUIRE(e == cudaSuccess && graph != nullptr, CC_ECUDA, "cc_generate: graph capture failed: %s",
+               cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CC_REQUIRE(e2 == cudaSuccess, CC_ECUDA, "cc_generate: graph instantiate failed: %s", cudaGetErrorString(e2));
+    cc_gpt2::GraphEntry ent;
+    ent.exec = exec;
+    ent.launches = m->launches;
+    it = m->graphs.emplace(key, ent).first;
+  }
+  it->second.last_use = ++m->use_clock;
+  CC_CUDA(cudaGraphLaunch(it->second.exec, s));
+  m->launches = (phase == PHASE_DECODE ? m->phase_launches : 0) + it->second.launches;
+  if (phase == PHASE_PREFILL) m->phase_launches = it->second.launches;
+  return CC_OK;
+}
+
+int generate_prefill(cc_gpt2* m, const void* prefix, int dtype, int B, int Tp, const cc_gen_cfg* g, cudaStream_t s,
+                     int phase) {
+  const bool sampling = g->mode == CC_GEN_NUCLEUS || g->mode == CC_GEN_SAMPLE;
   // h = inputs_embeds + wpe[0..Tp-1]   (modeling_gpt2.py:579-585); reads the caller's buffer, so it stays outside the graph
-  CC_TRY(gpt2_embed_prefix_run(prefix, dtype, m->wpe32, m->st.h, B, Tp, d, 0, s));
-
+  CC_TRY(gpt2_embed_prefix_run(prefix, dtype, m->wpe32, m->st.h, B, Tp, m->cfg.d, 0, s));
   if (sampling) {
     // per-call inputs of the sampling kernel live in handle-owned device memory
     const unsigned long long seed = g->seed;
@@ -400,39 +481,47 @@ int cc_generate(cc_gpt2* m, const void* prefix, int dtype, int B, int Tp, const 
     if (g->n_history > 0)
       CC_CUDA(cudaMemcpyAsync(m->d_history, g->history, sizeof(int32_t) * g->n_history, cudaMemcpyHostToDevice, s));
   }
-  if (!m->use_graphs || sampling) {  // sampling calls carry many free parameters: enqueued directly, not cached as graphs
-    CC_TRY(enqueue_generate(m, B, Tp, *g, s));
-  } else {
-    uint32_t tbits;
-    const float temp = g->temperature > 0.f ? g->temperature : 1.0f;
-    memcpy(&tbits, &temp, 4);
-    const cc_gpt2::Key key{g->mode, B, Tp, beam, EL, g->stop_token, tbits};
-    auto it = m->graphs.find(key);
-    if (it == m->graphs.end()) {
-      cudaGraph_t graph = nullptr;
-      CC_CUDA(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-      const int st = enqueue_generate(m, B, Tp, *g, m->cap_stream);
-      const cudaError_t e = cudaStreamEndCapture(m->cap_stream, &graph);
-      if (st != CC_OK) {
-        if (graph) cudaGraphDestroy(graph);
-        (void)cudaGetLastError();
-        return st;
-      }
-      CC_REQUIRE(e == cudaSuccess && graph != nullptr, CC_ECUDA, "cc_generate: graph capture failed: %s",
-                 cudaGetErrorString(e));
-      cudaGraphExec_t exec = nullptr;
-      const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
-      cudaGraphDestroy(graph);
-      CC_REQUIRE(e2 == cudaSuccess, CC_ECUDA, "cc_generate: graph instantiate failed: %s", cudaGetErrorString(e2));
-      it = m->graphs.emplace(key, exec).first;
-    }
-    CC_CUDA(cudaGraphLaunch(it->second, s));
-  }
+  return run_phase(m, B, Tp, g, s, phase);
+}
+
+int generate_results(cc_gpt2* m, int B, int EL, int32_t* tokens, int32_t* lengths, float* scores, cudaStream_t s) {
   CC_CUDA(cudaMemcpyAsync(tokens, m->g_tokens, static_cast<size_t>(B) * EL * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
   CC_CUDA(cudaMemcpyAsync(lengths, m->g_lengths, static_cast<size_t>(B) * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
   if (scores != nullptr)
     CC_CUDA(cudaMemcpyAsync(scores, m->g_scores, static_cast<size_t>(B) * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return CC_OK;
+}
+
+}  // namespace
+}  // namespace cc
+
+int cc_generate(cc_gpt2* m, const void* prefix, int dtype, int B, int Tp, const cc_gen_cfg* g, int32_t* tokens,
+                int32_t* lengths, float* scores, void* stream) {
+  using namespace cc;
+  CC_REQUIRE(m != nullptr && prefix != nullptr && g != nullptr && tokens != nullptr && lengths != nullptr, CC_EINVAL,
+             "cc_generate: null argument");
+  CC_TRY(validate_generate(m, B, Tp, g));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CC_TRY(generate_prefill(m, prefix, dtype, B, Tp, g, s, PHASE_ALL));
+  return generate_results(m, B, g->entry_length, tokens, lengths, scores, s);
+}
+
+int cc_generate_prefill(cc_gpt2* m, const void* prefix, int dtype, int B, int Tp, const cc_gen_cfg* g, void* stream) {
+  using namespace cc;
+  CC_REQUIRE(m != nullptr && prefix != nullptr && g != nullptr, CC_EINVAL, "cc_generate_prefill: null argument");
+  CC_TRY(validate_generate(m, B, Tp, g));
+  return generate_prefill(m, prefix, dtype, B, Tp, g, static_cast<cudaStream_t>(stream), PHASE_PREFILL);
+}
+
+int cc_generate_decode(cc_gpt2* m, int B, int Tp, const cc_gen_cfg* g, int32_t* tokens, int32_t* lengths, float* scores,
+                       void* stream) {
+  using namespace cc;
+  CC_REQUIRE(m != nullptr && g != nullptr && tokens != nullptr && lengths != nullptr, CC_EINVAL,
+             "cc_generate_decode: null argument");
+  CC_TRY(validate_generate(m, B, Tp, g));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CC_TRY(run_phase(m, B, Tp, g, s, PHASE_DECODE));
+  return generate_results(m, B, g->entry_length, tokens, lengths, scores, s);
 }
 
 int cc_gpt2_last_launches(cc_gpt2* m) { return m ? m->launches : 0; }

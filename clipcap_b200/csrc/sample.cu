@@ -268,11 +268,7 @@ int sample_run(const float* logits, int64_t ldl, int V, int mode, float inv_temp
              "sampling: history of %d + %d tokens exceeds %d", n_prefix, entry_len, SMP_MAX_HISTORY);
   SampleArgs a{logits, static_cast<long long>(ldl), V, mode, inv_temp, top_p, top_k, rep_penalty, len_penalty_scale,
                stop_token, prefix_hist, n_prefix, tokens, entry_len, step, stopped, lengths, seed};
-  static bool configured = false;
-  if (!configured) {
-    CC_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    configured = true;
-  }
+  CC_OPT_IN_SMEM(sample_kernel, 220 * 1024);
   sample_kernel<<<rows, SMP_THREADS, smem, s>>>(a);
   CC_CUDA(cudaGetLastError());
   return CC_OK;

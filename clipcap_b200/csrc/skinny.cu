@@ -247,11 +247,7 @@ int sk_launch(const SkArgs& a, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(ROWS16 ? 16 : 8) * (a.K + SK_PAD) * 2 + static_cast<size_t>(SK_WARPS) * 16 * COLS * 4;
   CC_REQUIRE(smem <= 227 * 1024, CC_ESHAPE, "skinny gemm: K=%d needs %zu bytes of shared memory", a.K, smem);
   auto kern = skinny_gemm_kernel<NT, EPI, ROWS16>;
-  static bool configured = false;
-  if (!configured) {
-    CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  CC_OPT_IN_SMEM(kern, 227 * 1024);
   const int n_tiles = (a.N + COLS - 1) / COLS;
   int per_sm = static_cast<int>(std::min<size_t>(4, (200 * 1024) / smem));
   if (EPI == EPI_ARGMAX) per_sm = std::min(per_sm, 2);  // every CTA ends with one atomicMax per row on the same few words

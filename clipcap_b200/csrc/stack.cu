@@ -74,18 +74,11 @@ int Stack::plan() {
     cls_last_S = 0;
   }
   if (dec_rows > 0) {
+    // `part` holds the split-K partial sums of one projection: sized for the largest split factor the planner may choose
+    // (16) so that plans made later for another row-block count or SM budget always fit. Allocated once per stack.
     const int max_blocks = dec_rows_pad / 128;
-    size_t need = 0;
-    for (int nb = 1; nb <= max_blocks; ++nb) {
-      int bn_o, sp_o, bn_2, sp_2;
-      gemm_pick_split(nb * 128, d, d, &bn_o, &sp_o);
-      gemm_pick_split(nb * 128, d, dff, &bn_2, &sp_2);
-      const size_t n = static_cast<size_t>(sp_o > sp_2 ? sp_o : sp_2) * nb * 128 * d;
-      if (n > need) need = n;
-    }
-    // `part` is allocated once per stack; plan() runs once after the layers are filled
-    if (part == nullptr) CC_TRY(arena_->alloc_t(&part, need));
-    dec_plans.assign(max_blocks, DecPlans{});
+    if (part == nullptr) CC_TRY(arena_->alloc_t(&part, static_cast<size_t>(kMaxSplitK) * dec_rows_pad * d));
+    dec_plans.clear();
     DecPlans* unused = nullptr;
     CC_TRY(dec_plans_for(max_blocks, &unused));  // the capacity plans exist from the start; smaller steps add theirs
   }
@@ -93,15 +86,17 @@ int Stack::plan() {
 }
 
 int Stack::dec_plans_for(int blocks, DecPlans** out) {
-  CC_REQUIRE(blocks >= 1 && blocks <= static_cast<int>(dec_plans.size()), CC_ESHAPE, "stack: %d decode row blocks (max %zu)",
-             blocks, dec_plans.size());
-  DecPlans& dp = dec_plans[blocks - 1];
+  CC_REQUIRE(blocks >= 1 && blocks <= dec_rows_pad / 128, CC_ESHAPE, "stack: %d decode row blocks (max %d)", blocks,
+             dec_rows_pad / 128);
+  DecPlans& dp = dec_plans[std::make_pair(blocks, num_sms())];  // tile shapes / split factors depend on the SM budget
   if (dp.o.empty()) {
     const size_t L = layers.size();
     const int rows = blocks * 128;
     int bn_o, sp_o, bn_2, sp_2;
     gemm_pick_split(rows, d, d, &bn_o, &sp_o);
     gemm_pick_split(rows, d, dff, &bn_2, &sp_2);
+    CC_REQUIRE(sp_o <= kMaxSplitK && sp_2 <= kMaxSplitK, CC_EINVAL, "stack: split-K factor %d / %d exceeds %d", sp_o, sp_2,
+               kMaxSplitK);
     std::vector<GemmPlan> po(L), p2(L);
     const int plan_rows = rows < dec_rows ? rows : dec_rows;
     for (size_t l = 0; l < L; ++l) {
@@ -195,13 +190,18 @@ int Stack::layer_last_row(int l, int B, int S, KvCache* kv, int slot_stride, cud
   CC_TRY(cls_attention_run(qkv16, static_cast<long long>(S) * 3 * d, d, 64, 3LL * d, att16, d, B, S, H, scale, s, S - 1));
   float* hl = h + static_cast<size_t>(S - 1) * d;  // row S-1 of every sequence, S rows apart
   const int64_t ld = static_cast<int64_t>(S) * d;
-  GemmPlan po, p2;
-  CC_TRY(gemm_plan(&po, att16, d, B, w.wo, d, d, EPI_RESID_F32, w.bo, hl, ld));
-  CC_TRY(gemm_run(po, B, s));
+  // The two residual GEMMs write rows S apart: their tensor maps depend on S and are encoded once per (layer, S)
+  LastRowPlans& lp = last_row_plans[std::make_pair(l, S)];
+  if (lp.rows == 0) {
+    const int nb = max_rows / S;
+    CC_TRY(gemm_plan(&lp.o, att16, d, nb, w.wo, d, d, EPI_RESID_F32, w.bo, hl, ld));
+    CC_TRY(gemm_plan(&lp.p2, mlp16, dff, nb, w.w2, d, dff, EPI_RESID_F32, w.b2, hl, ld));
+    lp.rows = nb;
+  }
+  CC_TRY(gemm_run(lp.o, B, s));
   CC_TRY(layernorm_run(hl, ld, w.ln2_g, w.ln2_b, ln16, d, B, d, eps, s));
   CC_TRY(gemm_run(p_1[l], B, s));
-  CC_TRY(gemm_plan(&p2, mlp16, dff, B, w.w2, d, dff, EPI_RESID_F32, w.b2, hl, ld));
-  CC_TRY(gemm_run(p2, B, s));
+  CC_TRY(gemm_run(lp.p2, B, s));
   launches += kv != nullptr ? 8 : 7;
   return CC_OK;
 }
@@ -228,7 +228,7 @@ int Stack::layer_decode(int l, int nseq, KvCache* kv, const int32_t* anc, int po
     return CC_OK;
   }
   DecPlans* dp = nullptr;  // plans for this step's row-block count (row groups use the capacity plans: they share `part`)
-  CC_TRY(dec_plans_for(row0 == 0 ? (nseq + 127) / 128 : static_cast<int>(dec_plans.size()), &dp));
+  CC_TRY(dec_plans_for(row0 == 0 ? (nseq + 127) / 128 : dec_rows_pad / 128, &dp));
   const size_t cache_off = l * kv->layer_elems + static_cast<size_t>(row0) * H * kv->t_max * 64;  // slot == row
   CC_TRY(ln_decode(w.ln1_g, w.ln1_b, ln16, nseq, s, row0));  // absorbs the previous layer's fc2 partial sums
   CC_TRY(gemm_run(p_qkv[l], nseq, s, row0));

@@ -751,11 +751,7 @@ int launch_attn_bwd_mma(const __half* q, const __half* k, const __half* v, int64
   const size_t smem = 4 * static_cast<size_t>(spad) * (HD * 2 + 16) + 2 * static_cast<size_t>(spad) * (spad * 2 + 16);
   if (smem > 227 * 1024) return CC_ESHAPE;
   auto kern = attention_bwd_mma_kernel<HD, NTMAX>;
-  static bool configured = false;
-  if (!configured) {
-    CC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  CC_OPT_IN_SMEM(kern, 227 * 1024);
   kern<<<B * H, 256, smem, s>>>(q, k, v, ld, d_o, ldo, dq, dk, dv, ldd, S, H, causal ? 1 : 0, scale);
   CC_CUDA(cudaGetLastError());
   return CC_OK;

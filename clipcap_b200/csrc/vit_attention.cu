@@ -419,11 +419,7 @@ namespace {
 int va_launch(const __half* base, uint64_t rows, uint64_t cols, int64_t ld, VaArgs a, int B, int H, cudaStream_t s) {
   CC_REQUIRE((reinterpret_cast<uintptr_t>(a.o) & 15) == 0, CC_EALIGN, "vit attention: output not 16-byte aligned");
   CC_REQUIRE(H <= 65535 && B <= 65535, CC_ESHAPE, "vit attention: grid too large (H=%d B=%d)", H, B);
-  static bool configured = false;
-  if (!configured) {
-    CC_CUDA(cudaFuncSetAttribute(vit_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VA_SMEM));
-    configured = true;
-  }
+  CC_OPT_IN_SMEM(vit_attn_kernel, VA_SMEM);
   // Engines call this with the same buffer for every layer, so the last descriptor is cached.
   struct Cached {
     const __half* base = nullptr;

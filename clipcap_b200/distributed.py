@@ -56,16 +56,20 @@ def gather_tokens(tokens_local: torch.Tensor, lengths_local: torch.Tensor, group
 
 
 def caption_step(encode_fn, model, pixels_local: torch.Tensor, entry_length: int, stop_token: int,
-                 prefix_all: Optional[torch.Tensor] = None, group: Optional[dist.ProcessGroup] = None):
-    """One pass of the hot path on this rank's shard: ViT -> mapper -> prefix all-gather -> greedy decode of the local
-    rows. Returns (tokens, lengths, prefix_all). Decode reads only this rank's own prefix, so the all-gather runs behind
-    it on the communicator's stream and is joined at the end of the step: a rank never idles waiting for a slower peer's
-    mapper before it may start decoding."""
-    from clipcap_b200.inference.base import generate_greedy_tokens
+                 prefix_all: Optional[torch.Tensor] = None, group: Optional[dist.ProcessGroup] = None,
+                 mode: str = "greedy", beam: int = 1):
+    """One pass of the hot path on this rank's shard: ViT -> mapper -> prefix all-gather -> greedy (or beam) decode of
+    the local rows. Returns (tokens, lengths, prefix_all). Decode reads only this rank's own prefix, so the all-gather
+    runs behind it on the communicator's stream and is joined at the end of the step: a rank never idles waiting for a
+    slower peer's mapper before it may start decoding."""
+    from clipcap_b200.inference.base import generate_beam_tokens, generate_greedy_tokens
     emb = encode_fn(pixels_local)
     prefix = model.transformer_mapper(emb)
     gathered, work = all_gather_prefix(prefix, group, prefix_all, async_op=True)
-    tokens, lengths, _ = generate_greedy_tokens(model, prefix, entry_length, stop_token)
+    if mode == "beam":
+        tokens, lengths, _ = generate_beam_tokens(model, prefix, None, beam, entry_length, 1.0, stop_token)
+    else:
+        tokens, lengths, _ = generate_greedy_tokens(model, prefix, entry_length, stop_token)
     if work is not None:
         work.wait()  # the caller's stream now sees the complete [world * B, K, d] tensor
     return tokens, lengths, gathered

@@ -70,13 +70,16 @@ class CLAPModel(nn.Module):
 
 
 def get_clap_encoder(normalize_embeddings: bool = False, device: str = "cuda",
-                     weights_path: Optional[str] = None) -> Tuple[Callable, Callable]:
+                     weights_path: Optional[str] = None, allow_random_init: bool = False) -> Tuple[Callable, Callable]:
     """clap.py:133-161. `weights_path` (or $CLIPCAP_B200_CLAP_WEIGHTS): a torch-saved ClapAudioModelWithProjection
-    state_dict; without it the tower keeps its random initialisation (no network here). The returned transform is the
-    identity on mel tensors."""
+    state_dict; without it the tower keeps its random initialisation (no network here) and warns unless
+    `allow_random_init` / $CLIPCAP_B200_ALLOW_RANDOM_INIT=1. The returned transform is the identity on mel tensors."""
     tower = ClapAudioTower()
     weights_path = weights_path or os.environ.get("CLIPCAP_B200_CLAP_WEIGHTS")
     if weights_path:
         tower.clap.load_state_dict(torch.load(weights_path, map_location="cpu"), strict=True)
+    else:
+        from clipcap_b200.encoders.clip import warn_random_init
+        warn_random_init("CLAP audio", "CLIPCAP_B200_CLAP_WEIGHTS", allow_random_init)
     model = CLAPModel(tower, normalize_embeddings=normalize_embeddings).eval().to(device)
     return model, (lambda mel: mel)

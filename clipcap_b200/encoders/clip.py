@@ -9,6 +9,7 @@ named parameters (`visual.*`) and runs libclipcap_b200's cc_vit_forward. The ref
 from __future__ import annotations
 
 import os
+import warnings
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -155,11 +156,24 @@ class TensorTransform:
         return (x - mean) / std
 
 
+def warn_random_init(what: str, env_var: str, allowed: bool) -> None:
+    """An encoder without pretrained weights produces meaningless embeddings: never let that pass silently."""
+    if allowed or os.environ.get("CLIPCAP_B200_ALLOW_RANDOM_INIT") == "1":
+        return
+    warnings.warn(f"clipcap_b200: no pretrained weights given for the {what} encoder (weights_path / ${env_var}); the "
+                  "tower is RANDOMLY INITIALISED and its embeddings are meaningless. Pass allow_random_init=True or set "
+                  "CLIPCAP_B200_ALLOW_RANDOM_INIT=1 if that is intended (benchmarks, tests).", RuntimeWarning,
+                  stacklevel=3)
+
+
 def get_clip_encoder(encoder_model_variant: str, window_size: Optional[int] = None, normalize_embeddings: bool = False,
                      use_windowed_embeddings: bool = False, window_overlap_percentage: float = 0.0,
-                     device: str = "cuda", weights_path: Optional[str] = None) -> Tuple[Callable, Callable]:
+                     device: str = "cuda", weights_path: Optional[str] = None,
+                     allow_random_init: bool = False) -> Tuple[Callable, Callable]:
     """clip.py:132-153. `weights_path` (or $CLIPCAP_B200_CLIP_WEIGHTS) = torch-saved state_dict with OpenAI `visual.*`
-    keys; without it the tower keeps its random initialisation (no network here)."""
+    keys. The reference always loads pretrained weights (`clip.load`); without a path the tower keeps its random
+    initialisation (no network here) and says so with a warning unless `allow_random_init` (benchmarks, tests) or
+    $CLIPCAP_B200_ALLOW_RANDOM_INIT=1 is set."""
     if encoder_model_variant not in CLIP_VARIANTS:
         raise ValueError(f"clipcap_b200 implements the CLIP ViT towers {sorted(CLIP_VARIANTS)}; "
                          f"got '{encoder_model_variant}'")
@@ -170,6 +184,8 @@ def get_clip_encoder(encoder_model_variant: str, window_size: Optional[int] = No
         sd = torch.load(weights_path, map_location="cpu")
         sd = {k: v.float() for k, v in sd.items() if k.startswith("visual.")}
         tower.load_state_dict(sd, strict=True)
+    else:
+        warn_random_init("CLIP " + encoder_model_variant, "CLIPCAP_B200_CLIP_WEIGHTS", allow_random_init)
     transform = TensorTransform(image_size)
     model = CLIPModel(tower, normalize_embeddings=normalize_embeddings, use_windowed_embeddings=use_windowed_embeddings)
     model = model.eval()

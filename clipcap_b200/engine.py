@@ -2,6 +2,7 @@
 libclipcap_b200.so on the caller's current CUDA stream. No fallbacks: a missing library or a non-sm_100 device raises."""
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import Dict, Iterable, Optional, Tuple
 
@@ -35,6 +36,33 @@ class _Handle:
             self.close()
         except Exception:
             pass
+
+
+class SmPartition(_Handle):
+    """cc_partition_* — the device's SMs split into a large partition (index 0: image tower, mapper, prefill) and a small
+    one (index 1: the decode loop), each with its own stream (CUDA green contexts). `with part.on(i):` makes partition i's
+    stream the current torch stream and sizes the kernels enqueued inside for its SM count (cc_set_sm_budget)."""
+    _destroy_name = "cc_partition_destroy"
+
+    def __init__(self, small_sms: int = 24, device="cuda"):
+        super().__init__()
+        self.device = torch.device(device)
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _ffi.check(_ffi.lib().cc_partition_create(C.byref(self._h), index, int(small_sms)))
+        lib = _ffi.lib()
+        self.sms = [lib.cc_partition_sms(self._h, i) for i in (0, 1)]
+        self.streams = [torch.cuda.ExternalStream(lib.cc_partition_stream(self._h, i), device=self.device) for i in (0, 1)]
+
+    @contextlib.contextmanager
+    def on(self, which: int):
+        lib = _ffi.lib()
+        before = lib.cc_get_sm_budget()
+        lib.cc_set_sm_budget(self.sms[which])
+        try:
+            with torch.cuda.stream(self.streams[which]):
+                yield self.streams[which]
+        finally:
+            lib.cc_set_sm_budget(before)
 
 
 class VitEngine(_Handle):
@@ -240,6 +268,40 @@ class Gpt2Engine(_Handle):
             _ffi.check(_ffi.lib().cc_generate(self._h, prefix.data_ptr(), _ffi.torch_dtype_code(prefix), B, Tp,
                                               C.byref(g), tokens.data_ptr(), lengths.data_ptr(), scores.data_ptr(),
                                               _ffi.current_stream_ptr()))
+        return tokens, lengths, scores
+
+    def _greedy_or_beam_cfg(self, mode, beam, entry_length, temperature, stop_token):
+        if mode not in ("greedy", "beam"):
+            raise ValueError("the two-phase generate supports the deterministic modes 'greedy' and 'beam'")
+        return _ffi.cc_gen_cfg(self._MODES[mode], beam, entry_length, float(temperature), stop_token, 1.0, 0, 1.0, 50, 1.0,
+                               0, None, 0)
+
+    def prefill(self, prefix: torch.Tensor, mode: str = "greedy", beam: int = 1, entry_length: int = 67,
+                temperature: float = 1.0, stop_token: int = 50256) -> Tuple[int, int]:
+        """cc_generate_prefill on the current stream: prefix -> KV cache + first token (handle state). Returns (B, Tp) to
+        hand to `decode`, which may run on another stream once it is ordered after this call."""
+        _require_cuda(prefix, "prefix embeddings")
+        if prefix.dim() != 3 or prefix.shape[2] != self.cfg.d:
+            raise ValueError(f"prefix must be [B, Tp, {self.cfg.d}], got {tuple(prefix.shape)}")
+        prefix = prefix.contiguous()
+        B, Tp, _ = prefix.shape
+        g = self._greedy_or_beam_cfg(mode, beam, entry_length, temperature, stop_token)
+        with torch.cuda.device(prefix.device):
+            _ffi.check(_ffi.lib().cc_generate_prefill(self._h, prefix.data_ptr(), _ffi.torch_dtype_code(prefix), B, Tp,
+                                                      C.byref(g), _ffi.current_stream_ptr()))
+        return B, Tp
+
+    def decode(self, B: int, Tp: int, mode: str = "greedy", beam: int = 1, entry_length: int = 67,
+               temperature: float = 1.0, stop_token: int = 50256):
+        """cc_generate_decode on the current stream: the remaining entry_length - 1 steps of the call `prefill` started.
+        -> (tokens, lengths, scores) as `generate`."""
+        g = self._greedy_or_beam_cfg(mode, beam, entry_length, temperature, stop_token)
+        tokens = torch.empty(B, entry_length, device=self.device, dtype=torch.int32)
+        lengths = torch.empty(B, device=self.device, dtype=torch.int32)
+        scores = torch.empty(B, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _ffi.check(_ffi.lib().cc_generate_decode(self._h, B, Tp, C.byref(g), tokens.data_ptr(), lengths.data_ptr(),
+                                                     scores.data_ptr(), _ffi.current_stream_ptr()))
         return tokens, lengths, scores
 
     @property

@@ -129,6 +129,20 @@ class GPT2LM(EngineModule):
             raise ValueError(f"sequence length {length} exceeds n_positions {self.n_positions}")
         return self._get_engine((max(8, seqs), min(self.n_positions, max(64, length))))
 
+    def decode_engines(self, n: int, seqs: int, length: int):
+        """n independent engines over the same weights (each with its own KV cache and workspaces): the serving pipeline
+        prefills batch i+1 in one while batch i still decodes in the other. Engine 0 is the module's own."""
+        first = self._engine_for(seqs, length)
+        key = (self._engine_key, self._engine_cap)
+        extra = getattr(self, "_extra_engines", None)
+        if extra is None or extra[0] != key or len(extra[1]) < n - 1:
+            if extra is not None:
+                for e in extra[1]:
+                    e.close()
+            built = [self._build_engine(self._engine_weights(), self._engine_cap, self._device()) for _ in range(n - 1)]
+            object.__setattr__(self, "_extra_engines", (key, built))
+        return [first] + list(self._extra_engines[1][:n - 1])
+
     @torch.no_grad()
     def forward(self, inputs_embeds: Optional[torch.Tensor] = None, attention_mask: Optional[torch.Tensor] = None,
                 input_ids: Optional[torch.Tensor] = None, **unused):

@@ -40,6 +40,9 @@ class FusedAdamW(Optimizer):
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 adamw_update(p.data, g, st["exp_avg"], st["exp_avg_sq"], group["lr"], b1, b2, group["eps"],
                              group["weight_decay"], st["step"])
+                # The update went through a raw pointer: tell autograd (and EngineModule._param_key, which keys the cached
+                # native engines on `_version`) that the parameter changed, as an in-place torch op would have.
+                torch.autograd.graph.increment_version(p)
         return loss
 
 

@@ -1,7 +1,16 @@
 """Host-side serving loop around the hot path: pinned host pixels (or, with `input_shape`, any encoder input such as the
-[4, 1001, 64] mel features of the CLAP tower) in, token ids in pinned host memory out, with the host->device copy of
-batch i+1 running on a copy stream while batch i is on the compute stream (double-buffered device staging). This is what `bench.py`'s end-to-end number measures; the reference moves one image at a time with a blocking
-`.to(device)` (docs/inference.md:22-27, preprocess/mapper.py:17).
+[4, 1001, 64] mel features of the CLAP tower) in, token ids in pinned host memory out. This is what `bench.py` measures;
+the reference moves one image at a time with a blocking `.to(device)` and decodes it before touching the next
+(docs/inference.md:22-27, inference/demo.py:30-45, preprocess/mapper.py:17).
+
+Two overlaps, both across consecutive batches:
+
+* the host->device copy of batch i+1 runs on a copy stream while batch i computes (double-buffered device staging);
+* with `partition_sms > 0` the GPU itself is split into two SM partitions (CUDA green contexts, engine.SmPartition): the
+  image tower + mapper + GPT-2 prefill of batch i+1 — tensor-bound, and power-bound on a B200 — run on the large partition
+  while the 19 decode steps of batch i — a chain of ~3200 dependent launches that leaves most of the machine idle — run
+  on the small one. Two GPT-2 engines (same weights, separate KV caches) alternate between batches, so a prefill never
+  touches the cache a decode loop is still reading. Token ids are the same function of the pixels either way.
 """
 from __future__ import annotations
 
@@ -9,17 +18,20 @@ from typing import Callable, Iterable, Iterator, Optional, Tuple
 
 import torch
 
-from clipcap_b200.distributed import caption_step
+from clipcap_b200.distributed import all_gather_prefix, caption_step
 
 
 class CaptionPipeline:
     def __init__(self, encode_fn: Callable, model, batch: int, image_size: int = 224, entry_length: int = 20,
                  stop_token: int = 50256, device="cuda", pixel_dtype: torch.dtype = torch.float32,
-                 prefix_all: Optional[torch.Tensor] = None, input_shape: Optional[Tuple[int, ...]] = None):
+                 prefix_all: Optional[torch.Tensor] = None, input_shape: Optional[Tuple[int, ...]] = None,
+                 partition_sms: int = 0, mode: str = "greedy", beam: int = 1):
         self.encode_fn, self.model = encode_fn, model
         self.entry_length, self.stop_token = entry_length, stop_token
+        self.mode, self.beam = mode, (beam if mode == "beam" else 1)
         self.device = torch.device(device)
         self.prefix_all = prefix_all
+        self.batch = batch
         self.copy_stream = torch.cuda.Stream(device=self.device)
         shape = (batch, *input_shape) if input_shape is not None else (batch, 3, image_size, image_size)
         self._px = [torch.empty(shape, device=self.device, dtype=pixel_dtype) for _ in range(2)]
@@ -30,7 +42,15 @@ class CaptionPipeline:
         self._done = [torch.cuda.Event() for _ in range(2)]       # results of slot i are in host memory
         self.h2d_bytes_per_batch = self._px[0].numel() * self._px[0].element_size()
         self.d2h_bytes_per_batch = self._tok[0].numel() * 4 + self._len[0].numel() * 4
+        self.partition = None
+        if partition_sms > 0:
+            from clipcap_b200.engine import SmPartition
+            self.partition = SmPartition(partition_sms, self.device)
+            self._prefilled = [torch.cuda.Event() for _ in range(2)]  # engine i holds the prefix + first token of its batch
+            self._decoded = [torch.cuda.Event() for _ in range(2)]    # engine i is free for the next prefill
+            self._lm = None
 
+    # ------------------------------------------------------------------ staging
     def _stage(self, slot: int, pixels_host: torch.Tensor, first_use: bool) -> None:
         if not pixels_host.is_pinned():
             raise ValueError("CaptionPipeline needs pinned host batches (tensor.pin_memory())")
@@ -40,16 +60,68 @@ class CaptionPipeline:
             self._px[slot][:pixels_host.shape[0]].copy_(pixels_host, non_blocking=True)
             self._copied[slot].record(self.copy_stream)
 
-    def run(self, batches: Iterable[torch.Tensor]) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+    # ------------------------------------------------------------------ one batch, enqueued (no host sync)
+    def _enqueue_sequential(self, pixels: torch.Tensor, slot: int) -> None:
+        compute = torch.cuda.current_stream(self.device)
+        toks, lens, _ = caption_step(self.encode_fn, self.model, pixels, self.entry_length, self.stop_token,
+                                     self.prefix_all, mode=self.mode, beam=self.beam)
+        rows = pixels.shape[0]
+        self._tok[slot][:rows].copy_(toks, non_blocking=True)
+        self._len[slot][:rows].copy_(lens, non_blocking=True)
+        self._done[slot].record(compute)
+
+    def _enqueue_partitioned(self, pixels: torch.Tensor, slot: int, index: int, staged: bool) -> None:
+        part = self.partition
+        rows = pixels.shape[0]
+        lm = self.model.language_model
+        K = self.model.transformer_mapper.prefix_length
+        if self._lm is None:
+            self._lm = lm.decode_engines(2, self.batch * self.beam, K + self.entry_length)
+        eng = self._lm[slot]
+        kw = dict(mode=self.mode, beam=self.beam, entry_length=self.entry_length, stop_token=self.stop_token)
+        with part.on(0) as front:      # large partition: image tower -> mapper -> [all-gather] -> prefill + first token
+            if staged:
+                front.wait_event(self._copied[slot])
+            emb = self.encode_fn(pixels)
+            prefix = self.model.transformer_mapper(emb)
+            if staged:
+                self._consumed[slot].record(front)
+            work = None
+            if self.prefix_all is not None:
+                _, work = all_gather_prefix(prefix, None, self.prefix_all, async_op=True)
+            if index >= 2:
+                front.wait_event(self._decoded[slot])   # this engine's previous batch has left the decode partition
+            eng.prefill(prefix, **kw)
+            if work is not None:
+                work.wait()
+            self._prefilled[slot].record(front)
+        with part.on(1) as back:       # small partition: the decode loop and the copy of the ids to the host
+            back.wait_event(self._prefilled[slot])
+            toks, lens, _ = eng.decode(rows, K, **kw)
+            self._decoded[slot].record(back)
+            self._tok[slot][:rows].copy_(toks, non_blocking=True)
+            self._len[slot][:rows].copy_(lens, non_blocking=True)
+            self._done[slot].record(back)
+
+    # ------------------------------------------------------------------ the loop
+    def run(self, batches: Iterable[torch.Tensor], resident: bool = False) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         """Yields (tokens [B, entry_length] int32, lengths [B] int32) in pinned host memory, one pair per input batch, in
-        order. The tensors of a yielded pair are reused two batches later."""
+        order. The tensors of a yielded pair are reused two batches later. `resident=True`: the batches are device tensors
+        already (no staging copy)."""
         it = iter(batches)
         compute = torch.cuda.current_stream(self.device)
         try:
             nxt = next(it)
         except StopIteration:
             return
-        self._stage(0, nxt, True)
+        if not resident:
+            self._stage(0, nxt, True)
+        elif self.partition is not None:
+            # the caller produced the resident batches on its current stream: order both partitions after it
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            for st in self.partition.streams:
+                st.wait_event(ready)
         i = 0
         pending = None  # (slot, rows) whose results have been enqueued but not yet handed out
         while nxt is not None:
@@ -58,19 +130,22 @@ class CaptionPipeline:
                 upcoming = next(it)
             except StopIteration:
                 upcoming = None
-            if upcoming is not None:  # copy of batch i+1 overlaps the compute of batch i
+            if upcoming is not None and not resident:  # copy of batch i+1 overlaps the compute of batch i
                 self._stage(slot ^ 1, upcoming, i == 0)
-            compute.wait_event(self._copied[slot])
-            toks, lens, _ = caption_step(self.encode_fn, self.model, self._px[slot][:rows], self.entry_length,
-                                         self.stop_token, self.prefix_all)
-            self._consumed[slot].record(compute)
+            pixels = nxt if resident else self._px[slot][:rows]
+            if self.partition is not None:
+                self._enqueue_partitioned(pixels, slot, i, not resident)
+            else:
+                if not resident:
+                    compute.wait_event(self._copied[slot])
+                # hand out batch i-1 only after batch i is enqueued (below): slot buffers alternate
+                self._enqueue_sequential(pixels, slot)
+                if not resident:
+                    self._consumed[slot].record(compute)
             if pending is not None:  # hand out batch i-1 while batch i runs
                 ps, pr = pending
                 self._done[ps].synchronize()
                 yield self._tok[ps][:pr], self._len[ps][:pr]
-            self._tok[slot][:rows].copy_(toks, non_blocking=True)
-            self._len[slot][:rows].copy_(lens, non_blocking=True)
-            self._done[slot].record(compute)
             pending = (slot, rows)
             nxt = upcoming
             i += 1

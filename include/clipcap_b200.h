@@ -176,7 +176,15 @@ typedef struct cc_gen_cfg {
  * Row i equals the reference called on sample i alone. */
 int cc_generate(cc_gpt2* h, const void* prefix, int dtype, int B, int Tp, const cc_gen_cfg* g, int32_t* tokens,
                 int32_t* lengths, float* scores, void* stream);
-/* number of kernel launches (graph nodes) the last cc_generate enqueued */
+/* The same call in two halves, for callers that run the tensor-bound prefill and the latency-bound decode loop on
+ * different streams / SM partitions (cc_partition_*): cc_generate_prefill runs `h = prefix + wpe`, the prefill of all Tp
+ * positions and the selection of the FIRST token (base.py:80-94 at step 0); cc_generate_decode runs the remaining
+ * entry_length - 1 steps and copies out the results exactly as cc_generate does. The caller orders the decode stream
+ * after the prefill (event) and does not touch the handle in between; results equal cc_generate's. */
+int cc_generate_prefill(cc_gpt2* h, const void* prefix, int dtype, int B, int Tp, const cc_gen_cfg* g, void* stream);
+int cc_generate_decode(cc_gpt2* h, int B, int Tp, const cc_gen_cfg* g, int32_t* tokens, int32_t* lengths, float* scores,
+                       void* stream);
+/* number of kernel launches (graph nodes) the last cc_generate (or prefill + decode pair) enqueued */
 int cc_gpt2_last_launches(cc_gpt2* h);
 void cc_gpt2_destroy(cc_gpt2* h);
 
@@ -270,6 +278,29 @@ int cc_op_skinny_gemm(const float* x32, const float* gamma, const float* beta, f
 int cc_op_attention_bwd(const void* q, const void* k, const void* v, int64_t ld, const void* d_o, int64_t ldo, void* dq,
                         void* dk, void* dv, int64_t ldd, int B, int S, int H, int hd, int causal, float scale,
                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * SM partitions for the two-stage serving pipeline (clipcap_b200/pipeline.py). The path's stages have opposite
+ * characters on a B200: image tower + mapper + prefill are tensor- and power-bound, the decode loop is a chain of
+ * dependent launches that leaves most SMs idle. cc_partition_create splits the device's SMs (CUDA green contexts) into
+ * a large partition (which = 0) and a small one (which = 1, >= small_sms SMs, rounded up to a multiple of 8) and creates
+ * one non-blocking stream in each; work enqueued on a partition's stream runs on its SMs only, so the decode of batch i
+ * overlaps the image tower of batch i+1 without either stalling the other. No reference counterpart (single stream,
+ * clipcap/inference/demo.py:30-45). */
+typedef struct cc_partition cc_partition;
+int cc_partition_create(cc_partition** p, int device, int small_sms);
+void* cc_partition_stream(cc_partition* p, int which); /* cudaStream_t owned by the partition */
+int cc_partition_sms(cc_partition* p, int which);      /* SMs provisioned for that partition */
+void cc_partition_destroy(cc_partition* p);
+
+/* SM budget of the calling process' next launches: the number of SMs the stream it enqueues on may use (0 = the whole
+ * device). A caller that splits the GPU into SM partitions (CUDA green contexts: the tensor-bound image tower of batch
+ * i+1 on one partition, the latency-bound decode loop of batch i on the other — clipcap_b200/pipeline.py) sets the
+ * budget of a partition before enqueuing on its stream; persistent grids, tile shapes and split-K factors are sized for
+ * it. Graphs captured by cc_generate are cached per budget. The reference has no counterpart (single stream,
+ * clipcap/inference/demo.py:30-45). */
+void cc_set_sm_budget(int n_sms);
+int cc_get_sm_budget(void);
 
 /* Live per-launch timing of the dominant kernel (the 128x256-tile tcgen05 GEMM): while enabled, every such launch that
  * is not inside a graph capture is bracketed by CUDA events on its own stream. cc_prof_read synchronises the device and

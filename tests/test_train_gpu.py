@@ -193,6 +193,39 @@ def test_training_step_api_drop_in(cuda_device):
     assert rel_err(prefix, want) < 3e-3
 
 
+def test_optimizer_step_invalidates_cached_engines(cuda_device):
+    """forward -> optimizer.step -> forward: the mapper engine built BEFORE the step (a validation pass, a caption callback)
+    must not serve stale weights afterwards. FusedAdamW updates through a raw pointer, so it bumps the parameters'
+    version counters itself (EngineModule keys its cached engine on them)."""
+    from clipcap_b200.encoders.config import EncoderConfig
+    from clipcap_b200.model import ClipCapModelPrefixOnly, Config, TrainingConfig
+    spec, gcfg, mcfg, map_w, lm_w, tokens, emb, *_ = load_train_case("tiny_a")
+    cfg = Config(language_model=spec, prefix_length=mcfg.K, projection_length=mcfg.P, transformer_layers=mcfg.L,
+                 transformer_attention_heads=mcfg.H, encoder_config=EncoderConfig(encoder_embedding_size=mcfg.E))
+    model = ClipCapModelPrefixOnly(cfg)
+    sd = {f"transformer_mapper.{k}": v for k, v in map_w.items()}
+    sd.update({f"language_model.{k}": v for k, v in lm_w.items()})
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda_device).train()
+    model.set_training_config(TrainingConfig(optimizer_lr=5e-2, use_deepspeed_optimisers=False, scheduler_warmup_steps=0,
+                                             total_steps=10))
+    opt = model.configure_optimizers()["optimizer"]
+    with torch.no_grad():
+        before = model.transformer_mapper(emb.to(cuda_device)).clone()   # builds and caches the mapper engine
+    assert rel_err(before, R.mapper_forward(map_w, emb, mcfg)) < 3e-3
+    versions = [p._version for p in model.transformer_mapper.parameters()]
+    loss = model.training_step((tokens.clone().to(cuda_device), emb.clone().to(cuda_device)), 0)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    assert all(p._version > v for p, v in zip(model.transformer_mapper.parameters(), versions))
+    with torch.no_grad():
+        after = model.transformer_mapper(emb.to(cuda_device))
+    new_w = {k: p.detach().cpu() for k, p in model.transformer_mapper.named_parameters()}
+    assert rel_err(after, before) > 1e-2                                  # the step really moved the output
+    assert rel_err(after, R.mapper_forward(new_w, emb, mcfg)) < 3e-3      # and it is the updated weights' output
+
+
 @pytest.mark.parametrize("B,Tt", [(1, 1), (5, 9), (2, 59)])
 def test_train_step_edge_shapes(cuda_device, B, Tt):
     """One sample with one token; a batch with a fully padded row and a row of token-0 only; captions that fill the model's
