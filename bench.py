@@ -3,14 +3,18 @@
 
   python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels behind the C ABI)
   python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the box's host cores (oracle port)
+  python bench.py --workload vit_only|beam5 ...            # BASELINE configs[2] / configs[3] per-GPU shards (extra lines)
 
 A step = one pass of the hot path over one batch of synthetic input:
   pixels [B,3,224,224] -> CLIP ViT-L/14 -> TransformerMapper (8 layers, K=40, P=10, 8 heads) -> GPT-2-medium greedy
   decode of 20 tokens (generate_beam(beam_size=1) semantics) -> token ids                      (BASELINE configs[1], B=256)
-`value` is timed with the pixels already resident in HBM; `e2e` is the same calls with pinned HOST pixels copied in and
-the token ids read back inside the timed region. N > 1: one process per GPU (torchrun), every rank runs its own B-image
-shard (weak scaling) and the prefix embeddings are all-gathered over NCCL.
-Prints ONE JSON line on rank 0.
+Both numbers go through the public serving loop, clipcap_b200.pipeline.CaptionPipeline: `value` with the pixels already
+resident in HBM, `e2e` with pinned HOST pixels copied in and the token ids read back inside the timed region. The loop
+splits the GPU into two SM partitions (CUDA green contexts): image tower + mapper + prefill of batch i+1 on the large one,
+the decode steps of batch i on the small one (--partition-sms 0 turns that off; results are bit-identical either way).
+The timed region covers K whole steps including the drain of the last batch's decode.
+N > 1: one process per GPU (torchrun), every rank runs its own B-image shard (weak scaling) and the prefix embeddings are
+all-gathered over NCCL. Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -25,14 +29,25 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "captions/sec (224x224 bs=256, 20-tok greedy)"
-UNIT = "captions/s"
 ENTRY_LENGTH = 20
 STOP_TOKEN = 50256
-WORKLOAD = dict(workload="configs[1]: ViT-L/14 -> TransformerMapper(L=8,K=40,P=10,H=8) -> GPT-2-medium, 224x224, "
-                         "bs=256 per GPU, 20-token greedy decode",
-                batch_per_gpu=256, entry_length=ENTRY_LENGTH, lm="gpt2-medium", encoder="ViT-L/14",
-                prefix_length=40, projection_length=10, mapper_layers=8, mapper_heads=8)
+DEFAULT_PARTITION_SMS = 32
+MODEL_KEYS = dict(entry_length=ENTRY_LENGTH, lm="gpt2-medium", encoder="ViT-L/14", prefix_length=40, projection_length=10,
+                  mapper_layers=8, mapper_heads=8)
+WORKLOADS = {
+    "caption": dict(
+        metric="captions/sec (224x224 bs=256, 20-tok greedy)", unit="captions/s", batch=256, mode="greedy", beam=1,
+        workload="configs[1]: ViT-L/14 -> TransformerMapper(L=8,K=40,P=10,H=8) -> GPT-2-medium, 224x224, bs=256 per GPU, "
+                 "20-token greedy decode"),
+    "vit_only": dict(
+        metric="images/sec (ViT-L/14 encode-only, bs=1024 over 8 GPUs)", unit="images/s", batch=128, mode=None, beam=1,
+        workload="configs[2]: ViT-L/14 encode-only, 224x224, bs=1024 synthetic images sharded over 8 GPUs = 128 per GPU"),
+    "beam5": dict(
+        metric="captions/sec (224x224 bs=2048 over 8 GPUs, beam=5, 20 tokens)", unit="captions/s", batch=256, mode="beam",
+        beam=5,
+        workload="configs[3]: ViT-L/14 -> TransformerMapper(L=8,K=40,P=10,H=8) -> GPT-2-medium, bs=2048 over 8 GPUs = 256 "
+                 "per GPU, beam=5, 20 tokens, NCCL prefix all-gather"),
+}
 
 
 def parse_args():
@@ -41,10 +56,20 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--workload", default="caption", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
+    ap.add_argument("--partition-sms", type=int, default=int(os.environ.get("CLIPCAP_B200_PARTITION_SMS",
+                                                                              DEFAULT_PARTITION_SMS)),
+                    help="SMs of the decode partition (0 = one stream, no SM partitioning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the prefix all-gather (attribution runs)")
     ap.add_argument("--cpu-captions", type=int, default=12, help="captions timed for the cpu_baseline sample")
     return ap.parse_args()
+
+
+def workload_config(name, batch, world):
+    w = WORKLOADS[name]
+    return dict(MODEL_KEYS, workload=w["workload"], batch_per_gpu=batch, global_batch=batch * world)
 
 
 # ------------------------------------------------------------------------------------------------ roofline helpers
@@ -58,23 +83,23 @@ def measured_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
-def vit_gemm_flops(B):
-    """Algorithmic FLOPs of the four GEMMs of one ViT-L/14 block over B images, x24 layers."""
-    rows = B * 257
-    per_layer = 2 * rows * 1024 * 3072 + 2 * rows * 1024 * 1024 + 2 * 2 * rows * 1024 * 4096
-    return 24 * per_layer
-
-
-def flops_per_caption():
-    d, L, V, K, T0 = 1024, 24, 50257, 40, 40
+def algorithmic_work(beam=1, Tp=40, EL=ENTRY_LENGTH):
+    """Per-image algorithmic work of each stage: FLOPs, and for the decode steps the HBM bytes
+    (weights once per step for the whole batch are returned separately)."""
+    d, L, V, K = 1024, 24, 50257, Tp
     vit = 2 * 256 * 588 * 1024 + 24 * (2 * 257 * 1024 * 3072 + 4 * 257 * 257 * 1024 + 2 * 257 * 1024 * 1024 +
                                         4 * 257 * 1024 * 4096) + 2 * 1024 * 768
     S = 50
     mapper = 2 * 768 * 10 * d + 8 * (16 * S * d * d + 4 * S * S * d)
     blk = L * (12 * d * d + 13 * d)
     prefill = K * 2 * blk + 2 * V * d + 2 * L * K * K * d
-    decode = sum(2 * blk + 2 * V * d + 4 * L * (T0 + s) * d for s in range(1, ENTRY_LENGTH))
-    return dict(vit=vit, mapper=mapper, prefill=prefill, decode=decode, total=vit + mapper + prefill + decode)
+    decode = beam * sum(2 * blk + 2 * V * d + 4 * L * (Tp + s) * d for s in range(1, EL))
+    kv_pos = L * 2 * d * 2  # bytes of K,V per sequence position (fp16)
+    # unique cache bytes read per image over the steps: the prefix once per image, generated positions once per beam
+    decode_kv_bytes = sum((Tp + beam * s) * kv_pos for s in range(1, EL))
+    weight_bytes_per_step = 2 * (blk + V * d)  # fp16 blocks + tied head, shared by the batch
+    return dict(vit=vit, mapper=mapper, prefill=prefill, decode=decode, decode_kv_bytes=decode_kv_bytes,
+                decode_weight_bytes_per_step=weight_bytes_per_step, total=vit + mapper + prefill + decode)
 
 
 class ClockSampler:
@@ -134,12 +159,22 @@ def cpu_reference_setup(state):
     return R, vit_w, map_w, lm_w, R.VitCfg(), R.MapperCfg(E=768, d=1024, P=10, K=40, H=8, L=8), R.Gpt2Cfg()
 
 
-def cpu_caption(R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg, pixels_one):
-    """One caption exactly as the reference produces it: batch size 1, no KV cache, generate_beam(beam_size=1)."""
+def cpu_caption(R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg, pixels_one, beam=1):
+    """One caption exactly as the reference produces it: batch size 1, no KV cache, generate_beam(beam_size=beam)."""
     import torch
     with torch.no_grad():
-        _, _, out = R.caption_greedy(vit_w, map_w, lm_w, vcfg, mcfg, gcfg, pixels_one, ENTRY_LENGTH, STOP_TOKEN)
-    return out[0][0]
+        if beam == 1:
+            _, _, out = R.caption_greedy(vit_w, map_w, lm_w, vcfg, mcfg, gcfg, pixels_one, ENTRY_LENGTH, STOP_TOKEN)
+            return out[0][0]
+        emb = R.vit_encode(vit_w, pixels_one, vcfg)
+        prefix = R.mapper_forward(map_w, emb, mcfg)
+        return R.generate_beam(lm_w, gcfg, prefix[0:1], beam, ENTRY_LENGTH, 1.0, STOP_TOKEN)[0]
+
+
+def cpu_encode(R, vit_w, vcfg, pixels):
+    import torch
+    with torch.no_grad():
+        return R.vit_encode(vit_w, pixels, vcfg)
 
 
 def synthetic_state(seed=0):
@@ -169,39 +204,86 @@ def synthetic_pixels(B, seed):
 
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the Python reference itself cannot travel to the
-    GPU box) on all host cores. One step = one caption (the reference is batch-size-1)."""
+    GPU box) on all host cores. One step = one unit (the reference is batch-size-1): a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
+    w = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     state = synthetic_state()
     R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg = cpu_reference_setup(state)
     px = synthetic_pixels(max(1, min(4, args.steps + args.warmup)), 1234)
+
+    def one(i):
+        p = px[i % px.shape[0]:i % px.shape[0] + 1]
+        if w["mode"] is None:
+            cpu_encode(R, vit_w, vcfg, p)
+        else:
+            cpu_caption(R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg, p, w["beam"])
+
     for i in range(args.warmup):
-        cpu_caption(R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg, px[i % px.shape[0]:i % px.shape[0] + 1])
+        one(i)
     times = []
     t0 = time.perf_counter()
     for i in range(args.steps):
         t1 = time.perf_counter()
-        cpu_caption(R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg, px[i % px.shape[0]:i % px.shape[0] + 1])
+        one(i)
         times.append(time.perf_counter() - t1)
     total = time.perf_counter() - t0
     value = args.steps / total
-    sample = f"{args.steps} captions, one image per step (reference is batch-size-1), fp32, no KV cache"
+    batch = args.batch or w["batch"]
+    sample = (f"{args.steps} units, one image per step (the reference is batch-size-1), fp32, no KV cache, "
+              f"{cores} host threads")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "p50_ms": 1e3 * statistics.median(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(WORKLOAD, note="CPU path: batch of 1 per step"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "p50_ms": 1e3 * statistics.median(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, batch, max(1, args.gpus)),
+        "reference_note": "CPU path: one image per step (bounded sample of the same workload)",
+        "cpu_baseline": {"value": value, "unit": w["unit"], "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": w["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
 # ------------------------------------------------------------------------------------------------ B200 side
+def stage_report(trace, B, beam, peaks, world_rank_note=""):
+    """Mean live stage times (CUDA events recorded inside the timed steps) against each stage's roofline."""
+    work = algorithmic_work(beam=beam)
+
+    def mean_ms(a, b):
+        vals = [r[a].elapsed_time(r[b]) for r in trace if a in r and b in r]
+        return sum(vals) / len(vals) if vals else None
+
+    t = {"vit": mean_ms("front0", "vit"), "mapper": mean_ms("vit", "mapper"), "prefill": mean_ms("mapper", "prefill"),
+         "decode": mean_ms("dec0", "dec1")}
+    stages, roof_ms = {}, 0.0
+    for name in ("vit", "mapper", "prefill"):
+        fl = work[name] * B
+        ideal = fl / (peaks["tf_sustained"] * 1e12) * 1e3
+        roof_ms += ideal
+        if t[name]:
+            ach = fl / (t[name] * 1e-3) / 1e12
+            stages[name] = {"bound": "tensor", "flops": fl, "ms": t[name], "achieved": ach, "unit": "TFLOP/s",
+                            "peak": peaks["tf_sustained"], "frac": ach / peaks["tf_sustained"], "roofline_ms": ideal}
+    by = (ENTRY_LENGTH - 1) * work["decode_weight_bytes_per_step"] + B * work["decode_kv_bytes"]
+    fl = work["decode"] * B
+    ideal_hbm = by / (peaks["hbm"] * 1e9) * 1e3
+    ideal_tc = fl / (peaks["tf_sustained"] * 1e12) * 1e3
+    ideal = max(ideal_hbm, ideal_tc)
+    roof_ms += ideal
+    if t["decode"]:
+        gbs = by / (t["decode"] * 1e-3) / 1e9
+        stages["decode"] = {"bound": "hbm" if ideal_hbm >= ideal_tc else "tensor", "bytes": by, "flops": fl,
+                            "ms": t["decode"], "achieved": gbs, "unit": "GB/s", "peak": peaks["hbm"],
+                            "frac": ideal / t["decode"], "roofline_ms": ideal,
+                            "ms_per_decode_step": t["decode"] / (ENTRY_LENGTH - 1)}
+    front = mean_ms("front0", "prefill")
+    return stages, roof_ms, front
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -226,12 +308,14 @@ def run_b200(args):
     from clipcap_b200 import _ffi
     from clipcap_b200.encoders.clip import CLIPModel, ViTImageTower
     from clipcap_b200.encoders.config import EncoderConfig
-    from clipcap_b200.distributed import caption_step
     from clipcap_b200.model import ClipCapModelPrefixOnly, Config
     from clipcap_b200.pipeline import CaptionPipeline
-    _ffi.lib()
+    lib = _ffi.lib()
 
-    B = args.batch
+    w = WORKLOADS[args.workload]
+    B = args.batch or w["batch"]
+    beam = w["beam"]
+    vit_only = w["mode"] is None
     state = synthetic_state()
     tower = ViTImageTower()
     tower.load_state_dict(state["vit"], strict=True)
@@ -246,26 +330,76 @@ def run_b200(args):
 
     px_host = synthetic_pixels(B, 1234 + rank).pin_memory()  # fp32, as the reference's preprocess produces
     px_dev = px_host.to(dev, non_blocking=True)
-    prefix_all = torch.empty(world * B, 40, 1024, device=dev, dtype=torch.float32) if world > 1 else None
+    gather = world > 1 and not args.no_gather and not vit_only
+    prefix_all = torch.empty(world * B, 40, 1024, device=dev, dtype=torch.float32) if gather else None
     tok_host = torch.empty(B, ENTRY_LENGTH, dtype=torch.int32).pin_memory()
     len_host = torch.empty(B, dtype=torch.int32).pin_memory()
+    emb_host = torch.empty(B, 768, dtype=torch.float32).pin_memory()
+    partition_sms = 0 if vit_only else max(0, args.partition_sms)
+    pipe, partition_note = None, None
+    if not vit_only:
+        try:
+            pipe = CaptionPipeline(encode_fn, model, B, 224, ENTRY_LENGTH, STOP_TOKEN, dev, prefix_all=prefix_all,
+                                   partition_sms=partition_sms, mode=w["mode"], beam=beam)
+        except Exception as e:  # noqa: BLE001 — no green contexts on this driver: same kernels on one stream
+            partition_note = f"SM partitioning unavailable ({type(e).__name__}: {e}); single stream"
+            partition_sms = 0
+            pipe = CaptionPipeline(encode_fn, model, B, 224, ENTRY_LENGTH, STOP_TOKEN, dev, prefix_all=prefix_all,
+                                   partition_sms=0, mode=w["mode"], beam=beam)
 
-    def step(pixels):
-        # cc_vit_forward -> cc_mapper_forward -> [prefix all-gather over NVLink, SURVEY §8e] -> cc_generate
-        toks, lens, _ = caption_step(encode_fn, model, pixels, ENTRY_LENGTH, STOP_TOKEN, prefix_all)
-        return toks, lens, None
+    # ---- the two step loops. Each returns the host time stamps at which a batch's result was handed out.
+    if vit_only:
+        px_stage = [torch.empty_like(px_dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
 
-    # End to end through the public serving loop (clipcap_b200.pipeline.CaptionPipeline): every step copies its pinned
-    # host pixels to the device and its token ids back; the copy of step i+1 overlaps the compute of step i.
-    pipe = CaptionPipeline(encode_fn, model, B, 224, ENTRY_LENGTH, STOP_TOKEN, dev, prefix_all=prefix_all)
+        def run_value(steps):
+            marks = []
+            for _ in range(steps):
+                encode_fn(px_dev)
+                marks.append(time.perf_counter())
+            return marks
 
-    def run_e2e(steps):
-        marks = []
-        for toks_h, lens_h in pipe.run(px_host for _ in range(steps)):
-            marks.append(time.perf_counter())
-            tok_host.copy_(toks_h)  # the caller consumes the ids
-            len_host.copy_(lens_h)
-        return marks
+        def run_e2e(steps):
+            # pinned host pixels -> device (copy stream, double-buffered) -> encode -> embeddings back to the host
+            marks, compute = [], torch.cuda.current_stream(dev)
+            copied = [torch.cuda.Event() for _ in range(2)]
+            used = [torch.cuda.Event() for _ in range(2)]
+            with torch.cuda.stream(copy_stream):
+                px_stage[0].copy_(px_host, non_blocking=True)
+                copied[0].record(copy_stream)
+            for i in range(steps):
+                s = i & 1
+                if i + 1 < steps:
+                    with torch.cuda.stream(copy_stream):
+                        if i >= 1:
+                            copy_stream.wait_event(used[s ^ 1])
+                        px_stage[s ^ 1].copy_(px_host, non_blocking=True)
+                        copied[s ^ 1].record(copy_stream)
+                compute.wait_event(copied[s])
+                emb = encode_fn(px_stage[s])
+                used[s].record(compute)
+                emb_host.copy_(emb, non_blocking=True)
+                marks.append(time.perf_counter())
+            return marks
+        h2d, d2h = px_host.numel() * 4, emb_host.numel() * 4
+        api = "clipcap_b200.encoders.CLIPModel.forward (pinned host pixels in, embeddings out, double-buffered H2D)"
+    else:
+        def run_value(steps):
+            marks = []
+            for toks_h, lens_h in pipe.run((px_dev for _ in range(steps)), resident=True):
+                marks.append(time.perf_counter())
+            return marks
+
+        def run_e2e(steps):
+            marks = []
+            for toks_h, lens_h in pipe.run(px_host for _ in range(steps)):
+                marks.append(time.perf_counter())
+                tok_host.copy_(toks_h)  # the caller consumes the ids
+                len_host.copy_(lens_h)
+            return marks
+        h2d, d2h = pipe.h2d_bytes_per_batch, pipe.d2h_bytes_per_batch
+        api = ("clipcap_b200.pipeline.CaptionPipeline (pinned host pixels in, token ids out, double-buffered H2D"
+               + (f", SM partitions {pipe.partition.sms[0]} + {pipe.partition.sms[1]}" if pipe.partition else "") + ")")
 
     def barrier():
         if world > 1:
@@ -273,114 +407,158 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        """K steps between barrier + synchronize on both sides, CUDA events around the whole region (the region ends
+        after a device synchronize, so every stream — both SM partitions, the copy stream — is inside it)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        evs[0].record()
-        for i in range(steps):
-            fn()
-            evs[i + 1].record()
+        ev0.record()
+        t0 = time.perf_counter()
+        marks = fn(steps)
+        torch.cuda.synchronize()
+        ev1.record()
         barrier()
-        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
-        total = evs[0].elapsed_time(evs[steps])
-        if world > 1:
-            t = torch.tensor([total], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total = t.item()
-        return total, per
+        mine = ev0.elapsed_time(ev1)
+        per = [1e3 * (b - a) for a, b in zip([t0] + marks[:-1], marks)]
+        return mine, per
 
-    for _ in range(max(3, args.warmup)):
-        step(px_dev)
+    run_value(max(3, args.warmup))
     barrier()
-    vit_eng, map_eng, lm_eng = tower._engine, model.transformer_mapper._engine, model.language_model._engine
-    launches_per_step = vit_eng.last_launches + map_eng.last_launches + lm_eng.last_launches + 1 + 3  # + embed, 3 copies
-
+    launches_per_step = tower._engine.last_launches
+    if not vit_only:
+        launches_per_step += model.transformer_mapper._engine.last_launches + pipe._engines()[0].last_launches + 1 + 3
+    if pipe is not None:
+        pipe.trace = []
     sampler = ClockSampler(local_rank)
     sampler.start()
-    total_ms, per = timed(lambda: step(px_dev), args.steps)
+    my_ms, per = timed(run_value, args.steps)
     clocks = sampler.stop()
+    trace = pipe.trace if pipe is not None else []
+    if pipe is not None:
+        pipe.trace = None
     run_e2e(2)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    t_start = time.perf_counter()
-    marks = run_e2e(args.steps)
-    ev1.record()
-    barrier()
-    e2e_ms = ev0.elapsed_time(ev1)
+    my_e2e_ms, e2e_per = timed(run_e2e, args.steps)
+
+    total_ms, e2e_ms, per_rank = my_ms, my_e2e_ms, None
     if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = t.item()
-    e2e_per = [1e3 * (b - a) for a, b in zip([t_start] + marks[:-1], marks)]
+        t = torch.tensor([my_ms, my_e2e_ms, float(clocks["sm_mhz"] or 0)], device=dev)
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        total_ms = max(x[0].item() for x in allt)   # the step of the job is the slowest rank's
+        e2e_ms = max(x[1].item() for x in allt)
+        per_rank = [{"rank": r, "ms_per_step": allt[r][0].item() / args.steps,
+                     "e2e_ms_per_step": allt[r][1].item() / args.steps, "sm_mhz": allt[r][2].item()}
+                    for r in range(world)]
+
+    # ---- multi-GPU exactness: every rank decodes rank 0's batch once more; the ids must equal rank 0's bit for bit
+    multi_gpu_exact = None
+    if world > 1 and not vit_only:
+        px0 = synthetic_pixels(B, 1234).to(dev)
+        toks0 = [t.clone() for t, _ in pipe.run([px0], resident=True)][0].to(dev)
+        ref = toks0.clone()
+        dist.broadcast(ref, src=0)
+        ok = torch.tensor([1 if torch.equal(ref, toks0) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        multi_gpu_exact = bool(ok.item())
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM, ViT block shapes), CUDA events around each launch
     peaks = measured_peaks()
     roof = None
     if rank == 0:
-        lib = _ffi.lib()
-        if hasattr(lib, "cc_prof_enable"):
-            import ctypes as C
-            lib.cc_prof_enable.argtypes = [C.c_int]
-            lib.cc_prof_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
-            lib.cc_prof_enable(1)
-            for _ in range(2):
-                encode_fn(px_dev)
-            torch.cuda.synchronize()
-            ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
-            lib.cc_prof_read(C.byref(ms), C.byref(fl), C.byref(n))
-            lib.cc_prof_enable(0)
-            if n.value > 0 and ms.value > 0:
-                ach = fl.value / (ms.value * 1e-3) / 1e12
-                traffic = None
-                tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-                if os.path.exists(tp):
-                    with open(tp) as f:
-                        traffic = json.load(f).get("traffic_bytes_per_launch")
-                roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tf_sustained"], "traffic": traffic,
-                        "kernel": "gemm_tn_kernel<256,*,2> (tcgen05 cta_group::2, 256x256 CTA-pair tile) over the ViT-L/14 block GEMMs",
-                        "launches_timed": n.value, "avg_launch_ms": ms.value / n.value,
-                        "flops_per_launch": fl.value / n.value, "peak_source": peaks["source"] + ", sustained bf16"}
+        import ctypes as C
+        lib.cc_prof_enable(1)
+        for _ in range(2):
+            encode_fn(px_dev)
+        torch.cuda.synchronize()
+        ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
+        lib.cc_prof_read(C.byref(ms), C.byref(fl), C.byref(n))
+        lib.cc_prof_enable(0)
+        if n.value > 0 and ms.value > 0:
+            ach = fl.value / (ms.value * 1e-3) / 1e12
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if os.path.exists(tp):
+                with open(tp) as f:
+                    traffic = json.load(f).get("traffic_bytes_per_launch")
+            roof = {"bound": "tensor", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["tf_sustained"], "traffic": traffic,
+                    "kernel": "gemm_tn_kernel<256,*,2> (tcgen05 cta_group::2, 256x256 CTA-pair tile) over the ViT-L/14 block GEMMs",
+                    "launches_timed": n.value, "avg_launch_ms": ms.value / n.value,
+                    "flops_per_launch": fl.value / n.value, "peak_source": peaks["source"] + ", sustained bf16",
+                    "timed": "two image-tower passes on the whole device right after the timed steps (same process)"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    captions = B * world
-    value = captions * args.steps / (total_ms * 1e-3)
-    fpc = flops_per_caption()
+    units = B * world
+    ms_per_step = total_ms / args.steps
+    value = units * args.steps / (total_ms * 1e-3)
+    work = algorithmic_work(beam=beam)
+    if roof is not None:
+        if vit_only:
+            ideal = work["vit"] * B / (peaks["tf_sustained"] * 1e12) * 1e3
+            roof["stages"] = {"vit": {"bound": "tensor", "flops": work["vit"] * B, "ms": ms_per_step,
+                                      "achieved": work["vit"] * B / (ms_per_step * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                      "peak": peaks["tf_sustained"], "roofline_ms": ideal,
+                                      "frac": ideal / ms_per_step}}
+            roof["step_roofline_ms"], roof["step_frac"] = ideal, ideal / ms_per_step
+        else:
+            stages, roof_ms, front_ms = stage_report(trace, B, beam, peaks)
+            roof["stages"] = stages
+            roof["step_roofline_ms"] = roof_ms           # sum of the stages' roofline times (SURVEY §8d table)
+            roof["step_frac"] = roof_ms / ms_per_step     # whole step against its roofline
+            roof["front_ms"] = front_ms                   # image tower + mapper + prefill of one batch (large partition)
+            roof["stages_note"] = ("stage ms = mean of CUDA-event intervals recorded inside the timed steps on the "
+                                   "stage's own stream; with SM partitions the decode stage of batch i overlaps the "
+                                   "other stages of batch i+1, so the stage times add up to more than ms_per_step")
+    cfg_out = dict(workload_config(args.workload, B, world), pixels_dtype="f32",
+                   l2="per-step working set (154 MB pixels, >1 GB activations, 1.4 GB weights) exceeds the 126 MB L2",
+                   weights="seeded random init (no checkpoints offline)",
+                   partition=(None if pipe is None or pipe.partition is None else
+                              {"front_sms": pipe.partition.sms[0], "decode_sms": pipe.partition.sms[1]}),
+                   timed_region="K steps back to back through the serving loop, incl. the drain of the last decode")
+    if partition_note:
+        cfg_out["partition_note"] = partition_note
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": total_ms / args.steps, "p50_ms": statistics.median(per), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": dict(WORKLOAD, global_batch=captions, pixels_dtype="f32",
-                       l2="per-step working set (154 MB pixels, >1 GB activations, 1.4 GB weights) exceeds the 126 MB L2",
-                       weights="seeded random init (no checkpoints offline)"),
-        "clocks": clocks,
-        "e2e": {"value": captions * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                "p50_ms": statistics.median(e2e_per), "h2d_bytes_per_step": pipe.h2d_bytes_per_batch,
-                "d2h_bytes_per_step": pipe.d2h_bytes_per_batch,
-                "api": "clipcap_b200.pipeline.CaptionPipeline (pinned host pixels in, token ids out, double-buffered H2D)"},
-        "gpu_launches": launches_per_step * args.steps,
-        "launches_per_step": launches_per_step,
-        "model_tflops": value * fpc["total"] / 1e12,
+        "metric": w["metric"], "value": value, "unit": w["unit"], "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "p50_ms": statistics.median(per),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": cfg_out, "clocks": clocks,
+        "e2e": {"value": units * args.steps / (e2e_ms * 1e-3), "unit": w["unit"], "ms_per_step": e2e_ms / args.steps,
+                "p50_ms": statistics.median(e2e_per), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": api},
+        "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+        "model_tflops": value * (work["vit"] if vit_only else work["total"]) / 1e12,
         "roofline": roof,
     }
+    if per_rank is not None:
+        out["per_rank"] = per_rank
+    if multi_gpu_exact is not None:
+        out["multi_gpu_exact"] = multi_gpu_exact
+    if world > 1:
+        out["collective"] = "none (--no-gather)" if not gather else "prefix all-gather (NCCL), fp32 [B,40,1024] per rank"
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg = cpu_reference_setup(state)
-        n = args.cpu_captions
-        cpu_caption(R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg, px_host[:1])  # warm-up
-        t0 = time.perf_counter()
-        cpu_tokens = [cpu_caption(R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg, px_host[i:i + 1]) for i in range(n)]
-        dt = time.perf_counter() - t0
-        gpu_tokens = tok_host[:n].tolist()
-        agree = sum(int(gpu_tokens[i][:len(cpu_tokens[i])] == cpu_tokens[i]) for i in range(n))
-        out["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": f"first {n} images of the same batch, one at a time (reference is batch-size-1), "
-                                         f"fp32, no KV cache; {agree}/{n} captions token-identical to the GPU run"}
+        n = args.cpu_captions if not vit_only else 8
+        if vit_only:
+            cpu_encode(R, vit_w, vcfg, px_host[:1])
+            t0 = time.perf_counter()
+            for i in range(n):
+                cpu_encode(R, vit_w, vcfg, px_host[i:i + 1])
+            dt = time.perf_counter() - t0
+            sample = f"first {n} images of the same batch, one at a time, fp32"
+        else:
+            cpu_caption(R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg, px_host[:1], beam)  # warm-up
+            t0 = time.perf_counter()
+            cpu_tokens = [cpu_caption(R, vit_w, map_w, lm_w, vcfg, mcfg, gcfg, px_host[i:i + 1], beam) for i in range(n)]
+            dt = time.perf_counter() - t0
+            gpu_tokens = tok_host[:n].tolist()
+            agree = sum(int(gpu_tokens[i][:len(cpu_tokens[i])] == list(cpu_tokens[i])) for i in range(n))
+            sample = (f"first {n} images of the same batch, one at a time (reference is batch-size-1), fp32, no KV cache; "
+                      f"{agree}/{n} captions token-identical to the GPU run")
+        out["cpu_baseline"] = {"value": n / dt, "unit": w["unit"], "cores": cores, "kind": "port", "sample": sample}
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:

@@ -14,11 +14,12 @@ Two overlaps, both across consecutive batches:
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Callable, Iterable, Iterator, Optional, Tuple
 
 import torch
 
-from clipcap_b200.distributed import all_gather_prefix, caption_step
+from clipcap_b200.distributed import all_gather_prefix
 
 
 class CaptionPipeline:
@@ -42,13 +43,14 @@ class CaptionPipeline:
         self._done = [torch.cuda.Event() for _ in range(2)]       # results of slot i are in host memory
         self.h2d_bytes_per_batch = self._px[0].numel() * self._px[0].element_size()
         self.d2h_bytes_per_batch = self._tok[0].numel() * 4 + self._len[0].numel() * 4
+        self.trace = None  # set to a list to collect per-batch stage events (bench.py: live stage times inside the step)
+        self._lm = None
         self.partition = None
         if partition_sms > 0:
             from clipcap_b200.engine import SmPartition
             self.partition = SmPartition(partition_sms, self.device)
             self._prefilled = [torch.cuda.Event() for _ in range(2)]  # engine i holds the prefix + first token of its batch
             self._decoded = [torch.cuda.Event() for _ in range(2)]    # engine i is free for the next prefill
-            self._lm = None
 
     # ------------------------------------------------------------------ staging
     def _stage(self, slot: int, pixels_host: torch.Tensor, first_use: bool) -> None:
@@ -61,47 +63,63 @@ class CaptionPipeline:
             self._copied[slot].record(self.copy_stream)
 
     # ------------------------------------------------------------------ one batch, enqueued (no host sync)
-    def _enqueue_sequential(self, pixels: torch.Tensor, slot: int) -> None:
-        compute = torch.cuda.current_stream(self.device)
-        toks, lens, _ = caption_step(self.encode_fn, self.model, pixels, self.entry_length, self.stop_token,
-                                     self.prefix_all, mode=self.mode, beam=self.beam)
-        rows = pixels.shape[0]
-        self._tok[slot][:rows].copy_(toks, non_blocking=True)
-        self._len[slot][:rows].copy_(lens, non_blocking=True)
-        self._done[slot].record(compute)
+    def _mark(self, rec, name: str, stream) -> None:
+        if rec is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            rec[name] = ev
 
-    def _enqueue_partitioned(self, pixels: torch.Tensor, slot: int, index: int, staged: bool) -> None:
+    def _engines(self):
+        if self._lm is None:
+            K = self.model.transformer_mapper.prefix_length
+            n = 2 if self.partition is not None else 1
+            self._lm = self.model.language_model.decode_engines(n, self.batch * self.beam, K + self.entry_length)
+        return self._lm
+
+    def _enqueue(self, pixels: torch.Tensor, slot: int, index: int, staged: bool) -> None:
+        """Image tower -> mapper -> [prefix all-gather] -> prefill + first token on the front stream, the remaining decode
+        steps + the copy of the ids to the host on the back stream. Without a partition both are the caller's stream."""
         part = self.partition
         rows = pixels.shape[0]
-        lm = self.model.language_model
         K = self.model.transformer_mapper.prefix_length
-        if self._lm is None:
-            self._lm = lm.decode_engines(2, self.batch * self.beam, K + self.entry_length)
-        eng = self._lm[slot]
+        eng = self._engines()[slot if part is not None else 0]
         kw = dict(mode=self.mode, beam=self.beam, entry_length=self.entry_length, stop_token=self.stop_token)
-        with part.on(0) as front:      # large partition: image tower -> mapper -> [all-gather] -> prefill + first token
+        rec = {} if self.trace is not None else None
+        compute = torch.cuda.current_stream(self.device)
+        with (part.on(0) if part is not None else contextlib.nullcontext(compute)) as front:
             if staged:
                 front.wait_event(self._copied[slot])
+            self._mark(rec, "front0", front)
             emb = self.encode_fn(pixels)
+            self._mark(rec, "vit", front)
             prefix = self.model.transformer_mapper(emb)
+            self._mark(rec, "mapper", front)
             if staged:
                 self._consumed[slot].record(front)
             work = None
-            if self.prefix_all is not None:
+            if self.prefix_all is not None:  # N > 1: every rank ends up with every rank's prefixes (SURVEY 8e)
                 _, work = all_gather_prefix(prefix, None, self.prefix_all, async_op=True)
-            if index >= 2:
-                front.wait_event(self._decoded[slot])   # this engine's previous batch has left the decode partition
+            if part is not None and index >= 2:
+                front.wait_event(self._decoded[slot])  # this engine's previous batch has left the decode partition
             eng.prefill(prefix, **kw)
+            self._mark(rec, "prefill", front)
             if work is not None:
                 work.wait()
-            self._prefilled[slot].record(front)
-        with part.on(1) as back:       # small partition: the decode loop and the copy of the ids to the host
-            back.wait_event(self._prefilled[slot])
+            if part is not None:
+                self._prefilled[slot].record(front)
+        with (part.on(1) if part is not None else contextlib.nullcontext(compute)) as back:
+            if part is not None:
+                back.wait_event(self._prefilled[slot])
+            self._mark(rec, "dec0", back)
             toks, lens, _ = eng.decode(rows, K, **kw)
-            self._decoded[slot].record(back)
+            self._mark(rec, "dec1", back)
+            if part is not None:
+                self._decoded[slot].record(back)
             self._tok[slot][:rows].copy_(toks, non_blocking=True)
             self._len[slot][:rows].copy_(lens, non_blocking=True)
             self._done[slot].record(back)
+        if rec is not None:
+            self.trace.append(rec)
 
     # ------------------------------------------------------------------ the loop
     def run(self, batches: Iterable[torch.Tensor], resident: bool = False) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
@@ -133,15 +151,7 @@ class CaptionPipeline:
             if upcoming is not None and not resident:  # copy of batch i+1 overlaps the compute of batch i
                 self._stage(slot ^ 1, upcoming, i == 0)
             pixels = nxt if resident else self._px[slot][:rows]
-            if self.partition is not None:
-                self._enqueue_partitioned(pixels, slot, i, not resident)
-            else:
-                if not resident:
-                    compute.wait_event(self._copied[slot])
-                # hand out batch i-1 only after batch i is enqueued (below): slot buffers alternate
-                self._enqueue_sequential(pixels, slot)
-                if not resident:
-                    self._consumed[slot].record(compute)
+            self._enqueue(pixels, slot, i, not resident)
             if pending is not None:  # hand out batch i-1 while batch i runs
                 ps, pr = pending
                 self._done[ps].synchronize()
