@@ -331,7 +331,10 @@ def run_b200(args):
     px_host = synthetic_pixels(B, 1234 + rank).pin_memory()  # fp32, as the reference's preprocess produces
     px_dev = px_host.to(dev, non_blocking=True)
     gather = world > 1 and not args.no_gather and not vit_only
-    prefix_all = torch.empty(world * B, 40, 1024, device=dev, dtype=torch.float32) if gather else None
+    comm = None
+    if gather:  # the C-ABI collective: cc_comm_create + in-place cc_allgather_prefix (NCCL over NVLink)
+        from clipcap_b200.distributed import PrefixComm
+        comm = PrefixComm.from_process_group(dev)
     tok_host = torch.empty(B, ENTRY_LENGTH, dtype=torch.int32).pin_memory()
     len_host = torch.empty(B, dtype=torch.int32).pin_memory()
     emb_host = torch.empty(B, 768, dtype=torch.float32).pin_memory()
@@ -339,13 +342,13 @@ def run_b200(args):
     pipe, partition_note = None, None
     if not vit_only:
         try:
-            pipe = CaptionPipeline(encode_fn, model, B, 224, ENTRY_LENGTH, STOP_TOKEN, dev, prefix_all=prefix_all,
-                                   partition_sms=partition_sms, mode=w["mode"], beam=beam)
+            pipe = CaptionPipeline(encode_fn, model, B, 224, ENTRY_LENGTH, STOP_TOKEN, dev, comm=comm,
+                                   prefix_dtype=torch.float16, partition_sms=partition_sms, mode=w["mode"], beam=beam)
         except Exception as e:  # noqa: BLE001 — no green contexts on this driver: same kernels on one stream
             partition_note = f"SM partitioning unavailable ({type(e).__name__}: {e}); single stream"
             partition_sms = 0
-            pipe = CaptionPipeline(encode_fn, model, B, 224, ENTRY_LENGTH, STOP_TOKEN, dev, prefix_all=prefix_all,
-                                   partition_sms=0, mode=w["mode"], beam=beam)
+            pipe = CaptionPipeline(encode_fn, model, B, 224, ENTRY_LENGTH, STOP_TOKEN, dev, comm=comm,
+                                   prefix_dtype=torch.float16, partition_sms=0, mode=w["mode"], beam=beam)
 
     # ---- the two step loops. Each returns the host time stamps at which a batch's result was handed out.
     if vit_only:
@@ -536,7 +539,9 @@ def run_b200(args):
     if multi_gpu_exact is not None:
         out["multi_gpu_exact"] = multi_gpu_exact
     if world > 1:
-        out["collective"] = "none (--no-gather)" if not gather else "prefix all-gather (NCCL), fp32 [B,40,1024] per rank"
+        out["collective"] = ("none (--no-gather)" if not gather else
+                             f"in-place ncclAllGather of the fp16 prefix [{B},40,1024] per rank ({B * 40 * 1024 * 2} bytes) through "
+                             f"cc_allgather_prefix on a side stream, NCCL {lib.cc_nccl_version()}")
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)

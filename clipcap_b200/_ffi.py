@@ -91,6 +91,13 @@ PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {
     "cc_generate_decode": (_i, [_vp, _i, _i, C.POINTER(cc_gen_cfg), _vp, _vp, _vp, _vp]),
     "cc_gpt2_last_launches": (_i, [_vp]),
     "cc_gpt2_destroy": (None, [_vp]),
+    "cc_comm_unique_id": (_i, [_vp]),
+    "cc_comm_create": (_i, [_pp, _vp, _i, _i]),
+    "cc_allgather_prefix": (_i, [_vp, _vp, C.c_size_t, _vp]),
+    "cc_comm_rank": (_i, [_vp]),
+    "cc_comm_nranks": (_i, [_vp]),
+    "cc_nccl_version": (_i, []),
+    "cc_comm_destroy": (None, [_vp]),
     "cc_partition_create": (_i, [_pp, _i, _i]),
     "cc_partition_stream": (_vp, [_vp, _i]),
     "cc_partition_sms": (_i, [_vp, _i]),

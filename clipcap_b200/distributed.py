@@ -42,6 +42,64 @@ def all_gather_prefix(prefix_local: torch.Tensor, group: Optional[dist.ProcessGr
     return (out, work) if async_op else out
 
 
+class PrefixComm:
+    """cc_comm_* — the C-ABI collective of the path: one NCCL communicator over the ranks of the job and the in-place
+    all-gather of the prefix buffer (each rank's mapper has written its own slot). The 128-byte NCCL id is made
+    on rank 0 and handed to the others through the launcher's process group (any backend)."""
+
+    def __init__(self, rank: int, world: int, unique_id: bytes, device="cuda"):
+        import ctypes as C
+        from clipcap_b200 import _ffi
+        self.rank, self.world = rank, world
+        self.device = torch.device(device)
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        with torch.cuda.device(self.device):
+            _ffi.check(_ffi.lib().cc_comm_create(C.byref(self._h), buf, rank, world))
+
+    @staticmethod
+    def make_unique_id() -> bytes:
+        import ctypes as C
+        from clipcap_b200 import _ffi
+        buf = C.create_string_buffer(128)
+        _ffi.check(_ffi.lib().cc_comm_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_process_group(cls, device="cuda", group: Optional[dist.ProcessGroup] = None) -> "PrefixComm":
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.make_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls(rank, world, box[0], device)
+
+    def slot(self, prefix_all: torch.Tensor) -> torch.Tensor:
+        """This rank's block of the gathered buffer [world * B_local, K, d] (a view: hand it to the mapper as `out`)."""
+        n = prefix_all.shape[0] // self.world
+        return prefix_all[self.rank * n:(self.rank + 1) * n]
+
+    def all_gather_(self, prefix_all: torch.Tensor) -> torch.Tensor:
+        """In place on the current stream: slot `rank` already holds this rank's prefixes; afterwards every slot is filled."""
+        from clipcap_b200 import _ffi
+        if not prefix_all.is_contiguous() or prefix_all.shape[0] % self.world != 0:
+            raise ValueError("prefix_all must be contiguous [world * B_local, K, d]")
+        per_rank = prefix_all.numel() * prefix_all.element_size() // self.world
+        with torch.cuda.device(prefix_all.device):
+            _ffi.check(_ffi.lib().cc_allgather_prefix(self._h, prefix_all.data_ptr(), per_rank, _ffi.current_stream_ptr()))
+        return prefix_all
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            from clipcap_b200 import _ffi
+            _ffi.lib().cc_comm_destroy(self._h)
+            self._h.value = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 def gather_tokens(tokens_local: torch.Tensor, lengths_local: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
     """Token ids [B_local, EL] + lengths [B_local] of every rank -> ([world*B_local, EL], [world*B_local]) on every rank."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:

@@ -178,14 +178,21 @@ class MapperEngine(_Handle):
             _ffi.check(_ffi.lib().cc_mapper_create(C.byref(self._h), C.byref(self.cfg), arr, len(keep), max_batch))
             torch.cuda.synchronize()
 
-    def forward(self, emb: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    def forward(self, emb: torch.Tensor, out_dtype: Optional[torch.dtype] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`out`: optional contiguous [B, K, d] fp32 / fp16 CUDA tensor to write into (e.g. this rank's slot of the
+        all-gathered prefix buffer), else a new tensor of `out_dtype` (default: the embeddings' dtype)."""
         _require_cuda(emb, "embeddings")
         c = self.cfg
         want = (c.W, c.E) if self.kind == "windowed" else (c.E,)
         if tuple(emb.shape[1:]) != want:
             raise ValueError(f"embeddings must be [B, {', '.join(map(str, want))}], got {tuple(emb.shape)}")
         emb = emb.contiguous()
-        out = torch.empty(emb.shape[0], c.K, c.d, device=emb.device, dtype=out_dtype or emb.dtype)
+        if out is None:
+            out = torch.empty(emb.shape[0], c.K, c.d, device=emb.device, dtype=out_dtype or emb.dtype)
+        elif (tuple(out.shape) != (emb.shape[0], c.K, c.d) or not out.is_contiguous() or not out.is_cuda
+              or out.dtype not in (torch.float32, torch.float16)):
+            raise ValueError(f"out must be a contiguous CUDA fp32 / fp16 tensor of shape {(emb.shape[0], c.K, c.d)}")
         with torch.cuda.device(emb.device):
             _ffi.check(_ffi.lib().cc_mapper_forward(self._h, emb.data_ptr(), _ffi.torch_dtype_code(emb), emb.shape[0],
                                                     out.data_ptr(), _ffi.torch_dtype_code(out),

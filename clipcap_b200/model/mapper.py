@@ -4,6 +4,8 @@ parameter containers only — they give the same default initialisation, in the 
 are never called."""
 from __future__ import annotations
 
+from typing import Optional
+
 import torch
 import torch.nn as nn
 
@@ -67,8 +69,11 @@ class TransformerMapper(EngineModule):
                             W=self.window_size, use_pos=self.use_pos, max_batch=capacity[0], device=device)
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self._get_engine((max(8, x.shape[0]),)).forward(x)
+    def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None,
+                out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """mapper.py:122-130. `out` / `out_dtype` (extensions): write the prefix into a caller-owned [B, K, d] buffer —
+        the rank's slot of the all-gathered prefix tensor — or return it in another dtype than the embeddings'."""
+        return self._get_engine((max(8, x.shape[0]),)).forward(x, out_dtype=out_dtype, out=out)
 
 
 class TransformerMapperWindowed(TransformerMapper):

@@ -26,13 +26,27 @@ class CaptionPipeline:
     def __init__(self, encode_fn: Callable, model, batch: int, image_size: int = 224, entry_length: int = 20,
                  stop_token: int = 50256, device="cuda", pixel_dtype: torch.dtype = torch.float32,
                  prefix_all: Optional[torch.Tensor] = None, input_shape: Optional[Tuple[int, ...]] = None,
-                 partition_sms: int = 0, mode: str = "greedy", beam: int = 1):
+                 partition_sms: int = 0, mode: str = "greedy", beam: int = 1, comm=None,
+                 prefix_dtype: Optional[torch.dtype] = None):
+        """`comm` (distributed.PrefixComm, N > 1): the prefix all-gather runs through the C ABI, in place — the mapper
+        writes this rank's slot of a [world * batch, K, d] buffer of `prefix_dtype` and cc_allgather_prefix completes it
+        on a side stream (decode reads only the local slot, so nothing waits for the peers except the end of the step).
+        `prefix_all` (legacy): torch.distributed all-gather into the given tensor. `prefix_dtype`: dtype of the prefix
+        handed from the mapper to the language model (default: the encoder output's)."""
         self.encode_fn, self.model = encode_fn, model
         self.entry_length, self.stop_token = entry_length, stop_token
         self.mode, self.beam = mode, (beam if mode == "beam" else 1)
         self.device = torch.device(device)
         self.prefix_all = prefix_all
+        self.comm, self.prefix_dtype = comm, prefix_dtype
         self.batch = batch
+        if comm is not None:
+            K, d = model.transformer_mapper.prefix_length, model.transformer_mapper.lm_embedding_size
+            self.prefix_all = torch.empty(comm.world * batch, K, d, device=self.device, dtype=prefix_dtype or pixel_dtype)
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+            self._mapped = torch.cuda.Event()     # this rank's slot of prefix_all is written
+            self._gathered = torch.cuda.Event()   # the all-gather of the current batch has completed
+            self._gather_pending = False
         self.copy_stream = torch.cuda.Stream(device=self.device)
         shape = (batch, *input_shape) if input_shape is not None else (batch, 3, image_size, image_size)
         self._px = [torch.empty(shape, device=self.device, dtype=pixel_dtype) for _ in range(2)]
@@ -92,12 +106,26 @@ class CaptionPipeline:
             self._mark(rec, "front0", front)
             emb = self.encode_fn(pixels)
             self._mark(rec, "vit", front)
-            prefix = self.model.transformer_mapper(emb)
+            if self.comm is not None:
+                if self._gather_pending:
+                    front.wait_event(self._gathered)   # the previous batch's collective no longer touches the buffer
+                prefix = self.model.transformer_mapper(emb, out=self.comm.slot(self.prefix_all)[:rows])
+            elif self.prefix_dtype is not None:
+                prefix = self.model.transformer_mapper(emb, out_dtype=self.prefix_dtype)
+            else:
+                prefix = self.model.transformer_mapper(emb)
             self._mark(rec, "mapper", front)
             if staged:
                 self._consumed[slot].record(front)
             work = None
-            if self.prefix_all is not None:  # N > 1: every rank ends up with every rank's prefixes
+            if self.comm is not None:   # N > 1: every rank ends up with every rank's prefixes
+                self._mapped.record(front)
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(self._mapped)
+                    self.comm.all_gather_(self.prefix_all)
+                    self._gathered.record(self.comm_stream)
+                self._gather_pending = True
+            elif self.prefix_all is not None:
                 _, work = all_gather_prefix(prefix, None, self.prefix_all, async_op=True)
             if part is not None and index >= 2:
                 front.wait_event(self._decoded[slot])  # this engine's previous batch has left the decode partition
@@ -117,6 +145,8 @@ class CaptionPipeline:
                 self._decoded[slot].record(back)
             self._tok[slot][:rows].copy_(toks, non_blocking=True)
             self._len[slot][:rows].copy_(lens, non_blocking=True)
+            if self.comm is not None:
+                back.wait_event(self._gathered)   # a finished step means the gathered prefixes are complete, too
             self._done[slot].record(back)
         if rec is not None:
             self.trace.append(rec)

@@ -31,7 +31,7 @@ enum cc_status {
   CC_ESHAPE = -2, /* unsupported / inconsistent shape */
   CC_EALIGN = -3, /* pointer or stride alignment */
   CC_ECUDA = -4,  /* CUDA runtime / driver error */
-  CC_ENCCL = -5,  /* collective error (reserved) */
+  CC_ENCCL = -5,  /* NCCL missing or a collective failed */
   CC_EARCH = -6,  /* device is not sm_100 */
   CC_ENOMEM = -7
 };
@@ -278,6 +278,23 @@ int cc_op_skinny_gemm(const float* x32, const float* gamma, const float* beta, f
 int cc_op_attention_bwd(const void* q, const void* k, const void* v, int64_t ld, const void* d_o, int64_t ldo, void* dq,
                         void* dk, void* dv, int64_t ldd, int B, int S, int H, int hd, int causal, float scale,
                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: the one exchange step of the path. One process per GPU; every rank encodes + maps its own images
+ * and writes its [B_local, K, d] prefix block into slot `rank` of a [nranks * B_local, K, d] buffer (pass that slot as
+ * cc_mapper_forward's `out`); cc_allgather_prefix completes the buffer on every rank with ONE in-place ncclAllGather over
+ * NVLink, enqueued on `stream` (no host sync). The 128-byte id comes from cc_comm_unique_id on rank 0 and reaches the
+ * other ranks through the launcher (torch.distributed store, MPI, a file). NCCL is bound with dlopen at first use;
+ * CC_ENCCL when it is missing or a call fails. No reference counterpart: its inference is single-device
+ * (clipcap/inference/args.py:22-27); the collective is the one BASELINE.json's north_star adds. */
+typedef struct cc_comm cc_comm;
+int cc_comm_unique_id(void* id_out /* 128 bytes */);
+int cc_comm_create(cc_comm** c, const void* unique_id /* 128 bytes */, int rank, int nranks);
+int cc_allgather_prefix(cc_comm* c, void* prefix_all, size_t bytes_per_rank, void* stream);
+int cc_comm_rank(cc_comm* c);
+int cc_comm_nranks(cc_comm* c);
+int cc_nccl_version(void); /* NCCL_VERSION_CODE of the library bound, 0 if none */
+void cc_comm_destroy(cc_comm* c);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * SM partitions for the two-stage serving pipeline (clipcap_b200/pipeline.py). The path's stages have opposite

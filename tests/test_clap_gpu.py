@@ -1,7 +1,8 @@
 """CLAP audio tower (cc_clap_*, SURVEY §8f rank 4 / BASELINE configs[4]) against oracle/restate_clap.py, which is itself
 pinned to transformers' ClapAudioModelWithProjection (tests/test_clap_oracle_cpu.py). Tolerances: the CUDA path feeds
 fp16 operands to the tensor cores and keeps the residual stream, LayerNorm statistics and softmax in fp32 — relative L2
-error of the [B, 512] embedding <= 1e-2 and cosine >= 0.9999 per sample, written below."""
+error of the [B, 512] embedding <= 2e-3 (measured 7e-4; the north star's stage tolerance is 1e-3 on max-abs) and cosine
+>= 0.99999 per sample, written below."""
 import pytest
 import torch
 
@@ -10,8 +11,8 @@ from oracle import restate_clap as RC
 
 pytestmark = pytest.mark.gpu
 
-REL = 1e-2
-COS = 0.9999
+REL = 2e-3
+COS = 0.99999
 
 
 def _weights(cfg, seed):

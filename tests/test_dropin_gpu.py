@@ -72,6 +72,37 @@ def test_docs_inference_sequence(cuda_device, tmp_path):
     assert len(one) == 1 and isinstance(one[0], str)
 
 
+@pytest.mark.parametrize("name", ["tiny_a", "tiny_b"])
+def test_model_forward_matches_golden(cuda_device, name):
+    """ClipCapModel.forward(tokens, embeddings, mask) (clipcap/model/model.py:43-58) on the GPU against the logits the
+    UNMODIFIED reference produced for the same weights and inputs (tests/golden/tiny_{a,b}.npz::fwd_logits, frozen by
+    tests/golden/make_golden.py), incl. the -1-padded mask handling of training batches."""
+    from golden_util import load_lm_case
+    from clipcap_b200.encoders.config import EncoderConfig
+    from clipcap_b200.model import ClipCapModelPrefixOnly, Config
+    spec, gcfg, mcfg, map_w, lm_w, g = load_lm_case(name)
+    cfg = Config(language_model=spec, prefix_length=mcfg.K, projection_length=mcfg.P, transformer_layers=mcfg.L,
+                 transformer_attention_heads=mcfg.H, encoder_config=EncoderConfig(encoder_embedding_size=mcfg.E))
+    model = ClipCapModelPrefixOnly(cfg)
+    sd = {f"transformer_mapper.{k}": v for k, v in map_w.items()}
+    sd.update({f"language_model.{k}": v for k, v in lm_w.items()})
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().to(cuda_device)
+    emb = torch.from_numpy(g["emb"]).to(cuda_device)
+    tokens = torch.from_numpy(g["fwd_tokens"]).to(cuda_device)
+    mask = torch.ones_like(tokens, dtype=torch.bool)
+    want = torch.from_numpy(g["fwd_logits"])
+    out = model(tokens, emb, mask)
+    assert tuple(out.logits.shape) == tuple(want.shape) == (tokens.shape[0], mcfg.K + tokens.shape[1], gcfg.V)
+    err = rel_err(out.logits, want)
+    assert err < 1e-3, err
+    # trailing padding (what the reference's dataloader produces): the logits of the real positions do not change
+    mask[:, -2:] = False
+    out2 = model(tokens, emb, mask)
+    keep = mcfg.K + tokens.shape[1] - 2
+    assert rel_err(out2.logits[:, :keep], want[:, :keep]) < 1e-3
+
+
 def test_get_encoder_errors():
     import clipcap_b200 as clipcap
     with pytest.raises(ValueError, match="invalid encoder name"):

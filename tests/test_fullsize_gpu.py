@@ -54,14 +54,28 @@ def test_greedy_full_batch_deterministic_and_batch_invariant(full):
 
 
 def test_greedy_full_size_rows_match_oracle(full):
+    """16 rows of the B = 256 batch against the oracle run on each image alone. Token ids must be equal; a flip is accepted
+    only where the oracle's own top-1 / top-2 margin is below twice the MEASURED end-to-end logit error of this run
+    (SURVEY 8d), and both numbers are reported."""
     st = full["state"]
-    rows = [0, 101, 255]
+    rows = list(range(0, 256, 17)) + [255]          # 16 rows spread over both 128-row blocks of the decode GEMMs
     px = full["px"][rows]
-    _, _, oracle = R.caption_greedy(st["vit"], st["mapper"], st["lm"], R.VitCfg(), R.MapperCfg(E=768, d=1024, P=10, K=40, H=8, L=8),
-                                    R.Gpt2Cfg(), px, EL, STOP)
+    gcfg = R.Gpt2Cfg()
+    _, prefix_ref, oracle = R.caption_greedy(st["vit"], st["mapper"], st["lm"], R.VitCfg(),
+                                             R.MapperCfg(E=768, d=1024, P=10, K=40, H=8, L=8), gcfg, px, EL, STOP)
+    # measured logit error: first-step logits of the GPU path (pixels -> ... -> logits) against the oracle's
+    ref_logits = R.gpt2_logits(st["lm"], prefix_ref, gcfg, last_only=True)[:, -1]
+    got_logits = full["lm"].logits(full["prefix"][rows].contiguous())
+    logit_err = float((got_logits.cpu() - ref_logits).abs().max())
+    rel = logit_err / float(ref_logits.abs().max())
+    assert rel < 1e-3, rel                          # the stage tolerance of the north star
     t, l, _ = full["lm"].generate(full["prefix"], "greedy", 1, EL, 1.0, STOP)
-    exact, flips = check_tokens_against_oracle(t[rows], l[rows], oracle, margin_tol=5e-3)
-    assert exact >= len(rows) - 1, (exact, flips)
+    exact, flips = check_tokens_against_oracle(t[rows], l[rows], oracle, margin_tol=2.0 * logit_err)
+    min_margin = min(min(tr["margin"][0] for tr in o[2]) for o in oracle)
+    print(f"full-size greedy: {exact}/{len(rows)} rows token-identical, {flips} flips; measured logit error {logit_err:.2e} "
+          f"(relative {rel:.1e}), smallest oracle margin over all steps {min_margin:.2e}")
+    assert exact + flips == len(rows)
+    assert flips == 0 or min_margin < 2.0 * logit_err
 
 
 def test_beam5_full_shard(full):

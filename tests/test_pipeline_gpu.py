@@ -48,6 +48,67 @@ def test_pipeline_equals_direct_calls(cuda_device):
     assert list(pipe.run([])) == []
 
 
+def test_partitioned_pipeline_equals_sequential(cuda_device):
+    """SM-partitioned serving loop (image tower + mapper + prefill on the large partition, decode of the previous batch on
+    the small one, two alternating GPT-2 engines): token ids bit-identical to the single-stream loop and to the direct
+    calls, ragged batch included, pinned-host and device-resident inputs alike."""
+    from clipcap_b200.inference.base import generate_greedy_tokens
+    from clipcap_b200.pipeline import CaptionPipeline
+    encode_fn, model, vcfg, stop = _build(cuda_device)
+    B, EL = 4, 7
+    batches = [synth.pixels(n, vcfg.image_size, seed=70 + i).pin_memory() for i, n in enumerate((4, 4, 3, 4, 4, 4, 2))]
+    seq = CaptionPipeline(encode_fn, model, B, vcfg.image_size, EL, stop, cuda_device)
+    want = [(t.clone(), l.clone()) for t, l in seq.run(batches)]
+    part = CaptionPipeline(encode_fn, model, B, vcfg.image_size, EL, stop, cuda_device, partition_sms=32)
+    assert part.partition is not None and sum(part.partition.sms) <= 148 and part.partition.sms[1] >= 32
+    for resident in (False, True):
+        src = [b.to(cuda_device) for b in batches] if resident else batches
+        got = [(t.clone(), l.clone()) for t, l in part.run(src, resident=resident)]
+        assert len(got) == len(batches)
+        for (gt, gl), (wt, wl) in zip(got, want):
+            assert torch.equal(gt, wt) and torch.equal(gl, wl)
+    px = batches[2]
+    prefix = model.transformer_mapper(encode_fn(px.to(cuda_device)))
+    t, l, _ = generate_greedy_tokens(model, prefix, EL, stop)
+    assert torch.equal(want[2][0], t.cpu()) and torch.equal(want[2][1], l.cpu())
+    # beam mode through the same loop
+    from clipcap_b200.inference.base import generate_beam_tokens
+    beam_pipe = CaptionPipeline(encode_fn, model, B, vcfg.image_size, EL, stop, cuda_device, partition_sms=32, mode="beam",
+                                beam=3)
+    got = [(t.clone(), l.clone()) for t, l in beam_pipe.run(batches[:3])]
+    for px, (gt, gl) in zip(batches[:3], got):
+        prefix = model.transformer_mapper(encode_fn(px.to(cuda_device)))
+        wt, wl, _ = generate_beam_tokens(model, prefix, None, 3, EL, 1.0, stop)
+        assert torch.equal(gt, wt.cpu()) and torch.equal(gl, wl.cpu())
+
+
+def test_two_phase_generate_equals_generate(cuda_device):
+    """cc_generate_prefill + cc_generate_decode (the halves the partitioned loop runs on different streams) give exactly
+    what cc_generate gives, greedy and beam, also when another prefill has run on a second engine in between."""
+    from clipcap_b200.engine import Gpt2Engine
+    cfg = R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64)
+    w = synth.gpt2_weights(cfg, wte_std=0.1)
+    B, Tp, EL, stop = 5, 5, 9, 1002
+    prefix = (torch.randn(B, Tp, cfg.d, generator=torch.Generator().manual_seed(3)) * 0.5).to(cuda_device)
+    other = (torch.randn(B, Tp, cfg.d, generator=torch.Generator().manual_seed(4)) * 0.5).to(cuda_device)
+    a = Gpt2Engine(w, cfg.d, cfg.L, cfg.H, cfg.V, cfg.n_pos, max_seqs=B * 3, max_len=Tp + EL, device=cuda_device)
+    b = Gpt2Engine(w, cfg.d, cfg.L, cfg.H, cfg.V, cfg.n_pos, max_seqs=B * 3, max_len=Tp + EL, device=cuda_device)
+    for mode, beam in (("greedy", 1), ("beam", 3)):
+        want = a.generate(prefix, mode, beam, EL, 1.0, stop)
+        for _ in range(2):  # second round replays the two captured graphs
+            n, tp = a.prefill(prefix, mode, beam, EL, 1.0, stop)
+            b.prefill(other, mode, beam, EL, 1.0, stop)
+            got = a.decode(n, tp, mode, beam, EL, 1.0, stop)
+            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+            if mode == "beam":
+                assert torch.equal(got[2], want[2])
+            else:
+                assert float(got[2].abs().max()) == 0.0  # greedy returns zero scores, never a previous beam call's
+        assert a.last_launches > 0
+    with pytest.raises(ValueError):
+        a.prefill(prefix, "nucleus", 1, EL, 1.0, stop)
+
+
 def test_pipeline_with_audio_encoder(cuda_device):
     """BASELINE configs[4] through the same serving loop: mel features -> CLAP tower -> mapper (E = 512) -> greedy decode."""
     from clipcap_b200.encoders import get_encoder
