@@ -510,18 +510,22 @@ decode_attn_bulk_kernel(const __half* __restrict__ qkv, __half* __restrict__ kca
   }
   __syncwarp();
   pdl_launch_dependents();
-  pdl_wait();
-  if (pair >= nseq * H) return;
+  const bool live = pair < nseq * H;
   const int seq = pair / H, h = pair % H;
-  const int d = H * 64;
-  const int kq = lane >> 3;
-  const int c = lane & 7;
   const long long own = (static_cast<long long>(seq) * H + h) * t_max;
-  if (lane == 0 && pos > 0) {
+  // The cache rows of positions < pos were written by EARLIER decode steps / the prefill (hundreds of kernels back in the
+  // stream), never by the predecessor kernel, so they start streaming before griddepcontrol.wait; q and this step's k, v
+  // (the predecessor's output) are only touched after it.
+  if (live && lane == 0 && pos > 0) {
     mbar_arrive_expect_tx(bar, 2u * pos * row_bytes);
     bulk_load(kbuf, kcache + own * 64, pos * row_bytes, bar);
     bulk_load(vbuf, vcache + own * 64, pos * row_bytes, bar);
   }
+  pdl_wait();
+  if (!live) return;
+  const int d = H * 64;
+  const int kq = lane >> 3;
+  const int c = lane & 7;
   const __half* qrow = qkv + static_cast<long long>(seq) * 3 * d + h * 64;
   const uint4 knew = *reinterpret_cast<const uint4*>(qrow + d + c * 8);
   const uint4 vnew = *reinterpret_cast<const uint4*>(qrow + 2 * d + c * 8);

@@ -87,7 +87,10 @@ int check_device_sm100() {
 }
 
 namespace {
-std::atomic<int> g_sm_budget{0};
+std::atomic<int> g_sm_budget{[] {
+  const char* e = getenv("CLIPCAP_B200_SM_BUDGET");  // development: size every launch for n SMs without partitioning
+  return e != nullptr ? atoi(e) : 0;
+}()};
 }
 
 void set_sm_budget(int n) { g_sm_budget.store(n > 0 ? n : 0); }
