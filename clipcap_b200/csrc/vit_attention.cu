@@ -37,7 +37,8 @@ constexpr int VA_K_BYTES = 256 * 64 * 2;
 constexpr int VA_V_BYTES = 256 * 64 * 2;
 constexpr int VA_C_BYTES = 512;  // CLS token rows of q, k, v (3 x 128 B, padded)
 constexpr int VA_STAGE = VA_Q_BYTES + VA_K_BYTES + VA_V_BYTES;
-constexpr int VA_SCRATCH = 2048;  // CLS-query probabilities (256 floats)
+constexpr int VA_PART = 72;       // floats per partial result of the CLS query row: 64 dims, warp max, warp sum (padded)
+constexpr int VA_SCRATCH = 2 * 8 * VA_PART * 4;  // per stage: one partial per softmax warp
 constexpr int VA_SMEM = 2 * VA_STAGE + 2 * VA_C_BYTES + VA_SCRATCH + 256 + 1024;
 constexpr int VA_TMEM_COLS = 512;  // 256 per stream: S [0,256) -> P [0,128) + O [128,192)
 constexpr int VA_EMPTY_ARRIVALS = 2 + 8 + 1;  // both MMA streams (commit), 8 softmax warps, CLS warp
@@ -82,6 +83,32 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(addr));
   return r;
 }
+// Blackwell packed fp32 pairs (FFMA2 / FADD2) and the three-input maximum (FMNMX3): the softmax threads are bound by
+// instruction issue (one thread per query row, ~4.5 instructions per score), so every instruction that handles two scores
+// at once counts.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 // byte offset of 16-byte chunk c of row r inside a [rows][64 fp16] tile with the 128-byte TMA swizzle
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return r * 128 + ((c ^ (r & 7)) << 4); }
 
@@ -104,6 +131,7 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
   auto o_full = [&](int t) { return bars + 80u + 8u * t; };
   auto t_free = [&](int t) { return bars + 96u + 8u * t; };
   const uint32_t tmem_slot = bars + 112u;
+  auto cls_full = [&](int s) { return bars + 128u + 8u * s; };  // the 8 partials of the CLS query row of stage s are written
   float* sPf = reinterpret_cast<float*>(smem_raw + (sP - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -120,6 +148,7 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
       mbar_init(p_full(i), 4);
       mbar_init(o_full(i), 1);
       mbar_init(t_free(i), 4);
+      mbar_init(cls_full(i), 8);
     }
     fence_mbar_init();
   }
@@ -191,7 +220,11 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
       }
     }
   } else if (warp == 3) {
-    // ------------------------------------------------------------ CLS query row (one per image and head), CUDA cores
+    // ------------------------------------------------------------ CLS query row (one per image and head): combine
+    // The row's 256 patch keys are scored by the softmax warps (thread == key, 32 keys per warp, see below): each warp
+    // leaves a partial result (64 dims, its local maximum and sum); this warp adds the CLS key itself and merges the eight
+    // partials the way a split-key softmax is merged. (One warp doing the whole row — 2.8 k instructions per item — was
+    // the slowest role of the CTA and set the pace of the whole kernel.)
     int it = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       const int s = it & 1;
@@ -199,70 +232,30 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
       const int b = w / H, h = w - b * H;
       const long long row0 = static_cast<long long>(b) * VA_S;  // CLS row of this image in the output
       mbar_wait(full_qk(s), ph_s);
-      float qf[64];
+      // q_cls . k_cls: lane handles dims 2*lane, 2*lane + 1
+      const uint32_t qu = lds32(sC(s, 0) + 4 * lane), ku = lds32(sC(s, 1) + 4 * lane);
+      const float2 qf = __half22float2(*reinterpret_cast<const __half2*>(&qu));
+      const float2 kf = __half22float2(*reinterpret_cast<const __half2*>(&ku));
+      float sc0 = qf.x * kf.x + qf.y * kf.y;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float tmp[8];
-        unpack8(lds128(sC(s, 0) + 16 * c), tmp);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) qf[8 * c + i] = tmp[i];
-      }
-      float sc0 = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float kf[8];
-        unpack8(lds128(sC(s, 1) + 16 * c), kf);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sc0 += qf[8 * c + e] * kf[e];
-      }
-      // scores: lane handles patch keys lane, lane + 32, ... (8 each)
-      float sc[8];
-      float mx = sc0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int kr = lane + 32 * i;
-        float d = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float kf[8];
-          unpack8(lds128(sK(s) + sw128_off(kr, c)), kf);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) d += qf[8 * c + e] * kf[e];
-        }
-        sc[i] = d;
-        mx = fmaxf(mx, d);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float ms = mx * a.scale_log2;
-      float sum = 0.f;
-      __syncwarp();  // previous item's readers of sPf are done
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float p = fast_exp2(sc[i] * a.scale_log2 - ms);
-        sum += p;
-        sPf[lane + 32 * i] = p;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      const float pc = fast_exp2(sc0 * a.scale_log2 - ms);
-      sum += pc;
-      __syncwarp();
-      // O: lane owns head dims 2*lane, 2*lane + 1
+      for (int o = 16; o > 0; o >>= 1) sc0 += __shfl_xor_sync(0xffffffffu, sc0, o);
       mbar_wait(full_v(s), ph_s);
       const uint32_t v0u = lds32(sC(s, 2) + 4 * lane);
       const float2 v0f = __half22float2(*reinterpret_cast<const __half2*>(&v0u));
-      float o0 = pc * v0f.x, o1 = pc * v0f.y;
-      const int c16 = lane >> 2;
-      const uint32_t within = (lane & 3) * 4;
-      const uint32_t vbase = sV(s);
-#pragma unroll 8
-      for (int kr = 0; kr < 256; ++kr) {
-        const float p = sPf[kr];
-        const uint32_t u = lds32(vbase + sw128_off(kr, c16) + within);
-        const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&u));
-        o0 += p * vf.x;
-        o1 += p * vf.y;
+      mbar_wait(cls_full(s), ph_s);
+      const float* part = sPf + s * 8 * VA_PART;
+      float mx = sc0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) mx = fmaxf(mx, part[g * VA_PART + 64]);
+      const float pc = fast_exp2((sc0 - mx) * a.scale_log2);
+      float o0 = pc * v0f.x, o1 = pc * v0f.y, sum = pc;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float f = fast_exp2((part[g * VA_PART + 64] - mx) * a.scale_log2);
+        const float2 pv = *reinterpret_cast<const float2*>(part + g * VA_PART + 2 * lane);
+        o0 += f * pv.x;
+        o1 += f * pv.y;
+        sum += f * part[g * VA_PART + 65];
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty(s));
@@ -308,18 +301,34 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
         stagger = false;
       }
       tc_fence_after();
-      // pass 1: row max (TMEM loads double-buffered in registers)
-      float mx = s0;
+      // pass 1: row max (TMEM loads double-buffered in registers). One thread owns a whole row, so the reduction is a
+      // serial chain per thread: four independent running maxima of FMNMX3 (two scores per instruction) keep the pipe
+      // fed. The chunk loops are rolled up to two chunks per trip: fully unrolled, the kernel's code (75 KB, each warp
+      // role in its own region) overflowed the instruction cache and the schedulers sat in "no instruction" stalls.
+      float mx;
       {
-        uint32_t sr[2][32];
-        tmem_ld_x32(t_row, sr[0]);
+        float m0 = s0, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        uint32_t sa[32], sb[32];
+        auto fold = [&](const uint32_t(&v)[32]) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+          for (int j = 0; j < 32; j += 8) {
+            m0 = fmax3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            m1 = fmax3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            m2 = fmax3(m2, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+            m3 = fmax3(m3, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+          }
+        };
+        tmem_ld_x32(t_row, sa);
+#pragma unroll 1
+        for (int c = 0; c < 8; c += 2) {
           tmem_ld_wait();
-          if (c + 1 < 8) tmem_ld_x32(t_row + 32 * (c + 1), sr[(c + 1) & 1]);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sr[c & 1][j]));
+          tmem_ld_x32(t_row + 32 * (c + 1), sb);
+          fold(sa);
+          tmem_ld_wait();
+          if (c + 2 < 8) tmem_ld_x32(t_row + 32 * (c + 2), sa);
+          fold(sb);
         }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
       const float ms = mx * a.scale_log2;
       if (release_stage >= 0) {
@@ -330,24 +339,42 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
         release_stage = -1;
       }
       // pass 2: p = exp2((s - max) * scale * log2 e), row sum, P -> TMEM as fp16 pairs
-      float sum = 0.f;
+      float sum;
       {
-        uint32_t sr[2][32];
-        tmem_ld_x32(t_row, sr[0]);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          tmem_ld_wait();
-          if (c + 1 < 8) tmem_ld_x32(t_row + 32 * (c + 1), sr[(c + 1) & 1]);
+        unsigned long long acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;  // two packed partial row sums (4 add chains)
+        const unsigned long long sc2 = pack_f32x2(a.scale_log2, a.scale_log2), nms2 = pack_f32x2(-ms, -ms);
+        uint32_t sa[32], sb[32];
+        // x = s * scale*log2(e) - max*scale*log2(e) for two scores per FFMA2, exp2 on the MUFU, sums per FADD2; the
+        // probabilities of chunk c go back to TMEM as fp16 pairs over S columns this thread has already consumed
+        auto chunk = [&](const uint32_t(&v)[32], int c) {
           uint32_t pr[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float p0 = fast_exp2(__uint_as_float(sr[c & 1][2 * j]) * a.scale_log2 - ms);
-            const float p1 = fast_exp2(__uint_as_float(sr[c & 1][2 * j + 1]) * a.scale_log2 - ms);
-            sum += p0 + p1;
+          for (int j = 0; j < 16; j += 2) {
+            float x0, x1, x2, x3;
+            unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, nms2), x0, x1);
+            unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3])), sc2, nms2), x2, x3);
+            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
+            acc0 = fadd2(acc0, pack_f32x2(p0, p1));
+            acc1 = fadd2(acc1, pack_f32x2(p2, p3));
             pr[j] = pack_half2(p0, p1);
+            pr[j + 1] = pack_half2(p2, p3);
           }
-          tmem_st_x16(t_row + 16 * c, pr);  // P chunk c lands on S columns this thread has already consumed
+          tmem_st_x16(t_row + 16 * c, pr);
+        };
+        tmem_ld_x32(t_row, sa);
+#pragma unroll 1
+        for (int c = 0; c < 8; c += 2) {
+          tmem_ld_wait();
+          tmem_ld_x32(t_row + 32 * (c + 1), sb);
+          chunk(sa, c);
+          tmem_ld_wait();
+          if (c + 2 < 8) tmem_ld_x32(t_row + 32 * (c + 2), sa);
+          chunk(sb, c + 1);
         }
+        float a0, a1, a2, a3;
+        unpack_f32x2(acc0, a0, a1);
+        unpack_f32x2(acc1, a2, a3);
+        sum = (a0 + a1) + (a2 + a3);
       }
       const float pc = fast_exp2(s0 * a.scale_log2 - ms);  // probability of the CLS key
       sum += pc;
@@ -356,7 +383,49 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(t));
 
-      // While the P V MMA runs: the next item's CLS-key score (its stage has been loading all along)
+      // While the P V MMA runs: this warp's share of the CLS QUERY row — thread == patch key t * 128 + r. Score against
+      // q_cls, softmax statistics local to the warp's 32 keys, and the warp's partial sum of p * V (lane owns two head
+      // dims); warp 3 merges the eight partials.
+      {
+        const int key = t * 128 + r;
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float qf[8], kf[8];
+          unpack8(lds128(sC(s, 0) + 16 * c), qf);
+          unpack8(lds128(sK(s) + sw128_off(key, c)), kf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sq += qf[i] * kf[i];
+        }
+        float wm = sq;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        const float pq = fast_exp2((sq - wm) * a.scale_log2);
+        float ws = pq;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
+        mbar_wait(full_v(s), ph_s);
+        const uint32_t vrow0 = sV(s) + (lane & 3) * 4;
+        const int c16 = lane >> 2, key0 = t * 128 + quad * 32;
+        float po0 = 0.f, po1 = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+          const float pj = __shfl_sync(0xffffffffu, pq, j);
+          const uint32_t u = lds32(vrow0 + sw128_off(key0 + j, c16));
+          const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&u));
+          po0 += pj * vf.x;
+          po1 += pj * vf.y;
+        }
+        float* part = sPf + (s * 8 + (warp - 4)) * VA_PART;
+        *reinterpret_cast<float2*>(part + 2 * lane) = make_float2(po0, po1);
+        if (lane == 0) {
+          part[64] = wm;
+          part[65] = ws;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cls_full(s));
+      }
+      // ... and the next item's CLS-key score (its stage has been loading all along)
       if (w + static_cast<int>(gridDim.x) < n_items) {
         mbar_wait(full_qk(s ^ 1), ((it + 1) >> 1) & 1u);
         s0 = cls_score(s ^ 1);

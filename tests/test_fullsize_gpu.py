@@ -40,9 +40,16 @@ def test_greedy_full_batch_deterministic_and_batch_invariant(full):
     t2, l2, _ = lm.generate(prefix, "greedy", 1, EL, 1.0, STOP)
     assert torch.equal(t1, t2) and torch.equal(l1, l2)
     assert int(l1.min()) >= 1 and int(l1.max()) <= EL
-    # rows 40..47 alone (a different batch size picks different GEMM tiles; the per-row arithmetic is the same)
+    # batch invariance, exact: the same 256 prefixes in another row order (rows land in other tiles / CTAs / cache slots;
+    # tile shapes and split-K factors depend only on the row count, so the per-row arithmetic is bit-identical)
+    perm = torch.roll(torch.arange(256), 101)
+    tp, lp, _ = lm.generate(prefix[perm.to(prefix.device)].contiguous(), "greedy", 1, EL, 1.0, STOP)
+    assert torch.equal(tp, t1[perm.to(t1.device)]) and torch.equal(lp, l1[perm.to(l1.device)])
+    # rows 40..47 alone run on the <= 16-row weight-streaming kernels (csrc/skinny.cu): other summation order in the last
+    # bits, so a row may differ where two logits are within rounding of each other — at most one row of the eight
     ts, ls, _ = lm.generate(prefix[40:48].contiguous(), "greedy", 1, EL, 1.0, STOP)
-    assert torch.equal(ts, t1[40:48]) and torch.equal(ls, l1[40:48])
+    same = sum(int(torch.equal(ts[i], t1[40 + i]) and int(ls[i]) == int(l1[40 + i])) for i in range(8))
+    assert same >= 7, same
     # The encode path is batch invariant up to the tile shape: a small batch runs 128-row tiles where the full batch runs
     # 256-row CTA-pair tiles, the fp32 sums differ in the last bits (ViT: < 1e-5) and an fp16 operand rounding can then
     # flip by one ulp further down (mapper: < 5e-4, inside the 1e-3 stage tolerance).
