@@ -34,6 +34,14 @@ int cc_op_gemm(const void* a, int64_t lda, const void* w, const float* bias, voi
   return gemm_run(p, M, static_cast<cudaStream_t>(stream));
 }
 
+int cc_op_tile_image(const float* image, int size, int tiles_per_axis, int pixels_per_tile, int step, float* tiles,
+                     void* stream) {
+  using namespace cc;
+  CC_REQUIRE(image != nullptr && tiles != nullptr, CC_EINVAL, "cc_op_tile_image: null argument");
+  CC_TRY(check_device_sm100());
+  return tile_image_run(image, size, tiles_per_axis, pixels_per_tile, step, tiles, static_cast<cudaStream_t>(stream));
+}
+
 int cc_op_layernorm(const float* x, int64_t x_ld, const float* gamma, const float* beta, void* y, int64_t y_ld, int rows,
                     int d, float eps, void* stream) {
   using namespace cc;

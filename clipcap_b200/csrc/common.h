@@ -252,6 +252,8 @@ int vit_im2col_run(const void* pixels, int dtype, __half* out, int B, int img, i
 int vit_embed_lnpre_run(const float* patches, const float* cls, const float* pos, const float* g, const float* b,
                         float* h, int B, int T, int w, float eps, cudaStream_t s);
 int l2_normalize_run(float* x, int rows, int cols, cudaStream_t s);
+// window tiling of a decoded square image [3, S, S] fp32 -> [n*n, 3, p, p] (tile (ty, tx) starts at pixel (ty, tx) * step)
+int tile_image_run(const float* img, int S, int n, int p, int step, float* tiles, cudaStream_t s);
 // mapper
 int mapper_fill_const_run(float* h, const float* prefix_const, const float* pos_emb, int B, int P, int K, int d,
                           cudaStream_t s);

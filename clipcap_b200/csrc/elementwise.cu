@@ -168,6 +168,25 @@ __global__ void mapper_fill_const_kernel(float* __restrict__ h, const float* __r
   }
 }
 
+// ---------------------------------------------------------------- window tiling of a decoded image (encoders/clip.py:60-82)
+// tiles[(ty * n + tx), c, i, j] = image[c, ty * step + i, tx * step + j]: the reference's
+// tensor.unfold(1, p, step).unfold(2, p, step) on the decoded [3, S, S] image, written tile-major so every tile is an
+// ordinary [3, p, p] image for the resize / normalise step that follows. Pure index arithmetic, one pass over the pixels.
+__global__ void tile_image_kernel(const float* __restrict__ img, int S, int n, int p, int step, float* __restrict__ tiles) {
+  const long long total = static_cast<long long>(n) * n * 3 * p * p;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += stride) {
+    const int j = static_cast<int>(i % p);
+    long long r = i / p;
+    const int ii = static_cast<int>(r % p);
+    r /= p;
+    const int c = static_cast<int>(r % 3);
+    const int tile = static_cast<int>(r / 3);
+    const int ty = tile / n, tx = tile - ty * n;
+    tiles[i] = img[(static_cast<long long>(c) * S + ty * step + ii) * S + tx * step + j];
+  }
+}
+
 // ---------------------------------------------------------------- GPT-2 input embedding
 template <typename SRC>
 __global__ void gpt2_embed_prefix_kernel(const SRC* __restrict__ e, const float* __restrict__ wpe, float* __restrict__ h,
@@ -303,6 +322,15 @@ int mapper_fill_const_run(float* h, const float* prefix_const, const float* pos_
                           cudaStream_t s) {
   const long long n = static_cast<long long>(B) * (P + K) * d;
   mapper_fill_const_kernel<<<grid_for(n, 256), 256, 0, s>>>(h, prefix_const, pos_emb, B, P, K, d);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+int tile_image_run(const float* img, int S, int n, int p, int step, float* tiles, cudaStream_t s) {
+  CC_REQUIRE(S > 0 && n > 0 && p > 0 && step > 0 && (n - 1) * step + p <= S, CC_ESHAPE,
+             "tile_image: %d x %d tiles of %d px at step %d do not fit a %d px image", n, n, p, step, S);
+  const long long total = static_cast<long long>(n) * n * 3 * p * p;
+  tile_image_kernel<<<grid_for(total, 256), 256, 0, s>>>(img, S, n, p, step, tiles);
   CC_CUDA(cudaGetLastError());
   return CC_OK;
 }

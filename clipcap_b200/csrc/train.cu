@@ -18,6 +18,8 @@ struct cc_train {
   cc_gpt2_cfg gc;
   int max_batch = 0, max_tokens = 0;
   int S = 0, T_max = 0, rows_m = 0, rows_l = 0, rows_sel = 0, v_pad = 0, head_chunk = 0;
+  int W = 1, Ptot = 0;      // windows per sample (TransformerMapperWindowed: window_size + 1) and projected tokens W * P
+  float* pos_tmp = nullptr;  // [Ptot * d] column sums of the projected-token gradients (pos_embeddings gradient / bias fold)
   cc::Arena arena;
   // ---- frozen language model
   struct LmLayer {
@@ -84,7 +86,9 @@ int train_build(cc_train* t, const cc_tensor* w, int nw) {
   const cc_mapper_cfg& mc = t->mc;
   const cc_gpt2_cfg& gc = t->gc;
   const int d = gc.d, B = t->max_batch;
-  t->S = mc.P + mc.K;
+  t->W = mc.kind == CC_MAPPER_WINDOWED ? mc.W : 1;
+  t->Ptot = t->W * mc.P;
+  t->S = t->Ptot + mc.K;
   t->T_max = mc.K + t->max_tokens;
   t->rows_m = B * t->S;
   t->rows_l = B * t->T_max;
@@ -169,8 +173,8 @@ int train_build(cc_train* t, const cc_tensor* w, int nw) {
   CC_TRY(A.alloc_t(&t->lin16, static_cast<size_t>(mc.P) * d * mc.E));
   const size_t rmax = rl > rm ? rl : rm;
   const size_t rows_pad = (rmax + 7) / 8 * 8;
-  const size_t b_pad = (static_cast<size_t>(B) + 7) / 8 * 8;
-  CC_TRY(A.alloc_t(&t->emb16, static_cast<size_t>(B) * mc.E));
+  const size_t b_pad = (static_cast<size_t>(B) * t->W + 7) / 8 * 8;  // rows of the input projection: (sample, window)
+  CC_TRY(A.alloc_t(&t->emb16, static_cast<size_t>(B) * t->W * mc.E));
   CC_TRY(A.alloc_t(&t->ln16, rmax * d));
   CC_TRY(A.alloc_t(&t->hid16, rmax * 4 * d));
   CC_TRY(A.alloc_t(&t->g16, rmax * d));
@@ -197,7 +201,7 @@ int train_build(cc_train* t, const cc_tensor* w, int nw) {
   {
     int widest = 2 * d;
     if (mc.K * d > widest) widest = mc.K * d;
-    if (mc.P * d > widest) widest = mc.P * d;
+    if (t->Ptot * d > widest) widest = t->Ptot * d;
     t->cs_floats = colsum_scratch_floats(widest);
     CC_TRY(A.alloc_t(&t->cs_scratch, t->cs_floats));
   }
@@ -209,7 +213,8 @@ int train_build(cc_train* t, const cc_tensor* w, int nw) {
   if (lin_b > b_elems) b_elems = lin_b;
   CC_TRY(A.alloc_t(&t->tr_a, a_elems));
   CC_TRY(A.alloc_t(&t->tr_b, b_elems));
-  CC_TRY(A.alloc_t(&t->dlin16, static_cast<size_t>(B) * mc.P * d));
+  CC_TRY(A.alloc_t(&t->dlin16, static_cast<size_t>(B) * t->Ptot * d));
+  CC_TRY(A.alloc_t(&t->pos_tmp, static_cast<size_t>(t->Ptot) * d));
   CC_TRY(A.alloc_t(&t->wqkv_grad, 3 * dd));
   return CC_OK;
 }
@@ -248,8 +253,10 @@ int cc_train_create(cc_train** h, const cc_mapper_cfg* mcfg, const cc_gpt2_cfg* 
              "cc_train_create: null argument");
   *h = nullptr;
   CC_TRY(check_device_sm100());
-  CC_REQUIRE(mcfg->kind == CC_MAPPER_TRANSFORMER, CC_ESHAPE,
-             "cc_train_create: only the (non-windowed) TransformerMapper is trainable here (kind %d)", mcfg->kind);
+  CC_REQUIRE(mcfg->kind == CC_MAPPER_TRANSFORMER || mcfg->kind == CC_MAPPER_WINDOWED, CC_ESHAPE,
+             "cc_train_create: the trainable mappers are TransformerMapper and TransformerMapperWindowed (kind %d)",
+             mcfg->kind);
+  if (mcfg->kind == CC_MAPPER_WINDOWED) CC_REQUIRE(mcfg->W >= 1, CC_ESHAPE, "cc_train_create: windowed mapper W=%d", mcfg->W);
   CC_REQUIRE(max_batch > 0 && max_tokens > 0, CC_EINVAL, "cc_train_create: max_batch=%d max_tokens=%d", max_batch, max_tokens);
   CC_REQUIRE(mcfg->d == gcfg->d, CC_ESHAPE, "cc_train_create: mapper width %d != LM width %d", mcfg->d, gcfg->d);
   CC_REQUIRE(gcfg->d % 8 == 0 && gcfg->d % gcfg->H == 0 && gcfg->d / gcfg->H == 64, CC_ESHAPE,
@@ -292,6 +299,8 @@ int cc_train_step(cc_train* t, const cc_tensor* params, int n_params, const cc_t
   const cc_mapper_cfg& mc = t->mc;
   const cc_gpt2_cfg& gc = t->gc;
   const int d = gc.d, S = t->S, K = mc.K, P = mc.P, T = K + Tt;
+  const int W = t->W, Ptot = t->Ptot;  // windowed mapper: W embeddings per sample -> W * P projected tokens (mapper.py:148-150)
+  const bool use_pos = mc.kind == CC_MAPPER_WINDOWED && mc.use_pos != 0;
   const int rows_m = B * S, rows_l = B * T, rows_sel = B * Tt;
   const int mhd = d / mc.H;
   const float mscale = 1.0f / sqrtf(static_cast<float>(mhd)), lscale = 0.125f;
@@ -306,6 +315,8 @@ int cc_train_step(cc_train* t, const cc_tensor* params, int n_params, const cc_t
   CC_TRY(dev_f32(params, n_params, "linear.weight", static_cast<int64_t>(P) * d * mc.E, &lin_w));
   CC_TRY(dev_f32(params, n_params, "linear.bias", static_cast<int64_t>(P) * d, &lin_b));
   CC_TRY(dev_f32(params, n_params, "prefix_const", static_cast<int64_t>(K) * d, &prefix_const));
+  const float* pos_emb = nullptr;
+  if (use_pos) CC_TRY(dev_f32(params, n_params, "pos_embeddings", static_cast<int64_t>(Ptot) * d, &pos_emb));
   CC_TRY(pack_weight_run(lin_w, P * d, mc.E, false, t->lin16, mc.E, s));
   std::vector<MapParams> mp(mc.L), mg(mc.L);
   for (int l = 0; l < mc.L; ++l) {
@@ -329,9 +340,13 @@ int cc_train_step(cc_train* t, const cc_tensor* params, int n_params, const cc_t
   }
 
   // ---------------------------------------------------------------- mapper forward (mapper.py:122-130)
-  CC_TRY(convert_to_f16_run(emb, emb_dtype, t->emb16, static_cast<int64_t>(B) * mc.E, s));
-  CC_TRY(gemm(t->emb16, mc.E, B, t->lin16, P * d, mc.E, EPI_F32, lin_b, t->hm, static_cast<int64_t>(S) * d, s, nl));
-  CC_TRY(mapper_fill_const_run(t->hm, prefix_const, nullptr, B, P, K, d, s));
+  // x = linear(emb).view(B, W * P, d) [+ pos_embeddings]; cat prefix_const (mapper.py:123-126 / 148-156). Window w of
+  // sample b lands at rows w*P .. of the sample's block: one GEMM per window (row stride S*d), as in cc_mapper_forward.
+  CC_TRY(convert_to_f16_run(emb, emb_dtype, t->emb16, static_cast<int64_t>(B) * W * mc.E, s));
+  for (int wdw = 0; wdw < W; ++wdw)
+    CC_TRY(gemm(t->emb16 + static_cast<size_t>(wdw) * mc.E, static_cast<int64_t>(W) * mc.E, B, t->lin16, P * d, mc.E, EPI_F32,
+                lin_b, t->hm + static_cast<size_t>(wdw) * P * d, static_cast<int64_t>(S) * d, s, nl));
+  CC_TRY(mapper_fill_const_run(t->hm, prefix_const, pos_emb, B, Ptot, K, d, s));
   *nl += 2;
   for (int l = 0; l < mc.L; ++l) {
     cc_train::MapLayer& M = t->mp[l];
@@ -350,7 +365,7 @@ int cc_train_step(cc_train* t, const cc_tensor* params, int n_params, const cc_t
 
   // ---------------------------------------------------------------- LM forward over [prefix, tokens] (model.py:45-56)
   CC_CUDA(cudaMemcpyAsync(t->tokens, tokens, sizeof(int32_t) * rows_sel, cudaMemcpyDefault, s));
-  CC_TRY(train_embed_run(t->tokens, B, Tt, K, t->hm + static_cast<size_t>(P) * d, static_cast<int64_t>(S) * d, t->wte32,
+  CC_TRY(train_embed_run(t->tokens, B, Tt, K, t->hm + static_cast<size_t>(Ptot) * d, static_cast<int64_t>(S) * d, t->wte32,
                          t->wpe32, t->h, t->targets, d, gc.V, s));
   *nl += 1;
   for (int l = 0; l < gc.L; ++l) {
@@ -420,10 +435,10 @@ int cc_train_step(cc_train* t, const cc_tensor* params, int n_params, const cc_t
   }
 
   // ---------------------------------------------------------------- mapper backward (activation + parameter gradients)
-  // d prefix = dh[:, :K]  ->  rows P.. of the mapper stream; rows 0..P-1 start at zero
+  // d prefix = dh[:, :K]  ->  rows W*P.. of the mapper stream; the projected-token rows start at zero
   float* dhm = t->hm;  // the mapper's stream buffer is free now (its layers are stashed): reuse it for the gradient
   CC_CUDA(cudaMemsetAsync(dhm, 0, hbytes_m, s));
-  CC_CUDA(cudaMemcpy2DAsync(dhm + static_cast<size_t>(P) * d, static_cast<size_t>(S) * d * sizeof(float), t->dh,
+  CC_CUDA(cudaMemcpy2DAsync(dhm + static_cast<size_t>(Ptot) * d, static_cast<size_t>(S) * d * sizeof(float), t->dh,
                             static_cast<size_t>(T) * d * sizeof(float), static_cast<size_t>(K) * d * sizeof(float), B,
                             cudaMemcpyDeviceToDevice, s));
   float* gl_w;
@@ -487,13 +502,28 @@ int cc_train_step(cc_train* t, const cc_tensor* params, int n_params, const cc_t
                              const_cast<float*>(g.n1_b), inv_scale, t->ln_scratch, s));
     *nl += 26;
   }
-  // ---- inputs of the transformer: x = cat(linear(emb).view(B, P, d), prefix_const)   (mapper.py:123-126)
-  CC_TRY(colsum_f32_run(dhm + static_cast<size_t>(P) * d, static_cast<int64_t>(S) * d, B, K * d, inv_scale, g_pc, t->cs_scratch, t->cs_floats, s));
-  CC_TRY(colsum_f32_run(dhm, static_cast<int64_t>(S) * d, B, P * d, inv_scale, gl_b, t->cs_scratch, t->cs_floats, s));
-  CC_TRY(convert_from_f32_run(dhm, static_cast<int64_t>(S) * d, t->dlin16, CC_F16, B, P * d, s));
-  const int bp_rows = (B + 7) / 8 * 8;
-  CC_TRY(transpose16_run(t->dlin16, static_cast<int64_t>(P) * d, B, P * d, t->tr_a, bp_rows, s));
-  CC_TRY(transpose16_run(t->emb16, mc.E, B, mc.E, t->tr_b, bp_rows, s));
+  // ---- inputs of the transformer: x = cat(linear(emb).view(B, W*P, d) [+ pos_embeddings], prefix_const)
+  //      (mapper.py:123-126 / 148-156). The W*P*d projected-token gradients of a sample are contiguous, so [B, W*P*d]
+  //      (row stride S*d) read as [(B*W), P*d] is the gradient of the linear layer's output in (sample, window) order —
+  //      the order of the embeddings.
+  CC_TRY(colsum_f32_run(dhm + static_cast<size_t>(Ptot) * d, static_cast<int64_t>(S) * d, B, K * d, inv_scale, g_pc, t->cs_scratch, t->cs_floats, s));
+  float* g_pos = t->pos_tmp;  // sum over the batch per (window, token, channel): IS the pos_embeddings gradient
+  if (use_pos) {
+    const float* gp;
+    CC_TRY(dev_f32(grads, n_grads, "pos_embeddings", static_cast<int64_t>(Ptot) * d, &gp));
+    g_pos = const_cast<float*>(gp);
+  }
+  CC_TRY(colsum_f32_run(dhm, static_cast<int64_t>(S) * d, B, Ptot * d, inv_scale, g_pos, t->cs_scratch, t->cs_floats, s));
+  if (W == 1) {
+    if (g_pos != gl_b) CC_CUDA(cudaMemcpyAsync(gl_b, g_pos, sizeof(float) * P * d, cudaMemcpyDeviceToDevice, s));
+  } else {  // the bias is shared by the windows: fold them
+    CC_TRY(colsum_f32_run(g_pos, static_cast<int64_t>(P) * d, W, P * d, 1.f, gl_b, t->cs_scratch, t->cs_floats, s));
+  }
+  CC_TRY(convert_from_f32_run(dhm, static_cast<int64_t>(S) * d, t->dlin16, CC_F16, B, Ptot * d, s));
+  const int bw = B * W;
+  const int bp_rows = (bw + 7) / 8 * 8;
+  CC_TRY(transpose16_run(t->dlin16, static_cast<int64_t>(P) * d, bw, P * d, t->tr_a, bp_rows, s));
+  CC_TRY(transpose16_run(t->emb16, mc.E, bw, mc.E, t->tr_b, bp_rows, s));
   CC_TRY(gemm(t->tr_a, bp_rows, P * d, t->tr_b, mc.E, bp_rows, EPI_F32, nullptr, gl_w, mc.E, s, nl));
   CC_TRY(scale_f32_run(gl_w, static_cast<int64_t>(P) * d * mc.E, inv_scale, s));
   *nl += 9;

@@ -8,6 +8,7 @@ named parameters (`visual.*`) and runs libclipcap_b200's cc_vit_forward. The ref
 """
 from __future__ import annotations
 
+import math
 import os
 import warnings
 from typing import Callable, Optional, Tuple
@@ -128,32 +129,86 @@ class CLIPModel(nn.Module):
 
 
 class TensorTransform:
-    """Minimal stand-in for CLIPTransform (clip.py:9-103, host-side PIL work, out of scope): takes a PIL image, a path
-    or a uint8/float tensor [3,H,W] and returns the CLIP-normalised [3,S,S] tensor (bicubic resize of the short side,
-    centre crop). Windowed tiling is not provided."""
+    """Stand-in for CLIPTransform (clip.py:9-103) on decoded images: takes a PIL image, a path or a uint8/float tensor
+    [3,H,W] and returns the CLIP-normalised [3,S,S] tensor (bicubic resize of the short side, centre crop). With
+    `use_windowed_embeddings` it returns [window_size + 1, 3, S, S] — the global view followed by the window tiles in
+    row-major order (clip.py:83-103): centre crop to a square (clip.py:35-47), bilinear resize to a multiple of the tile
+    grid (clip.py:49-58), window tiling on the device (cc_op_tile_image = the reference's unfold, clip.py:60-82), then the
+    same resize + normalisation per tile. File decoding (PIL) stays with the caller's data loader. What the reference's
+    own tile path does as committed cannot be reproduced literally: `image.convert("rgb")` (clip.py:70) raises, and its
+    Normalize / flatten act on the tile-x axis instead of the channels (clip.py:91,99); this follows the documented
+    intent — one CLIP-normalised image per tile."""
 
-    def __init__(self, image_size: int):
+    def __init__(self, image_size: int, use_windowed_embeddings: bool = False, window_size: Optional[int] = 9,
+                 window_overlap_percentage: float = 0.0, device="cuda"):
         self.image_size = image_size
+        self.use_windowed_embeddings = use_windowed_embeddings
+        self.window_size = window_size
+        self.window_overlap_percentage = window_overlap_percentage
+        self.device = device
+        if use_windowed_embeddings:  # clip.py:14-15
+            assert math.sqrt(window_size).is_integer(), \
+                "`window_size` must be a square number with CLIP, e.g. (3x3) = 9 for tiles of 3 by 3."
 
-    def __call__(self, image) -> torch.Tensor:
-        import torch.nn.functional as F
+    @staticmethod
+    def _decode(image) -> torch.Tensor:
         if isinstance(image, str):
             from PIL import Image
             image = Image.open(image)
         if not isinstance(image, torch.Tensor):
             import numpy as np
             image = torch.from_numpy(np.asarray(image.convert("RGB"))).permute(2, 0, 1)
-        x = image.float() / 255.0 if image.dtype == torch.uint8 else image.float()
+        return image.float() / 255.0 if image.dtype == torch.uint8 else image.float()
+
+    def _clip_view(self, x: torch.Tensor) -> torch.Tensor:
+        """[..., 3, H, W] in [0, 1] -> CLIP-normalised [..., 3, S, S]."""
+        import torch.nn.functional as F
         S = self.image_size
-        _, H, W = x.shape
+        lead = x.shape[:-3]
+        x = x.reshape(-1, *x.shape[-3:])
+        H, W = x.shape[-2:]
         s = S / min(H, W)
         nh, nw = max(S, round(H * s)), max(S, round(W * s))
-        x = F.interpolate(x[None], size=(nh, nw), mode="bicubic", align_corners=False, antialias=True)[0]
+        x = F.interpolate(x, size=(nh, nw), mode="bicubic", align_corners=False, antialias=True)
         t, l = (nh - S) // 2, (nw - S) // 2
-        x = x[:, t:t + S, l:l + S].clamp(0, 1)
-        mean = torch.tensor(CLIP_MEAN).view(3, 1, 1)
-        std = torch.tensor(CLIP_STD).view(3, 1, 1)
-        return (x - mean) / std
+        x = x[..., t:t + S, l:l + S].clamp(0, 1)
+        mean = torch.tensor(CLIP_MEAN, device=x.device).view(3, 1, 1)
+        std = torch.tensor(CLIP_STD, device=x.device).view(3, 1, 1)
+        return ((x - mean) / std).reshape(*lead, 3, S, S)
+
+    def tile_image(self, square: torch.Tensor) -> torch.Tensor:
+        """clip.py:60-82 on a decoded square image [3, S, S] (CUDA, fp32): -> [window_size, 3, p, p]."""
+        import ctypes as C  # noqa: F401
+        from clipcap_b200 import _ffi
+        if not square.is_cuda:
+            raise RuntimeError("clipcap_b200: window tiling runs on the device (there is no CPU path)")
+        size = square.shape[-1]
+        n = int(math.sqrt(self.window_size))
+        p = size // n
+        step = math.floor(p * (1 - self.window_overlap_percentage / 100)) if self.window_overlap_percentage != 0 else p
+        square = square.float().contiguous()
+        tiles = torch.empty(n * n, 3, p, p, device=square.device, dtype=torch.float32)
+        with torch.cuda.device(square.device):
+            _ffi.check(_ffi.lib().cc_op_tile_image(square.data_ptr(), size, n, p, step, tiles.data_ptr(),
+                                                   _ffi.current_stream_ptr()))
+        return tiles
+
+    def __call__(self, image) -> torch.Tensor:
+        import torch.nn.functional as F
+        x = self._decode(image)
+        if not self.use_windowed_embeddings:
+            return self._clip_view(x)
+        x = x.to(self.device)
+        _, H, W = x.shape
+        side = min(H, W)                                   # centre crop to a square, clip.py:35-47
+        t, l = (H - side) // 2, (W - side) // 2
+        sq = x[:, t:t + side, l:l + side]
+        n = int(math.sqrt(self.window_size))
+        target = math.ceil(side / n) * n                   # ensure_tileable, clip.py:49-58
+        if target != side:
+            sq = F.interpolate(sq[None], size=(target, target), mode="bilinear", align_corners=False)[0]
+        tiles = self.tile_image(sq)
+        return torch.cat((self._clip_view(x)[None], self._clip_view(tiles)), dim=0)  # clip.py:95-101
 
 
 def warn_random_init(what: str, env_var: str, allowed: bool) -> None:
@@ -186,7 +241,8 @@ def get_clip_encoder(encoder_model_variant: str, window_size: Optional[int] = No
         tower.load_state_dict(sd, strict=True)
     else:
         warn_random_init("CLIP " + encoder_model_variant, "CLIPCAP_B200_CLIP_WEIGHTS", allow_random_init)
-    transform = TensorTransform(image_size)
+    transform = TensorTransform(image_size, use_windowed_embeddings, window_size if window_size else 9,
+                                window_overlap_percentage, device)
     model = CLIPModel(tower, normalize_embeddings=normalize_embeddings, use_windowed_embeddings=use_windowed_embeddings)
     model = model.eval()
     model = model.to(device)

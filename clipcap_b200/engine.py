@@ -323,10 +323,14 @@ class TrainEngine(_Handle):
     _destroy_name = "cc_train_destroy"
 
     def __init__(self, lm_weights: Dict[str, torch.Tensor], E=768, d=1024, P=10, K=40, H=8, L=8, lm_layers=24,
-                 lm_heads=16, V=50257, n_pos=1024, eps=1e-5, max_batch=64, max_tokens=67, device="cuda"):
+                 lm_heads=16, V=50257, n_pos=1024, eps=1e-5, max_batch=64, max_tokens=67, device="cuda",
+                 kind="transformer", W=1, use_pos=False):
+        """kind "windowed" (TransformerMapperWindowed, mapper.py:133-160): embeddings are [B, W, E] (W = window_size + 1)
+        and `pos_embeddings` joins the parameters / gradients when `use_pos`."""
         super().__init__()
         self.device = torch.device(device)
-        self.mcfg = _ffi.cc_mapper_cfg(_ffi.CC_MAPPER_TRANSFORMER, E, d, P, K, H, L, 1, 0, eps)
+        self.kind = kind
+        self.mcfg = _ffi.cc_mapper_cfg(MapperEngine.KINDS[kind], E, d, P, K, H, L, W, int(bool(use_pos)), eps)
         self.gcfg = _ffi.cc_gpt2_cfg(d, lm_layers, lm_heads, V, n_pos, eps)
         self.max_batch, self.max_tokens = max_batch, max_tokens
         with torch.cuda.device(self.device):
@@ -342,8 +346,9 @@ class TrainEngine(_Handle):
         with d loss / d param. No host synchronisation."""
         _require_cuda(emb, "embeddings")
         _require_cuda(tokens, "tokens")
-        if emb.dim() != 2 or emb.shape[1] != self.mcfg.E:
-            raise ValueError(f"embeddings must be [B, {self.mcfg.E}], got {tuple(emb.shape)}")
+        want = (self.mcfg.W, self.mcfg.E) if self.kind == "windowed" else (self.mcfg.E,)
+        if tuple(emb.shape[1:]) != want:
+            raise ValueError(f"embeddings must be [B, {', '.join(map(str, want))}], got {tuple(emb.shape)}")
         if tokens.dim() != 2 or tokens.shape[0] != emb.shape[0]:
             raise ValueError(f"tokens must be [B, Tt] with B = {emb.shape[0]}, got {tuple(tokens.shape)}")
         for name, t in list(params.items()) + list((grads or {}).items()):

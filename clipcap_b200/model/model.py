@@ -135,8 +135,6 @@ class ClipCapModelPrefixOnly(ClipCapModel):
 
     def _train_engine_for(self, batch: int, n_tokens: int) -> TrainEngine:
         lm, mp = self.language_model, self.transformer_mapper
-        if isinstance(mp, TransformerMapperWindowed):
-            raise NotImplementedError("training the windowed mapper is not implemented in clipcap_b200")
         dev = next(mp.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError(f"clipcap_b200: model is on {dev}; move it to a B200 (`.to('cuda')`) — there is no CPU path")
@@ -150,7 +148,8 @@ class ClipCapModelPrefixOnly(ClipCapModel):
         cap = (max(batch, cap[0]), max(n_tokens, cap[1]))
         eng = TrainEngine(lm.state_dict(), E=mp.encoder_embedding_size, d=mp.lm_embedding_size, P=mp.projection_length,
                           K=mp.prefix_length, H=mp.num_heads, L=mp.num_layers, lm_layers=lm.n_layer, lm_heads=lm.n_head,
-                          V=lm.vocab_size, n_pos=lm.n_positions, max_batch=cap[0], max_tokens=cap[1], device=dev)
+                          V=lm.vocab_size, n_pos=lm.n_positions, max_batch=cap[0], max_tokens=cap[1], device=dev,
+                          kind=mp.kind, W=mp.window_size, use_pos=mp.use_pos)
         object.__setattr__(self, "_train_engine", eng)
         object.__setattr__(self, "_train_key", key)
         object.__setattr__(self, "_train_cap", cap)

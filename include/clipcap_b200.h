@@ -261,6 +261,13 @@ int cc_op_attention(const void* q, const void* k, const void* v, int64_t ld, voi
                     int hd, int causal, float scale, void* stream);
 int cc_op_decode_attention(const void* qkv, void* kcache, void* vcache, const int32_t* anc, void* o, int nseq, int H,
                            int t_max, int pos, float scale, void* stream);
+/* Window tiling of a decoded square image (CLIPTransform.tile_image, clipcap/encoders/clip.py:60-82:
+ * tensor.unfold(1, p, step).unfold(2, p, step)): image [3, size, size] fp32 on the device ->
+ * tiles [tiles_per_axis^2, 3, p, p], tile (ty, tx) = pixels [ty*step, ty*step + p) x [tx*step, tx*step + p), row-major over
+ * (ty, tx). step = p without overlap, floor(p * (1 - overlap / 100)) with (clip.py:65-68). */
+int cc_op_tile_image(const float* image, int size, int tiles_per_axis, int pixels_per_tile, int step, float* tiles,
+                     void* stream);
+
 /* One sampling step (the token-selection kernel of the NUCLEUS / SAMPLE modes) on given logits [rows, V] fp32:
  * tokens[row * entry_length + step] receives the draw; stopped / lengths [rows] int32 are updated; cfg->history is a
  * DEVICE pointer here. Used by the distribution tests. */

@@ -115,9 +115,13 @@ def _mapper_attention(x, wq, wkv, wp, bp, H):
     return out @ wp.t() + bp                                   # :41
 
 
-def mapper_forward(w: Weights, emb: torch.Tensor, cfg: MapperCfg) -> torch.Tensor:
+def mapper_forward(w: Weights, emb: torch.Tensor, cfg: MapperCfg, relu_mask_fp16: bool = False) -> torch.Tensor:
     """TransformerMapper.forward (clipcap/model/mapper.py:122-130) / TransformerMapperWindowed.forward (:148-160) /
-    upstream MLP mapper. Keys are relative to `transformer_mapper.`."""
+    upstream MLP mapper. Keys are relative to `transformer_mapper.`.
+    `relu_mask_fp16` (test instrument, not reference behaviour): the ReLU of the MLP keeps a hidden unit according to the
+    pre-activation computed from fp16-ROUNDED operands — the decision a kernel with fp16 GEMM operands takes — while
+    values and gradients stay fp32. Used to show that the gradient error behind the ReLU mask comes from units whose
+    pre-activation is within operand rounding of zero, not from the arithmetic."""
     B = emb.shape[0]
     if cfg.kind == "mlp":
         h = torch.tanh(emb @ w["model.0.weight"].t() + w["model.0.bias"])
@@ -133,7 +137,13 @@ def mapper_forward(w: Weights, emb: torch.Tensor, cfg: MapperCfg) -> torch.Tenso
         x = x + _mapper_attention(y, w[p + "attn.to_queries.weight"], w[p + "attn.to_keys_values.weight"],
                                   w[p + "attn.project.weight"], w[p + "attn.project.bias"], cfg.H)   # :108
         y = _ln(x, w[p + "norm2.weight"], w[p + "norm2.bias"], cfg.eps)
-        y = torch.relu(y @ w[p + "mlp.fc1.weight"].t() + w[p + "mlp.fc1.bias"])                       # :82-84
+        pre = y @ w[p + "mlp.fc1.weight"].t() + w[p + "mlp.fc1.bias"]
+        if relu_mask_fp16:
+            with torch.no_grad():
+                keep = (y.half().float() @ w[p + "mlp.fc1.weight"].half().float().t() + w[p + "mlp.fc1.bias"]) > 0
+            y = pre * keep
+        else:
+            y = torch.relu(pre)                                                                       # :82-84
         x = x + y @ w[p + "mlp.fc2.weight"].t() + w[p + "mlp.fc2.bias"]                               # :86, :109
     return x[:, Ptot:]                                                             # :128 / :158
 
@@ -323,7 +333,7 @@ def generate_sampling(w: Weights, cfg: Gpt2Cfg, embeds: torch.Tensor, mode: str,
 
 # ------------------------------------------------------------------------------------------------ training step
 def training_loss(map_w: Weights, lm_w: Weights, mcfg: MapperCfg, gcfg: Gpt2Cfg, tokens: torch.Tensor,
-                  emb: torch.Tensor) -> torch.Tensor:
+                  emb: torch.Tensor, relu_mask_fp16: bool = False) -> torch.Tensor:
     """ClipCapModel.training_step (clipcap/model/model.py:94-113) with forward (model.py:43-58): tokens [B, Tt] int64 with
     -1 padding, emb [B, E]. Differentiable in map_w (torch autograd) — the gradient oracle of cc_train_step.
     The padding mask (model.py:52-56) is not applied: with trailing padding and a causal LM no scored position can see a
@@ -332,7 +342,7 @@ def training_loss(map_w: Weights, lm_w: Weights, mcfg: MapperCfg, gcfg: Gpt2Cfg,
     mask = tokens.ge(0)                                              # :103
     tokens[~mask] = 0                                                # :104
     token_embeddings = lm_w["transformer.wte.weight"][tokens]        # :45
-    prefix = mapper_forward(map_w, emb, mcfg)                        # :46
+    prefix = mapper_forward(map_w, emb, mcfg, relu_mask_fp16)        # :46
     inputs = torch.cat((prefix, token_embeddings), dim=1)            # :49
     logits = gpt2_logits(lm_w, inputs, gcfg)                         # :56
     logits = logits[:, mcfg.K - 1:-1]                                # :109
@@ -340,10 +350,10 @@ def training_loss(map_w: Weights, lm_w: Weights, mcfg: MapperCfg, gcfg: Gpt2Cfg,
 
 
 def training_loss_and_grads(map_w: Weights, lm_w: Weights, mcfg: MapperCfg, gcfg: Gpt2Cfg, tokens: torch.Tensor,
-                            emb: torch.Tensor) -> Tuple[float, Dict[str, torch.Tensor]]:
+                            emb: torch.Tensor, relu_mask_fp16: bool = False) -> Tuple[float, Dict[str, torch.Tensor]]:
     """loss.backward() of the step above for ClipCapModelPrefixOnly (model.py:116-123): gradients of every mapper tensor."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in map_w.items()}
-    loss = training_loss(leaves, lm_w, mcfg, gcfg, tokens, emb)
+    loss = training_loss(leaves, lm_w, mcfg, gcfg, tokens, emb, relu_mask_fp16)
     loss.backward()
     return float(loss.detach()), {k: v.grad.detach() for k, v in leaves.items()}
 

@@ -103,6 +103,37 @@ def test_model_forward_matches_golden(cuda_device, name):
     assert rel_err(out2.logits[:, :keep], want[:, :keep]) < 1e-3
 
 
+@pytest.mark.parametrize("size,window_size,overlap", [(224, 9, 0.0), (300, 16, 0.0), (257, 4, 25.0), (96, 9, 10.0)])
+def test_window_tiling_equals_reference_unfold(cuda_device, size, window_size, overlap):
+    """cc_op_tile_image against the reference's own tiling arithmetic (CLIPTransform.tile_image, clipcap/encoders/clip.py:
+    60-82: tensor.unfold(1, p, step).unfold(2, p, step), step from the overlap percentage), bit for bit, and the whole
+    windowed transform's output layout [window_size + 1, 3, S, S] (clip.py:95-101) feeding the windowed encoder call."""
+    import math
+    from clipcap_b200.encoders.clip import TensorTransform
+    n = int(math.sqrt(window_size))
+    img = torch.rand(3, size, size, generator=torch.Generator().manual_seed(size))
+    tr = TensorTransform(28, use_windowed_embeddings=True, window_size=window_size, window_overlap_percentage=overlap,
+                         device=cuda_device)
+    target = math.ceil(size / n) * n
+    sq = img if target == size else torch.nn.functional.interpolate(img[None], size=(target, target), mode="bilinear",
+                                                                    align_corners=False)[0]
+    p = target // n
+    step = math.floor(p * (1 - overlap / 100)) if overlap != 0 else p
+    ref = sq.unfold(1, p, step).unfold(2, p, step)[:, :n, :n]          # [3, ny, nx, p, p]   (clip.py:73-80)
+    want = ref.permute(1, 2, 0, 3, 4).reshape(n * n, 3, p, p)            # tile-major, channels inside each tile
+    got = tr.tile_image(sq.to(cuda_device))
+    assert torch.equal(got.cpu(), want)
+    out = tr(img)
+    assert tuple(out.shape) == (window_size + 1, 3, 28, 28) and out.is_cuda
+    plain = TensorTransform(28)
+    assert rel_err(out[0], plain(img)) < 1e-5                            # global view first (clip.py:97-99)
+    assert rel_err(out[1], plain(want[0])) < 1e-5                        # then the tiles, each a CLIP-normalised image
+    with pytest.raises(RuntimeError):
+        tr.tile_image(sq)                                                # CPU tensor: no CPU path
+    with pytest.raises(AssertionError):
+        TensorTransform(28, use_windowed_embeddings=True, window_size=8)  # clip.py:14-15
+
+
 def test_get_encoder_errors():
     import clipcap_b200 as clipcap
     with pytest.raises(ValueError, match="invalid encoder name"):

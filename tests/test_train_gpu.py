@@ -26,10 +26,15 @@ def _cos(a, b):
 def _engine(gcfg, mcfg, lm_w, B, Tt, dev):
     from clipcap_b200.engine import TrainEngine
     return TrainEngine(lm_w, E=mcfg.E, d=mcfg.d, P=mcfg.P, K=mcfg.K, H=mcfg.H, L=mcfg.L, lm_layers=gcfg.L, lm_heads=gcfg.H,
-                       V=gcfg.V, n_pos=gcfg.n_pos, max_batch=B, max_tokens=Tt, device=dev)
+                       V=gcfg.V, n_pos=gcfg.n_pos, max_batch=B, max_tokens=Tt, device=dev,
+                       kind=getattr(mcfg, "kind", "transformer"), W=getattr(mcfg, "W", 1),
+                       use_pos=getattr(mcfg, "use_pos", False))
 
 
-def _check_grads(got, want, tol=GRAD_TOL):
+def _check_grads(got, want, tol=GRAD_TOL, gated_tol=None, cos_min=COS_MIN):
+    """Per tensor: ||a-b|| / ||b|| < tol and cosine > cos_min; element-wise max error < tol except behind the ReLU mask.
+    `gated_tol`: separate norm tolerance for the ReLU-gated tensors (tiny batches, where one flipped unit is a visible
+    share of the gradient)."""
     assert set(got) == set(want)
     worst = 0.0
     for k in sorted(want):
@@ -37,8 +42,10 @@ def _check_grads(got, want, tol=GRAD_TOL):
         e, c = rel_err(a, b), _cos(a, b)
         l2 = float((a - b).norm() / b.norm().clamp_min(1e-30))
         worst = max(worst, l2)
-        assert l2 < tol and c > COS_MIN, f"{k}: norm err {l2:.3e}, cosine {c:.6f}"
-        if not k.endswith(RELU_GATED):
+        gated = k.endswith(RELU_GATED)
+        lim = gated_tol if (gated and gated_tol is not None) else tol
+        assert l2 < lim and c > (cos_min if not gated or gated_tol is None else 0.998), f"{k}: norm err {l2:.3e}, cosine {c:.6f}"
+        if not gated:
             assert e < tol, f"{k}: max element err {e:.3e}"
     return worst
 
@@ -88,6 +95,22 @@ def test_train_step_gpt2_small_shapes(cuda_device):
     loss = eng.step(params, emb.to(cuda_device), tokens.to(cuda_device), grads)
     assert abs(float(loss) - want_loss) < LOSS_TOL * abs(want_loss)
     _check_grads(grads, want)
+    # The ReLU-mask claim at the width where it shows (see test_relu_mask_explains_the_gated_gradient_error): against the
+    # oracle that takes the mask decisions of fp16-rounded operands, the gated tensors are as close as the others.
+    _, masked = R.training_loss_and_grads(map_w, lm_w, mcfg, gcfg, tokens, emb, relu_mask_fp16=True)
+
+    def l2(a, b):
+        return float((a.float().cpu() - b).norm() / b.norm().clamp_min(1e-30))
+
+    gated = [k for k in want if k.endswith(RELU_GATED)]
+    worst_plain = max(l2(grads[k], want[k]) for k in gated)
+    worst_masked = max(l2(grads[k], masked[k]) for k in gated)
+    worst_other = max(l2(grads[k], want[k]) for k in want if k not in gated)
+    print(f"GPT-2-small width: gated tensors vs fp32 oracle {worst_plain:.2e}, vs oracle with fp16-operand mask "
+          f"{worst_masked:.2e}; other tensors {worst_other:.2e}")
+    # The emulated mask only knows the rounding of the fc1 operands, not the (1e-3-level) differences of the LayerNorm
+    # output that feeds them, so some border units still differ: the error must shrink, not vanish.
+    assert worst_masked < worst_plain and worst_masked < 2e-2, (worst_plain, worst_masked, worst_other)
 
 
 @pytest.mark.parametrize("cfg", [(2, 107, 16, 64, 1), (3, 50, 8, 128, 0), (2, 33, 4, 96, 0), (1, 160, 2, 64, 1),
@@ -191,6 +214,92 @@ def test_training_step_api_drop_in(cuda_device):
         prefix = model.transformer_mapper(emb.to(cuda_device))
     want = R.mapper_forward({k: v.detach() for k, v in ref_p.items()}, emb, mcfg)
     assert rel_err(prefix, want) < 3e-3
+
+
+@pytest.mark.parametrize("use_pos", [True, False])
+def test_windowed_mapper_train_step_matches_oracle(cuda_device, use_pos):
+    """training_step + backward with TransformerMapperWindowed (clipcap/model/mapper.py:133-160 under model.py:22-32,
+    94-113): W = window_size + 1 embeddings per sample, the linear layer shared by the windows, the optional learned
+    pos_embeddings (gradient = batch sum of the projected-token gradients). The oracle side of this case is pinned against
+    the reference's own training_step + backward (tests/test_train_cpu.py, same seeds and shapes)."""
+    gcfg = R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64)
+    mcfg = R.MapperCfg(kind="windowed", E=64, d=128, P=3, K=5, H=2, L=2, W=3, use_pos=use_pos)
+    map_w, lm_w = synth.mapper_weights(mcfg, seed=61), synth.gpt2_weights(gcfg, seed=62, wte_std=0.1)
+    emb = synth.embeddings(9, 64, seed=63).view(3, 3, 64)
+    tokens = torch.randint(1, gcfg.V, (3, 9), generator=torch.Generator().manual_seed(64))
+    tokens[1, 6:] = -1
+    tokens[2, 2:] = -1
+    want_loss, want = R.training_loss_and_grads(map_w, lm_w, mcfg, gcfg, tokens, emb)
+    assert ("pos_embeddings" in want) == use_pos
+    eng = _engine(gcfg, mcfg, lm_w, 3, 9, cuda_device)
+    params = {k: v.to(cuda_device).contiguous() for k, v in map_w.items()}
+    grads = {k: torch.full_like(v, float("nan")) for k, v in params.items()}
+    loss = eng.step(params, emb.to(cuda_device), tokens.to(cuda_device), grads)
+    assert abs(float(loss) - want_loss) < LOSS_TOL * abs(want_loss)
+    _check_grads(grads, want, gated_tol=6e-2)   # 3 samples x 14 tokens: one flipped hidden unit is ~4 % of fc1.bias' gradient
+    # forward only (validation): same loss, no gradient buffers touched
+    assert abs(float(eng.step(params, emb.to(cuda_device), tokens.to(cuda_device))) - want_loss) < LOSS_TOL * abs(want_loss)
+    with pytest.raises(ValueError):
+        eng.step(params, emb[:, 0].to(cuda_device), tokens.to(cuda_device), grads)   # [B, E] is not a windowed input
+
+
+@pytest.mark.parametrize("name", list(LM_CASES))
+def test_relu_mask_explains_the_gated_gradient_error(cuda_device, name):
+    """The tensors directly behind the ReLU mask (mlp.fc1.*, norm2.*) carry 1-4e-2 gradient error against the fp32 oracle
+    while every other tensor is at 2-6e-3. Claim: a hidden unit whose pre-activation is within fp16 operand rounding of
+    zero takes the other branch. Proof: give the ORACLE the mask decisions of fp16-rounded operands (values and gradients
+    still fp32, oracle/restate.py relu_mask_fp16) — the gated tensors then agree as well as all the others."""
+    spec, gcfg, mcfg, map_w, lm_w, tokens, emb, *_ = load_train_case(name)
+    eng = _engine(gcfg, mcfg, lm_w, tokens.shape[0], tokens.shape[1], cuda_device)
+    params = {k: v.to(cuda_device).contiguous() for k, v in map_w.items()}
+    grads = {k: torch.empty_like(v) for k, v in params.items()}
+    eng.step(params, emb.to(cuda_device), tokens.to(cuda_device), grads)
+    _, plain = R.training_loss_and_grads(map_w, lm_w, mcfg, gcfg, tokens, emb)
+    _, masked = R.training_loss_and_grads(map_w, lm_w, mcfg, gcfg, tokens, emb, relu_mask_fp16=True)
+
+    def l2(a, b):
+        return float((a.float().cpu() - b).norm() / b.norm().clamp_min(1e-30))
+
+    gated = [k for k in plain if k.endswith(RELU_GATED)]
+    worst_plain = max(l2(grads[k], plain[k]) for k in gated)
+    worst_masked = max(l2(grads[k], masked[k]) for k in gated)
+    worst_other = max(l2(grads[k], plain[k]) for k in plain if k not in gated)
+    print(f"{name}: gated tensors vs fp32 oracle {worst_plain:.2e}, vs oracle with fp16-operand mask {worst_masked:.2e}; "
+          f"other tensors {worst_other:.2e}")
+    assert worst_masked < 8e-3, worst_masked
+    assert worst_other < 8e-3, worst_other
+
+
+def test_windowed_model_training_step_api(cuda_device):
+    """ClipCapModelPrefixOnly with use_windowed_embeddings (model.py:22-32): training_step -> backward -> optimizer step
+    through the module API, loss against the oracle."""
+    from clipcap_b200.encoders.config import EncoderConfig
+    from clipcap_b200.model import ClipCapModelPrefixOnly, Config, TrainingConfig
+    gcfg = R.Gpt2Cfg(d=128, L=2, H=2, V=1003, n_pos=64)
+    mcfg = R.MapperCfg(kind="windowed", E=64, d=128, P=3, K=5, H=2, L=2, W=3, use_pos=True)
+    map_w, lm_w = synth.mapper_weights(mcfg, seed=61), synth.gpt2_weights(gcfg, seed=62, wte_std=0.1)
+    cfg = Config(language_model="tiny:128:2:2:1003:64", prefix_length=5, projection_length=3, transformer_layers=2,
+                 transformer_attention_heads=2, use_positional_embeddings=True,
+                 encoder_config=EncoderConfig(encoder_embedding_size=64, use_windowed_embeddings=True, window_size=2))
+    model = ClipCapModelPrefixOnly(cfg)
+    sd = {f"transformer_mapper.{k}": v for k, v in map_w.items()}
+    sd.update({f"language_model.{k}": v for k, v in lm_w.items()})
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda_device).train()
+    model.set_training_config(TrainingConfig(optimizer_lr=1e-3, use_deepspeed_optimisers=False, scheduler_warmup_steps=0,
+                                             total_steps=4))
+    opt = model.configure_optimizers()["optimizer"]
+    emb = synth.embeddings(9, 64, seed=63).view(3, 3, 64)
+    tokens = torch.randint(1, gcfg.V, (3, 9), generator=torch.Generator().manual_seed(64))
+    want_loss, _ = R.training_loss_and_grads(map_w, lm_w, mcfg, gcfg, tokens, emb)
+    loss = model.training_step((tokens.clone().to(cuda_device), emb.to(cuda_device)), 0)
+    assert abs(float(loss) - want_loss) < LOSS_TOL * abs(want_loss)
+    opt.zero_grad()
+    loss.backward()
+    assert model.transformer_mapper.pos_embeddings.grad is not None
+    opt.step()
+    loss2 = model.training_step((tokens.clone().to(cuda_device), emb.to(cuda_device)), 1)
+    assert float(loss2) < float(loss)   # one AdamW step on the same batch lowers its loss
 
 
 def test_optimizer_step_invalidates_cached_engines(cuda_device):
