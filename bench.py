@@ -37,14 +37,16 @@ MODEL_KEYS = dict(entry_length=ENTRY_LENGTH, lm="gpt2-medium", encoder="ViT-L/14
 WORKLOADS = {
     "caption": dict(
         metric="captions/sec (224x224 bs=256, 20-tok greedy)", unit="captions/s", batch=256, mode="greedy", beam=1,
+        partition_sms=DEFAULT_PARTITION_SMS,
         workload="configs[1]: ViT-L/14 -> TransformerMapper(L=8,K=40,P=10,H=8) -> GPT-2-medium, 224x224, bs=256 per GPU, "
                  "20-token greedy decode"),
     "vit_only": dict(
         metric="images/sec (ViT-L/14 encode-only, bs=1024 over 8 GPUs)", unit="images/s", batch=128, mode=None, beam=1,
+        partition_sms=0,
         workload="configs[2]: ViT-L/14 encode-only, 224x224, bs=1024 synthetic images sharded over 8 GPUs = 128 per GPU"),
     "beam5": dict(
         metric="captions/sec (224x224 bs=2048 over 8 GPUs, beam=5, 20 tokens)", unit="captions/s", batch=256, mode="beam",
-        beam=5,
+        beam=5, partition_sms=0,
         workload="configs[3]: ViT-L/14 -> TransformerMapper(L=8,K=40,P=10,H=8) -> GPT-2-medium, bs=2048 over 8 GPUs = 256 "
                  "per GPU, beam=5, 20 tokens, NCCL prefix all-gather"),
 }
@@ -58,9 +60,9 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="caption", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
-    ap.add_argument("--partition-sms", type=int, default=int(os.environ.get("CLIPCAP_B200_PARTITION_SMS",
-                                                                              DEFAULT_PARTITION_SMS)),
-                    help="SMs of the decode partition (0 = one stream, no SM partitioning)")
+    ap.add_argument("--partition-sms", type=int, default=int(os.environ.get("CLIPCAP_B200_PARTITION_SMS", "-1")),
+                    help="SMs of the decode partition (0 = one stream, no SM partitioning; default: the workload's — 32 for "
+                         "the greedy caption step, 0 for beam-5, whose 1280-row decode is throughput-bound like the rest)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the prefix all-gather (attribution runs)")
     ap.add_argument("--cpu-captions", type=int, default=12, help="captions timed for the cpu_baseline sample")
@@ -338,7 +340,7 @@ def run_b200(args):
     tok_host = torch.empty(B, ENTRY_LENGTH, dtype=torch.int32).pin_memory()
     len_host = torch.empty(B, dtype=torch.int32).pin_memory()
     emb_host = torch.empty(B, 768, dtype=torch.float32).pin_memory()
-    partition_sms = 0 if vit_only else max(0, args.partition_sms)
+    partition_sms = 0 if vit_only else (w["partition_sms"] if args.partition_sms < 0 else args.partition_sms)
     pipe, partition_note = None, None
     if not vit_only:
         try:
@@ -470,10 +472,18 @@ def run_b200(args):
         import ctypes as C
         lib.cc_prof_enable(1)
         for _ in range(2):
-            encode_fn(px_dev)
+            emb_p = encode_fn(px_dev)
+            if not vit_only:
+                model.transformer_mapper(emb_p)
         torch.cuda.synchronize()
         ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
         lib.cc_prof_read(C.byref(ms), C.byref(fl), C.byref(n))
+        families = {}
+        for bn, label in ((512, "pair_256x256"), (256, "128x256"), (128, "128x128"), (64, "128x64"), (32, "128x32")):
+            fm, ff, fn = C.c_double(), C.c_double(), C.c_longlong()
+            lib.cc_prof_read_family(bn, C.byref(fm), C.byref(ff), C.byref(fn))
+            if fn.value > 0 and fm.value > 0:
+                families[label] = {"launches": fn.value, "ms": fm.value, "tflops": ff.value / (fm.value * 1e-3) / 1e12}
         lib.cc_prof_enable(0)
         if n.value > 0 and ms.value > 0:
             ach = fl.value / (ms.value * 1e-3) / 1e12
@@ -487,7 +497,8 @@ def run_b200(args):
                     "kernel": "gemm_tn_kernel<256,*,2> (tcgen05 cta_group::2, 256x256 CTA-pair tile) over the ViT-L/14 block GEMMs",
                     "launches_timed": n.value, "avg_launch_ms": ms.value / n.value,
                     "flops_per_launch": fl.value / n.value, "peak_source": peaks["source"] + ", sustained bf16",
-                    "timed": "two image-tower passes on the whole device right after the timed steps (same process)"}
+                    "timed": "two image-tower (+ mapper) passes on the whole device right after the timed steps (same process)",
+                    "gemm_families": families}
 
     if rank != 0:
         if world > 1:

@@ -106,6 +106,7 @@ PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {
     "cc_get_sm_budget": (_i, []),
     "cc_prof_enable": (None, [_i]),
     "cc_prof_read": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "cc_prof_read_family": (None, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "cc_op_gemm": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "cc_op_layernorm": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _vp]),
     "cc_op_attention": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp]),
@@ -116,6 +117,7 @@ PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {
     "cc_op_sample": (_i, [_vp, _i, _i, C.POINTER(cc_gen_cfg), _i, _vp, _vp, _vp, _vp]),
     "cc_train_create": (_i, [_pp, C.POINTER(cc_mapper_cfg), C.POINTER(cc_gpt2_cfg), C.POINTER(cc_tensor), _i, _i, _i]),
     "cc_train_step": (_i, [_vp, C.POINTER(cc_tensor), _i, C.POINTER(cc_tensor), _i, _vp, _i, _vp, _i, _i, _f, _vp, _vp]),
+    "cc_train_last_nonfinite": (_i, [_vp, _vp]),
     "cc_train_last_launches": (_i, [_vp]),
     "cc_train_destroy": (None, [_vp]),
     "cc_op_adamw": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp]),

@@ -21,6 +21,11 @@ void cc_prof_read(double* ms, double* flops, long long* n) {
   cc::gemm_prof_read(ms, flops, n);
 }
 
+void cc_prof_read_family(int bn, double* ms, double* flops, long long* n) {
+  if (ms == nullptr || flops == nullptr || n == nullptr) return;
+  cc::gemm_prof_read_family(bn, ms, flops, n);
+}
+
 int cc_op_gemm(const void* a, int64_t lda, const void* w, const float* bias, void* out, int64_t ldc, int M, int N, int K,
                int epi, int bn, void* stream) {
   using namespace cc;

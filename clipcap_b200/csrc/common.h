@@ -183,6 +183,7 @@ int gemm_pick_bn(int M, int N, int K);
 // Live timing of GEMM launches with CUDA events on the launching stream (cc_prof_*; bench.py's roofline figure).
 void gemm_prof_enable(bool on);
 void gemm_prof_read(double* ms, double* flops, long long* n);
+void gemm_prof_read_family(int bn, double* ms, double* flops, long long* n);
 
 // pack(acc, n) used by EPI_ARGMAX: high 32 bits = order-preserving float key, low 32 bits = ~n (ties -> lowest index)
 __host__ __device__ inline uint32_t argmax_key_index(unsigned long long key) { return ~static_cast<uint32_t>(key); }

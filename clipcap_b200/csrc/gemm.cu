@@ -817,14 +817,16 @@ void gemm_prof_enable(bool on) {
   g_prof_on = on;
 }
 
-// Sums duration / algorithmic FLOPs (2*M*N*K) over the recorded launches of the 128x256 tile (the dominant kernel).
-void gemm_prof_read(double* ms, double* flops, long long* n) {
+// Sums duration / algorithmic FLOPs (2*M*N*K) over the recorded launches of one tile family: bn = 512 the 256 x 256 CTA-pair
+// tile, 256 / 128 / 64 / 32 the single-CTA tiles of that width, 0 every launch, -1 the big tiles (256 and 512: the
+// dominant kernel of the bench's roofline figure).
+void gemm_prof_read_family(int bn, double* ms, double* flops, long long* n) {
   *ms = 0;
   *flops = 0;
   *n = 0;
   cudaDeviceSynchronize();
   for (auto& r : g_prof) {
-    if (r.bn != 256 && r.bn != 512) continue;
+    if (bn == -1 ? (r.bn != 256 && r.bn != 512) : (bn != 0 && r.bn != bn)) continue;
     float t = 0.f;
     if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) continue;
     *ms += t;
@@ -832,6 +834,8 @@ void gemm_prof_read(double* ms, double* flops, long long* n) {
     *n += 1;
   }
 }
+
+void gemm_prof_read(double* ms, double* flops, long long* n) { gemm_prof_read_family(-1, ms, flops, n); }
 
 int gemm_run(const GemmPlan& p, int M, cudaStream_t s, int row0) {
   CC_REQUIRE(M > 0 && row0 >= 0 && row0 + M <= p.max_rows, CC_ESHAPE, "gemm_run: rows %d..%d outside plan (max %d)", row0,

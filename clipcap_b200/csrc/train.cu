@@ -19,6 +19,7 @@ struct cc_train {
   int max_batch = 0, max_tokens = 0;
   int S = 0, T_max = 0, rows_m = 0, rows_l = 0, rows_sel = 0, v_pad = 0, head_chunk = 0;
   int W = 1, Ptot = 0;      // windows per sample (TransformerMapperWindowed: window_size + 1) and projected tokens W * P
+  int* nonfinite = nullptr;   // device counter: non-finite gradient elements of the last step with gradients
   float* pos_tmp = nullptr;  // [Ptot * d] column sums of the projected-token gradients (pos_embeddings gradient / bias fold)
   cc::Arena arena;
   // ---- frozen language model
@@ -215,6 +216,8 @@ int train_build(cc_train* t, const cc_tensor* w, int nw) {
   CC_TRY(A.alloc_t(&t->tr_b, b_elems));
   CC_TRY(A.alloc_t(&t->dlin16, static_cast<size_t>(B) * t->Ptot * d));
   CC_TRY(A.alloc_t(&t->pos_tmp, static_cast<size_t>(t->Ptot) * d));
+  CC_TRY(A.alloc_t(&t->nonfinite, 1));
+  CC_CUDA(cudaMemset(t->nonfinite, 0, sizeof(int)));
   CC_TRY(A.alloc_t(&t->wqkv_grad, 3 * dd));
   return CC_OK;
 }
@@ -527,7 +530,25 @@ int cc_train_step(cc_train* t, const cc_tensor* params, int n_params, const cc_t
   CC_TRY(gemm(t->tr_a, bp_rows, P * d, t->tr_b, mc.E, bp_rows, EPI_F32, nullptr, gl_w, mc.E, s, nl));
   CC_TRY(scale_f32_run(gl_w, static_cast<int64_t>(P) * d * mc.E, inv_scale, s));
   *nl += 9;
+  // overflow check: every gradient tensor handed back is scanned once (75 M floats at the benchmark mapper: ~0.1 ms)
+  CC_CUDA(cudaMemsetAsync(t->nonfinite, 0, sizeof(int), s));
+  for (int i = 0; i < n_grads; ++i) {
+    int64_t numel = 1;
+    for (int k = 0; k < grads[i].ndim; ++k) numel *= grads[i].shape[k];
+    CC_TRY(count_nonfinite_run(static_cast<const float*>(grads[i].data), numel, t->nonfinite, s));
+  }
+  *nl += n_grads;
   return CC_OK;
+}
+
+int cc_train_last_nonfinite(cc_train* t, void* stream) {
+  if (t == nullptr) return -1;
+  int host = 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cudaMemcpyAsync(&host, t->nonfinite, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess)
+    return -1;
+  return host;
 }
 
 int cc_train_last_launches(cc_train* t) { return t ? t->launches : 0; }

@@ -54,6 +54,9 @@ int loss_reduce_run(const float* row_loss, int n, const int* n_valid, float* los
 int train_embed_run(const int32_t* tokens, int B, int Tt, int K, const float* prefix, int64_t prefix_ld,
                     const float* wte, const float* wpe, float* h, int32_t* targets, int d, int V, cudaStream_t s);
 
+// count += number of non-finite elements of x (overflow check of the gradients produced under the static loss scale)
+int count_nonfinite_run(const float* x, int64_t n, int* count, cudaStream_t s);
+
 // torch.optim.AdamW update (decoupled weight decay, bias correction), step >= 1.
 int adamw_run(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
               float weight_decay, int step, cudaStream_t s);

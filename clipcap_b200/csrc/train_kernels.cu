@@ -608,6 +608,15 @@ __global__ void train_embed_kernel(const int32_t* __restrict__ tokens, int Tt, i
   for (int c = threadIdx.x; c < d; c += blockDim.x) dst[c] = src[c] + pe[c];
 }
 
+// ---------------------------------------------------------------- overflow detection for the static loss scale
+__global__ void count_nonfinite_kernel(const float* __restrict__ x, long long n, int* __restrict__ count) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  int bad = 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) bad += !isfinite(x[i]);
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad != 0) atomicAdd(count, bad);
+}
+
 // ---------------------------------------------------------------- AdamW
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
@@ -615,6 +624,10 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
     const float gi = g[i];
+    // A non-finite gradient element (fp16 overflow of an activation gradient under the static loss scale) must not reach the
+    // moments: exp_avg / exp_avg_sq would stay poisoned for good. The element is skipped for this step; the step's
+    // non-finite count is reported by cc_train_step (cc_train_last_nonfinite) so a caller can lower its loss scale.
+    if (!isfinite(gi)) continue;
     float pi = p[i] * (1.f - lr * weight_decay);
     const float mi = beta1 * m[i] + (1.f - beta1) * gi;
     const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
@@ -831,6 +844,13 @@ int loss_reduce_run(const float* row_loss, int n, const int* n_valid, float* los
 int train_embed_run(const int32_t* tokens, int B, int Tt, int K, const float* prefix, int64_t prefix_ld,
                     const float* wte, const float* wpe, float* h, int32_t* targets, int d, int V, cudaStream_t s) {
   train_embed_kernel<<<B * (K + Tt), 256, 0, s>>>(tokens, Tt, K, prefix, prefix_ld, wte, wpe, h, targets, d, V);
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+int count_nonfinite_run(const float* x, int64_t n, int* count, cudaStream_t s) {
+  if (n <= 0) return CC_OK;
+  count_nonfinite_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, n, count);
   CC_CUDA(cudaGetLastError());
   return CC_OK;
 }

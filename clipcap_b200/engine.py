@@ -370,6 +370,11 @@ class TrainEngine(_Handle):
                                                 _ffi.current_stream_ptr()))
         return loss
 
+    def last_nonfinite(self) -> int:
+        """Non-finite gradient elements of the last step with gradients (host sync): > 0 means the loss scale overflowed."""
+        with torch.cuda.device(self.device):
+            return _ffi.lib().cc_train_last_nonfinite(self._h, _ffi.current_stream_ptr())
+
     @property
     def last_launches(self) -> int:
         return _ffi.lib().cc_train_last_launches(self._h)

@@ -171,5 +171,15 @@ class ClipCapModelPrefixOnly(ClipCapModel):
         self.log("loss", loss)
         return loss
 
+    def check_overflow(self) -> bool:
+        """Dynamic loss scaling hook (call it every few steps; it synchronises): True if the last training step's gradients
+        held non-finite values — the static scale of the fp16 activation gradients overflowed. The scale is then halved for
+        the following steps; the optimiser has skipped the offending elements (cc_op_adamw), its state is intact."""
+        eng = getattr(self, "_train_engine", None)
+        if eng is None or eng.last_nonfinite() <= 0:
+            return False
+        self.loss_scale = max(1.0, float(self.loss_scale) / 2.0)
+        return True
+
     def log(self, name: str, value) -> None:  # Lightning's self.log; keeps the last value without a host sync
         object.__setattr__(self, "_last_logged", (name, value.detach() if torch.is_tensor(value) else value))

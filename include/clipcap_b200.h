@@ -240,6 +240,10 @@ int cc_train_create(cc_train** h, const cc_mapper_cfg* mapper_cfg, const cc_gpt2
 int cc_train_step(cc_train* h, const cc_tensor* params, int n_params, const cc_tensor* grads, int n_grads,
                   const void* emb /*[B,E]*/, int emb_dtype, const int32_t* tokens /*[B,Tt]*/, int B, int Tt, float loss_scale,
                   float* loss, void* stream);
+/* Number of non-finite elements among the gradients the last cc_train_step with gradients wrote (synchronises `stream`).
+ * Activation gradients travel in fp16 under the caller's static loss scale; a non-zero count means that scale overflowed:
+ * halve it and repeat the step (cc_op_adamw skips non-finite gradient elements, so the optimiser state is never poisoned). */
+int cc_train_last_nonfinite(cc_train* h, void* stream);
 int cc_train_last_launches(cc_train* h);
 void cc_train_destroy(cc_train* h);
 /* torch.optim.AdamW update on flat fp32 device arrays (configure_optimizers, model.py:67-91); step counts from 1. */
@@ -331,6 +335,9 @@ int cc_get_sm_budget(void);
  * returns the summed duration (ms), algorithmic FLOPs (2*M*N*K) and launch count since cc_prof_enable(1). */
 void cc_prof_enable(int on);
 void cc_prof_read(double* ms, double* flops, long long* n);
+/* The same sums for one tile family of the tcgen05 GEMM: bn = 512 the 256 x 256 CTA-pair tile, 256 / 128 / 64 / 32 the
+ * single-CTA tiles of that width (the decode and small-batch shapes), 0 every recorded launch. */
+void cc_prof_read_family(int bn, double* ms, double* flops, long long* n);
 
 #ifdef __cplusplus
 }

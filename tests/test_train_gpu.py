@@ -270,6 +270,30 @@ def test_relu_mask_explains_the_gated_gradient_error(cuda_device, name):
     assert worst_other < 8e-3, worst_other
 
 
+def test_loss_scale_overflow_is_detected_and_does_not_poison_adamw(cuda_device):
+    """A loss scale far too large overflows the fp16 activation gradients: cc_train_step reports the non-finite gradient
+    elements, cc_op_adamw leaves those elements (parameter and moments) untouched, and the module's check_overflow()
+    halves the scale. With a sane scale the count is zero."""
+    from clipcap_b200.engine import adamw_update
+    spec, gcfg, mcfg, map_w, lm_w, tokens, emb, *_ = load_train_case("tiny_a")
+    eng = _engine(gcfg, mcfg, lm_w, tokens.shape[0], tokens.shape[1], cuda_device)
+    params = {k: v.to(cuda_device).contiguous() for k, v in map_w.items()}
+    grads = {k: torch.zeros_like(v) for k, v in params.items()}
+    eng.step(params, emb.to(cuda_device), tokens.to(cuda_device), grads, loss_scale=1024.0)
+    assert eng.last_nonfinite() == 0
+    eng.step(params, emb.to(cuda_device), tokens.to(cuda_device), grads, loss_scale=1e30)
+    bad = eng.last_nonfinite()
+    assert bad > 0 and bad == sum(int((~torch.isfinite(g)).sum()) for g in grads.values())
+    # the optimiser skips exactly the non-finite elements
+    p = torch.ones(8, device=cuda_device)
+    g = torch.tensor([0.5, float("nan"), float("inf"), -0.5, 0.0, float("-inf"), 1.0, 2.0], device=cuda_device)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    adamw_update(p, g, m, v, 1e-2, 0.9, 0.999, 1e-8, 0.1, 1)
+    skipped = ~torch.isfinite(g)
+    assert torch.equal(p[skipped], torch.ones(3, device=cuda_device)) and float(m[skipped].abs().max()) == 0.0
+    assert torch.isfinite(p).all() and torch.isfinite(m).all() and torch.isfinite(v).all() and (p[~skipped] != 1.0).all()
+
+
 def test_windowed_model_training_step_api(cuda_device):
     """ClipCapModelPrefixOnly with use_windowed_embeddings (model.py:22-32): training_step -> backward -> optimizer step
     through the module API, loss against the oracle."""
