@@ -15,11 +15,14 @@
 // All 257 keys are visible at once, so the softmax is a plain two-pass one (row max, then exp2 with the scale folded in);
 // thread == query row == TMEM lane, no shuffles.
 //
-// The kernel is persistent (one CTA per SM, 384 threads) and MUFU-bound by design (128 x 257 exp2 per tile):
+// The kernel is persistent (one CTA per SM, 640 threads) and MUFU-bound by design (128 x 257 exp2 per tile):
 //   warp 0        TMA producer: Q (2 tiles), K, V of the next (image, head) into the other of two 96 KB stages
 //   warps 1, 2    one MMA issuer per query tile ("stream"): S_t, then - once its softmax group has written P_t - O_t
 //   warp 3        CLS query row
-//   warps 4..7    softmax group of tile 0, warps 8..11 softmax group of tile 1
+//   warps 4..11   softmax group of tile 0, warps 12..19 of tile 1: TWO threads per query row (warp = lane quadrant x
+//                 column half; the halves exchange row maximum / sum through shared memory), so every scheduler holds
+//                 four arithmetic warps instead of two — one thread per row left the kernel bound by dependent-instruction
+//                 latency at 50 % issue utilisation
 // The two streams only share the stage buffers, so they drift half a period apart and one group's exp2 phase overlaps the
 // other's MMAs, TMEM round trips and epilogue stores.
 #include <cstdlib>
@@ -30,7 +33,7 @@
 namespace cc {
 namespace {
 
-constexpr int VA_THREADS = 384;
+constexpr int VA_THREADS = 640;  // producer, 2 MMA issuers, CLS-row merger, 16 softmax warps (two threads per query row)
 constexpr int VA_S = 257;
 constexpr int VA_Q_BYTES = 256 * 64 * 2;  // both 128-query tiles
 constexpr int VA_K_BYTES = 256 * 64 * 2;
@@ -38,10 +41,12 @@ constexpr int VA_V_BYTES = 256 * 64 * 2;
 constexpr int VA_C_BYTES = 512;  // CLS token rows of q, k, v (3 x 128 B, padded)
 constexpr int VA_STAGE = VA_Q_BYTES + VA_K_BYTES + VA_V_BYTES;
 constexpr int VA_PART = 72;       // floats per partial result of the CLS query row: 64 dims, warp max, warp sum (padded)
-constexpr int VA_SCRATCH = 2 * 8 * VA_PART * 4;  // per stage: one partial per softmax warp
+constexpr int VA_NSW = 16;        // softmax warps: 2 tiles x 4 lane quadrants x 2 column halves
+constexpr int VA_XCH = 2 * 2 * 128 * 3 * 4;  // per (tile, half, row): row maximum, row sum, half of the CLS-key score
+constexpr int VA_SCRATCH = 2 * VA_NSW * VA_PART * 4 + VA_XCH;  // per stage one partial per softmax warp + the exchange
 constexpr int VA_SMEM = 2 * VA_STAGE + 2 * VA_C_BYTES + VA_SCRATCH + 256 + 1024;
 constexpr int VA_TMEM_COLS = 512;  // 256 per stream: S [0,256) -> P [0,128) + O [128,192)
-constexpr int VA_EMPTY_ARRIVALS = 2 + 8 + 1;  // both MMA streams (commit), 8 softmax warps, CLS warp
+constexpr int VA_EMPTY_ARRIVALS = 2 + VA_NSW + 1;  // both MMA streams (commit), the softmax warps, CLS warp
 
 // Where token `tok` of {q,k,v} of (image b, head h) lives in the [rows, ld] fp16 matrix the TMA descriptor covers:
 //   row = b * row_b + h * row_h + row_w[which] + tok,   column = col_w[which] + h * col_h
@@ -145,10 +150,10 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
       mbar_init(full_v(i), 1);
       mbar_init(empty(i), VA_EMPTY_ARRIVALS);
       mbar_init(s_full(i), 1);
-      mbar_init(p_full(i), 4);
+      mbar_init(p_full(i), 8);
       mbar_init(o_full(i), 1);
-      mbar_init(t_free(i), 4);
-      mbar_init(cls_full(i), 8);
+      mbar_init(t_free(i), 8);
+      mbar_init(cls_full(i), VA_NSW);
     }
     fence_mbar_init();
   }
@@ -213,8 +218,9 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
         tc_fence_after();
         const uint64_t dv = umma_desc_kmajor_sw128(sV(s));
 #pragma unroll
-        for (int k = 0; k < 16; ++k)
-          umma_f16_ts(tm + 128, tm + 8 * k, dv + static_cast<uint64_t>(k) * (2048 >> 4), idesc_o, k != 0 ? 1u : 0u);
+        for (int k = 0; k < 16; ++k)  // P of keys 0..127 at columns [0,64), of keys 128..255 at [128,192); O at [192,256)
+          umma_f16_ts(tm + 192, tm + (k < 8 ? 8 * k : 128 + 8 * (k - 8)), dv + static_cast<uint64_t>(k) * (2048 >> 4), idesc_o,
+                      k != 0 ? 1u : 0u);
         umma_commit(o_full(t));
         umma_commit(empty(s));
       }
@@ -243,14 +249,14 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
       const uint32_t v0u = lds32(sC(s, 2) + 4 * lane);
       const float2 v0f = __half22float2(*reinterpret_cast<const __half2*>(&v0u));
       mbar_wait(cls_full(s), ph_s);
-      const float* part = sPf + s * 8 * VA_PART;
+      const float* part = sPf + s * VA_NSW * VA_PART;
       float mx = sc0;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) mx = fmaxf(mx, part[g * VA_PART + 64]);
+      for (int g = 0; g < VA_NSW; ++g) mx = fmaxf(mx, part[g * VA_PART + 64]);
       const float pc = fast_exp2((sc0 - mx) * a.scale_log2);
       float o0 = pc * v0f.x, o1 = pc * v0f.y, sum = pc;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < VA_NSW; ++g) {
         const float f = fast_exp2((part[g * VA_PART + 64] - mx) * a.scale_log2);
         const float2 pv = *reinterpret_cast<const float2*>(part + g * VA_PART + 2 * lane);
         o0 += f * pv.x;
@@ -263,32 +269,40 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
       *reinterpret_cast<uint32_t*>(a.o + row0 * a.ldo + h * 64 + 2 * lane) = pack_half2(o0 * inv, o1 * inv);
     }
   } else {
-    // ------------------------------------------------------------ softmax + epilogue of tile t, thread == query row
-    const int t = (warp - 4) >> 2;
-    const int quad = warp & 3;
-    const int r = quad * 32 + lane;  // row inside the 128-query tile == TMEM lane
+    // ------------------------------------------------------------ softmax + epilogue of tile t: two threads per query row
+    const int t = (warp - 4) >> 3;
+    const int quad = warp & 3;         // TMEM lane quadrant (== warp % 4)
+    const int hh = ((warp - 4) >> 2) & 1;  // column half of S (keys 128*hh ..) / dim half of O (32*hh ..)
+    const int r = quad * 32 + lane;    // row inside the 128-query tile == TMEM lane
     const uint32_t t_row = tmem_base + 256u * t + (static_cast<uint32_t>(quad * 32) << 16);
-    // score of this thread's query row against the CLS key of the item in stage s (needs Q and the CLS key row)
-    auto cls_score = [&](int s) {
+    const uint32_t s_cols = t_row + 128u * hh;        // this thread's 128 columns of S
+    const uint32_t p_cols = t_row + 128u * hh;        // its 64 columns of P (fp16 pairs) start where its S columns start
+    float* xch = sPf + 2 * VA_NSW * VA_PART;          // [tile][half][row][3]
+    float* mine = xch + ((t * 2 + hh) * 128 + r) * 3;
+    const float* other = xch + ((t * 2 + (hh ^ 1)) * 128 + r) * 3;
+    const uint32_t pair_bar = 1 + t * 4 + quad;       // named barrier of the two warps that share these 32 rows
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
+    // this thread's half (32 dims) of the score of its query row against the CLS key of the item in stage s
+    auto cls_score_half = [&](int s) {
       float s0 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float qf[8], kf[8];
-        unpack8(lds128(sQ(s) + t * 128 * 128 + sw128_off(r, c)), qf);
-        unpack8(lds128(sC(s, 1) + 16 * c), kf);
+        unpack8(lds128(sQ(s) + t * 128 * 128 + sw128_off(r, 4 * hh + c)), qf);
+        unpack8(lds128(sC(s, 1) + 16 * (4 * hh + c)), kf);
 #pragma unroll
         for (int i = 0; i < 8; ++i) s0 += qf[i] * kf[i];
       }
       return s0;
     };
     int it = 0;
-    float s0 = 0.f;
+    float s0h = 0.f;
     if (static_cast<int>(blockIdx.x) < n_items) {
       mbar_wait(full_qk(0), 0);
-      s0 = cls_score(0);
+      s0h = cls_score_half(0);
     }
     bool stagger = (t == 1);  // start the two streams half a period apart so their exp2 phases interleave
-    int release_stage = -1;   // stage whose Q buffer holds this warp's in-flight output rows
+    int release_stage = -1;   // stage whose Q buffer holds this warp pair's in-flight output rows (issuer warp only)
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       const int s = it & 1;
       const uint32_t ph_s = (it >> 1) & 1u, ph = it & 1u;
@@ -301,13 +315,10 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
         stagger = false;
       }
       tc_fence_after();
-      // pass 1: row max (TMEM loads double-buffered in registers). One thread owns a whole row, so the reduction is a
-      // serial chain per thread: four independent running maxima of FMNMX3 (two scores per instruction) keep the pipe
-      // fed. The chunk loops are rolled up to two chunks per trip: fully unrolled, the kernel's code (75 KB, each warp
-      // role in its own region) overflowed the instruction cache and the schedulers sat in "no instruction" stalls.
-      float mx;
+      // pass 1: maximum of this thread's 128 scores (four independent FMNMX3 chains, TMEM loads double-buffered)
+      float mloc;
       {
-        float m0 = s0, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
         uint32_t sa[32], sb[32];
         auto fold = [&](const uint32_t(&v)[32]) {
 #pragma unroll
@@ -318,34 +329,38 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
             m3 = fmax3(m3, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
           }
         };
-        tmem_ld_x32(t_row, sa);
+        tmem_ld_x32(s_cols, sa);
 #pragma unroll 1
-        for (int c = 0; c < 8; c += 2) {
+        for (int c = 0; c < 4; c += 2) {
           tmem_ld_wait();
-          tmem_ld_x32(t_row + 32 * (c + 1), sb);
+          tmem_ld_x32(s_cols + 32 * (c + 1), sb);
           fold(sa);
           tmem_ld_wait();
-          if (c + 2 < 8) tmem_ld_x32(t_row + 32 * (c + 2), sa);
+          if (c + 2 < 4) tmem_ld_x32(s_cols + 32 * (c + 2), sa);
           fold(sb);
         }
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        mloc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
+      mine[0] = mloc;
+      mine[2] = s0h;
+      pair_sync();  // both halves' maxima and CLS-key partial scores are visible
+      const float s0 = hh == 0 ? s0h + other[2] : other[2] + s0h;  // same operand order in both threads: identical bits
+      const float mx = fmaxf(fmaxf(mloc, other[0]), s0);
       const float ms = mx * a.scale_log2;
       if (release_stage >= 0) {
         if (lane == 0) {
           bulk_wait_read<0>();
-          mbar_arrive(empty(release_stage));  // this warp no longer touches that stage
+          mbar_arrive(empty(release_stage));  // the output rows staged in that stage have left
         }
         release_stage = -1;
       }
-      // pass 2: p = exp2((s - max) * scale * log2 e), row sum, P -> TMEM as fp16 pairs
-      float sum;
+      // pass 2: p = exp2((s - max) * scale * log2 e) for this thread's 128 scores, partial row sum, P -> TMEM as fp16 pairs
+      // over S columns this thread has already consumed
+      float sloc;
       {
-        unsigned long long acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;  // two packed partial row sums (4 add chains)
+        unsigned long long acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
         const unsigned long long sc2 = pack_f32x2(a.scale_log2, a.scale_log2), nms2 = pack_f32x2(-ms, -ms);
         uint32_t sa[32], sb[32];
-        // x = s * scale*log2(e) - max*scale*log2(e) for two scores per FFMA2, exp2 on the MUFU, sums per FADD2; the
-        // probabilities of chunk c go back to TMEM as fp16 pairs over S columns this thread has already consumed
         auto chunk = [&](const uint32_t(&v)[32], int c) {
           uint32_t pr[16];
 #pragma unroll
@@ -359,64 +374,66 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
             pr[j] = pack_half2(p0, p1);
             pr[j + 1] = pack_half2(p2, p3);
           }
-          tmem_st_x16(t_row + 16 * c, pr);
+          tmem_st_x16(p_cols + 16 * c, pr);
         };
-        tmem_ld_x32(t_row, sa);
+        tmem_ld_x32(s_cols, sa);
 #pragma unroll 1
-        for (int c = 0; c < 8; c += 2) {
+        for (int c = 0; c < 4; c += 2) {
           tmem_ld_wait();
-          tmem_ld_x32(t_row + 32 * (c + 1), sb);
+          tmem_ld_x32(s_cols + 32 * (c + 1), sb);
           chunk(sa, c);
           tmem_ld_wait();
-          if (c + 2 < 8) tmem_ld_x32(t_row + 32 * (c + 2), sa);
+          if (c + 2 < 4) tmem_ld_x32(s_cols + 32 * (c + 2), sa);
           chunk(sb, c + 1);
         }
         float a0, a1, a2, a3;
         unpack_f32x2(acc0, a0, a1);
         unpack_f32x2(acc1, a2, a3);
-        sum = (a0 + a1) + (a2 + a3);
+        sloc = (a0 + a1) + (a2 + a3);
       }
+      mine[1] = sloc;
       const float pc = fast_exp2(s0 * a.scale_log2 - ms);  // probability of the CLS key
-      sum += pc;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(t));
 
-      // While the P V MMA runs: this warp's share of the CLS QUERY row — thread == patch key t * 128 + r. Score against
-      // q_cls, softmax statistics local to the warp's 32 keys, and the warp's partial sum of p * V (lane owns two head
-      // dims); warp 3 merges the eight partials.
+      // While the P V MMA runs: this warp's share of the CLS QUERY row — 16 patch keys per warp, two lanes per key
+      // (32 dims each). Score against q_cls, softmax statistics local to the warp's keys, and the warp's partial sum of
+      // p * V (lane owns two head dims); warp 3 merges the sixteen partials.
       {
-        const int key = t * 128 + r;
+        const int key0 = t * 128 + quad * 32 + hh * 16;
+        const int key = key0 + (lane >> 1), dh = lane & 1;
         float sq = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           float qf[8], kf[8];
-          unpack8(lds128(sC(s, 0) + 16 * c), qf);
-          unpack8(lds128(sK(s) + sw128_off(key, c)), kf);
+          unpack8(lds128(sC(s, 0) + 16 * (4 * dh + c)), qf);
+          unpack8(lds128(sK(s) + sw128_off(key, 4 * dh + c)), kf);
 #pragma unroll
           for (int i = 0; i < 8; ++i) sq += qf[i] * kf[i];
         }
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
         float wm = sq;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        for (int o = 16; o > 1; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
         const float pq = fast_exp2((sq - wm) * a.scale_log2);
-        float ws = pq;
+        float ws = dh == 0 ? pq : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
         mbar_wait(full_v(s), ph_s);
         const uint32_t vrow0 = sV(s) + (lane & 3) * 4;
-        const int c16 = lane >> 2, key0 = t * 128 + quad * 32;
+        const int c16 = lane >> 2;
         float po0 = 0.f, po1 = 0.f;
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) {
-          const float pj = __shfl_sync(0xffffffffu, pq, j);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float pj = __shfl_sync(0xffffffffu, pq, 2 * j);
           const uint32_t u = lds32(vrow0 + sw128_off(key0 + j, c16));
           const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&u));
           po0 += pj * vf.x;
           po1 += pj * vf.y;
         }
-        float* part = sPf + (s * 8 + (warp - 4)) * VA_PART;
+        float* part = sPf + (s * VA_NSW + (warp - 4)) * VA_PART;
         *reinterpret_cast<float2*>(part + 2 * lane) = make_float2(po0, po1);
         if (lane == 0) {
           part[64] = wm;
@@ -426,49 +443,49 @@ vit_attn_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__
         if (lane == 0) mbar_arrive(cls_full(s));
       }
       // ... and the next item's CLS-key score (its stage has been loading all along)
+      float s0h_next = 0.f;
       if (w + static_cast<int>(gridDim.x) < n_items) {
         mbar_wait(full_qk(s ^ 1), ((it + 1) >> 1) & 1u);
-        s0 = cls_score(s ^ 1);
+        s0h_next = cls_score_half(s ^ 1);
       }
-      const float inv = 1.f / sum;
+      pair_sync();  // both halves' row sums are visible (and every read of the exchange slots above is done)
+      const float inv = 1.f / ((hh == 0 ? sloc + other[1] : other[1] + sloc) + pc);
 
       mbar_wait(o_full(t), ph);
       tc_fence_after();
-      uint32_t orr[2][32];
-      tmem_ld_x32(t_row + 128, orr[0]);
-      tmem_ld_x32(t_row + 160, orr[1]);
+      uint32_t orr[32];  // this thread's 32 head dims of its output row
+      tmem_ld_x32(t_row + 192 + 32 * hh, orr);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_free(t));  // the stream's TMEM columns may take the next S
-      uint4 v0r[8];  // CLS value row (o_full implies full_v of this stage)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) v0r[c] = lds128(sC(s, 2) + 16 * c);
-      // The output rows leave through shared memory and one TMA store per warp (32 rows x 128 B): a thread-per-row
-      // global store would touch 32 cache lines per instruction. The staging area is this tile's Q buffer, dead since the
-      // S MMA and the CLS-key scores; the stage is released once the bulk store has read it.
+      // The output rows leave through shared memory and one TMA store per warp PAIR (32 rows x 128 B): the staging area is
+      // this tile's Q buffer, dead since the S MMA and the CLS-key scores; the stage is released once the bulk store has
+      // read it.
       const uint32_t stg = sQ(s) + t * 128 * 128 + quad * 32 * 128;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int c = 0; c < 4; ++c) {
+        float vf[8];
+        unpack8(lds128(sC(s, 2) + 16 * (4 * hh + c)), vf);  // CLS value row (o_full implies full_v of this stage)
+        uint32_t op[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          float vf[8];
-          unpack8(v0r[half * 4 + c], vf);
-          uint32_t op[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            op[i] = pack_half2((__uint_as_float(orr[half][8 * c + 2 * i]) + pc * vf[2 * i]) * inv,
-                               (__uint_as_float(orr[half][8 * c + 2 * i + 1]) + pc * vf[2 * i + 1]) * inv);
-          st_shared_v4(stg + sw128_off(lane, half * 4 + c), op[0], op[1], op[2], op[3]);
-        }
+        for (int i = 0; i < 4; ++i)
+          op[i] = pack_half2((__uint_as_float(orr[8 * c + 2 * i]) + pc * vf[2 * i]) * inv,
+                             (__uint_as_float(orr[8 * c + 2 * i + 1]) + pc * vf[2 * i + 1]) * inv);
+        st_shared_v4(stg + sw128_off(lane, 4 * hh + c), op[0], op[1], op[2], op[3]);
       }
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(&map_o, stg, h * 64, static_cast<int>(row0) + 1 + 128 * t + 32 * quad);
-        bulk_commit();
+      pair_sync();  // both halves of the 32 staged rows are written (and this warp is done with the stage's Q / K / V / CLS rows)
+      if (hh == 0) {
+        if (lane == 0) {
+          tma_store_2d(&map_o, stg, h * 64, static_cast<int>(row0) + 1 + 128 * t + 32 * quad);
+          bulk_commit();
+        }
+        release_stage = s;  // released (above / after the loop) once the bulk store has read the staging rows
+      } else if (lane == 0) {
+        mbar_arrive(empty(s));  // this warp no longer touches the stage; the pending store is the issuer warp's to wait for
       }
-      release_stage = s;  // released (below / next iteration) once the bulk store has read the staging rows
+      s0h = s0h_next;
     }
   }
 
