@@ -751,6 +751,8 @@ int attention_run(const __half* q, const __half* k, const __half* v, int64_t ld,
       return e != nullptr && e[0] == '1';
     }();
     if (!no_tc && vit_attention_fits(S, hd, causal, ld, ldo, q, k, v)) return vit_attention_run(q, k, v, ld, o, ldo, B, S, H, scale, s);
+    if (!no_tc && small_attention_fits(S, hd, ld, ldo, q, k, v, o))
+      return small_attention_run(q, k, v, ld, o, ldo, B, S, H, hd, causal, scale, s);
   }
 #define CC_ATTN_CASE(HD)                                                                         \
   if (hd == HD)                                                                                  \

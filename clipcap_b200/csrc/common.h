@@ -224,6 +224,12 @@ int vit_attention_run(const __half* q, const __half* k, const __half* v, int64_t
 // block, which is what lets the loads run at HBM speed.
 int vit_attention_heads_run(const __half* qkvh, __half* o, int64_t ldo, int B, int S, int H, float scale, cudaStream_t s);
 constexpr int kVitAttnTokens = 257;
+// tcgen05 attention for S <= 128 tokens, head dim 64 / 128, full or causal (mapper, GPT-2 prefill, training forward):
+// one (sequence, head) = one 128-row tile (small_attention.cu). attention_run tries it after the ViT kernel.
+bool small_attention_fits(int S, int hd, int64_t ld, int64_t ldo, const __half* q, const __half* k, const __half* v,
+                          const __half* o);
+int small_attention_run(const __half* q, const __half* k, const __half* v, int64_t ld, __half* o, int64_t ldo, int B, int S,
+                        int H, int hd, bool causal, float scale, cudaStream_t s);
 
 // KV cache: [layer][k|v][slot][head][t_max][64] fp16. Decode step: append this step's k,v (from qkv[nseq,3d]) at position
 // `pos` of slot `seq`, then attend over positions 0..pos, position t being read from slot anc[seq*t_max + t]

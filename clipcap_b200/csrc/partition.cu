@@ -89,12 +89,15 @@ int partition_build(cc_partition* p, int device, int small_sms) {
   CUdevResource all;
   CC_DRV(d.get_res(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
   const int total = static_cast<int>(all.sm.smCount);
-  CC_REQUIRE(small_sms >= 8 && small_sms <= total - 8, CC_EINVAL,
-             "cc_partition_create: the small partition needs 8 .. %d SMs (got %d; partitions are multiples of 8 SMs)",
-             total - 8, small_sms);
+  CC_REQUIRE(small_sms >= 2 && small_sms <= total - 8, CC_EINVAL,
+             "cc_partition_create: the small partition needs 2 .. %d SMs (got %d)", total - 8, small_sms);
   CUdevResource small_res, rest;
   unsigned int groups = 1;
-  CC_DRV(d.split(&small_res, &groups, &all, &rest, 0, static_cast<unsigned int>(small_sms)));
+  // Multiples of 8 SMs split along the GPC hierarchy (the default). Any other count asks the driver to treat the SMs
+  // independently of their hierarchy (finer partitions; thread-block clusters larger than a CTA pair are then not
+  // guaranteed inside a partition — this library launches none).
+  const unsigned int flags = (small_sms % 8 == 0) ? 0u : static_cast<unsigned int>(CU_DEV_SM_RESOURCE_SPLIT_IGNORE_SM_COSCHEDULING);
+  CC_DRV(d.split(&small_res, &groups, &all, &rest, flags, static_cast<unsigned int>(small_sms)));
   CC_REQUIRE(groups == 1 && small_res.sm.smCount > 0 && rest.sm.smCount > 0, CC_ECUDA,
              "cc_partition_create: could not split %d SMs into %d + rest", total, small_sms);
   CUdevResource res[2] = {rest, small_res};

@@ -1,0 +1,359 @@
+// tcgen05 attention for short sequences: S <= 128 tokens, head dim 64 or 128, full or causal. Covers the mapper's
+// MultiHeadAttention (clipcap/model/attention.py:24-41 under mapper.py:107-110: S = P + K = 50, 8 heads of 128 at GPT-2-medium
+// width, no mask) and the causal self-attention of the GPT-2 prefill (K = 40 prefix positions, 16 heads of 64; HF
+// modeling_gpt2.py:54-72) — the two contractions of the path that still ran on mma.sync (attn_fwd_kernel).
+//
+// One work item is ONE 128-row tcgen05 tile holding `nslots` sequences of the same head: 1 sequence of S <= 128 tokens, 2 of
+// S <= 64 (64-row slots) or 4 of S <= 32 (32-row slots) — a slot never straddles a warp, so a warp's TMEM loads stay uniform.
+//   S  = Q K^T        M = 128, N = 128 when packed (cross-slot blocks are computed and ignored) or ceil32(S) keys, K = head dim;
+//                     Q and K are K-major 128B-swizzled tiles exactly as TMA lands them;
+//   P  = softmax(S)   thread == query row == TMEM lane: two passes over the scores of its own slot (maximum; exp2, sum), keys
+//                     >= S and — causal — keys > row masked; P goes back to TMEM as fp16 pairs over the columns S occupied,
+//                     with zeros over the other slots' keys;
+//   O  = P V          A = P from TMEM (tcgen05.mma TS form), B = V as the MN-major operand as TMA lands its [key][64] rows,
+//                     64 output dims per MMA group; accumulator in TMEM columns [128, 128 + hd).
+// The three operand boxes come through a 3-D tensor map over the packed projection [B][S][row stride] with box
+// {64 columns, slot rows, nslots sequences}: rows >= S of a slot and sequences >= B are zero-filled by TMA (never the next
+// sequence's rows), so padded keys contribute exactly 0 to P V.
+// CTA = 160 threads: warp 0 drives TMA and issues the MMAs (one thread), warps 1-4 are the softmax / epilogue group.
+// Operands sit in a ring of STAGES tiles: with two stages the next item's loads are in flight while the current item's
+// softmax runs; TMEM is single-buffered (the S MMA of item i+1 is ordered behind the P V MMA of item i in the issue
+// thread). Two CTAs share an SM (256 TMEM columns each) so one CTA's MMA round trips hide behind the other's softmax.
+#include <cstdlib>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cc {
+namespace {
+
+constexpr int SA_THREADS = 160;
+constexpr int SA_SLAB = 128 * 128;  // one 64-column slab of a 128-row operand tile
+constexpr int SA_TMEM_COLS = 256;
+
+struct SaArgs {
+  __half* o;
+  long long ldo;
+  int B, S, H;
+  int nslots, slot_rows;  // sequences per tile and rows per sequence slot (128 / nslots)
+  int SP;                 // keys a softmax thread walks: ceil32(S) (== slot_rows when packed)
+  int NS;                 // N of the S MMA = keys of the P V MMA: 128 when packed, SP otherwise
+  int box_rows;           // rows per slot a TMA box brings
+  int col_q, col_k, col_v;  // column of head 0 of q / k / v inside a row of the packed matrix
+  int causal;
+  float scale_log2;
+  uint32_t idesc_s;  // instruction descriptor of the S MMA (N is a run-time value)
+  int n_items;
+};
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <int HD, int STAGES>
+struct SaCfg {
+  static constexpr int kSlabs = HD / 64;
+  static constexpr int kOperand = kSlabs * SA_SLAB;  // Q, K or V tile
+  static constexpr int kStage = 3 * kOperand;
+  static constexpr int kSmem = STAGES * kStage + 128 + 1024;  // + barriers + alignment slack
+  static constexpr int kCtasPerSm = kSmem <= 113 * 1024 ? 2 : 1;
+};
+
+template <int HD, int STAGES>
+__global__ void __launch_bounds__(SA_THREADS, SaCfg<HD, STAGES>::kCtasPerSm)
+small_attn_kernel(const __grid_constant__ CUtensorMap map, SaArgs a) {
+  using Cfg = SaCfg<HD, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES * Cfg::kStage;
+  // full[st] at bars + 8 st, freed[st] at bars + 16 + 8 st
+  const uint32_t s_full = bars + 32, p_full = bars + 40, o_full = bars + 48, o_free = bars + 56, tmem_slot = bars + 64;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map);
+#pragma unroll
+    for (int st = 0; st < STAGES; ++st) {
+      mbar_init(bars + 8 * st, 1);
+      mbar_init(bars + 16 + 8 * st, 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, SA_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot_ptr;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA + MMA issue (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc_o = umma_idesc_f16(128, 64) | (1u << 16);  // bit 16: B is MN-major
+      const uint32_t bytes = 3u * Cfg::kSlabs * a.box_rows * a.nslots * 128;
+      auto load = [&](int w, int st) {
+        const int bg = w / a.H, h = w - bg * a.H;
+        const uint32_t sQ = base + st * Cfg::kStage, sK = sQ + Cfg::kOperand, sV = sK + Cfg::kOperand;
+        const uint32_t full = bars + 8 * st;
+        mbar_arrive_expect_tx(full, bytes);
+#pragma unroll
+        for (int sl = 0; sl < Cfg::kSlabs; ++sl) {
+          tma_load_3d(&map, full, sQ + sl * SA_SLAB, a.col_q + h * HD + 64 * sl, 0, bg * a.nslots);
+          tma_load_3d(&map, full, sK + sl * SA_SLAB, a.col_k + h * HD + 64 * sl, 0, bg * a.nslots);
+          tma_load_3d(&map, full, sV + sl * SA_SLAB, a.col_v + h * HD + 64 * sl, 0, bg * a.nslots);
+        }
+      };
+      if (static_cast<int>(blockIdx.x) < a.n_items) load(blockIdx.x, 0);
+      int it = 0;
+      for (int w = blockIdx.x; w < a.n_items; w += gridDim.x, ++it) {
+        const int st = it % STAGES;
+        const uint32_t sQ = base + st * Cfg::kStage, sK = sQ + Cfg::kOperand, sV = sK + Cfg::kOperand;
+        mbar_wait(bars + 8 * st, (it / STAGES) & 1u);
+        tc_fence_after();
+        // S[128 x NS] = Q K^T over the head dim
+#pragma unroll
+        for (int sl = 0; sl < Cfg::kSlabs; ++sl) {
+          const uint64_t dq = umma_desc_kmajor_sw128(sQ + sl * SA_SLAB), dk = umma_desc_kmajor_sw128(sK + sl * SA_SLAB);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss(tm, dq + 2u * k, dk + 2u * k, a.idesc_s, (sl | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        const int wn = w + gridDim.x;
+        if (STAGES > 1 && wn < a.n_items) {
+          // the next item's operands go to the stage the item before this one used: its P V MMA was issued an iteration ago
+          const int stn = (it + 1) % STAGES;
+          if (it + 1 >= STAGES) mbar_wait(bars + 16 + 8 * stn, ((it + 1) / STAGES - 1) & 1u);
+          load(wn, stn);
+        }
+        // O[128 x hd] = P V over the NS keys: A = P from TMEM (8 columns per 16 keys), B = V rows (MN-major, 2 KB per step)
+        mbar_wait(p_full, it & 1u);
+        if (it > 0) mbar_wait(o_free, (it - 1) & 1u);  // the group has read the previous item's O out of these columns
+        tc_fence_after();
+#pragma unroll
+        for (int ns = 0; ns < Cfg::kSlabs; ++ns) {
+          const uint64_t dv = umma_desc_kmajor_sw128(sV + ns * SA_SLAB);
+          for (int k = 0; k < a.NS / 16; ++k)
+            umma_f16_ts(tm + 128 + 64 * ns, tm + 8 * k, dv + static_cast<uint64_t>(k) * (2048 >> 4), idesc_o, k != 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(bars + 16 + 8 * st);
+        if (STAGES == 1 && wn < a.n_items) {
+          mbar_wait(bars + 16, it & 1u);  // this item's MMAs have read the only stage
+          load(wn, 0);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax + epilogue, thread == query row
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t t_row = tm + (static_cast<uint32_t>(quad * 32) << 16);
+    const int S = a.S, SP = a.SP;
+    const int slot = r / a.slot_rows, rr = r - slot * a.slot_rows;
+    const int kb = a.nslots > 1 ? slot * a.slot_rows : 0;     // first key column of this row's slot
+    const int last = a.causal ? (rr < S ? rr : S - 1) : S - 1;  // last visible key of this row (slot-local)
+    int it = 0;
+    for (int w = blockIdx.x; w < a.n_items; w += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+      const int bg = w / a.H, h = w - bg * a.H;
+      const int b = bg * a.nslots + slot;
+      mbar_wait(s_full, ph);
+      tc_fence_after();
+      // pass 1: maximum over the visible keys
+      float mx = -INFINITY;
+      for (int c = 0; c < SP; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(t_row + kb + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c + j <= last) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+      const float ms = mx * a.scale_log2;
+      // pass 2: probabilities (0 for masked keys), row sum, P -> TMEM as fp16 pairs over consumed S columns
+      float sum = 0.f;
+      for (int c = 0; c < SP; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(t_row + kb + c, v);
+        tmem_ld_wait();
+        uint32_t pr[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float p0 = (c + 2 * j <= last) ? fast_exp2(__uint_as_float(v[2 * j]) * a.scale_log2 - ms) : 0.f;
+          const float p1 = (c + 2 * j + 1 <= last) ? fast_exp2(__uint_as_float(v[2 * j + 1]) * a.scale_log2 - ms) : 0.f;
+          sum += p0 + p1;
+          pr[j] = pack_half2(p0, p1);
+        }
+        tmem_st_x16(t_row + ((kb + c) >> 1), pr);
+      }
+      if (a.nslots > 1) {
+        // zeros over the other slots' keys (after this row's own scores have been read: the zeros land on S columns)
+        uint32_t z[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z[j] = 0u;
+        for (int c = 0; c < 128; c += 32)
+          if (c < kb || c >= kb + SP) tmem_st_x16(t_row + (c >> 1), z);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      const float inv = 1.f / sum;
+
+      mbar_wait(o_full, ph);
+      tc_fence_after();
+      const bool live = rr < S && b < a.B;
+      __half* orow = a.o + (static_cast<long long>(b) * S + rr) * a.ldo + h * HD;
+#pragma unroll
+      for (int c = 0; c < HD; c += 32) {
+        uint32_t v[32];
+        tmem_ld_x32(t_row + 128 + c, v);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 out;
+            out.x = pack_half2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+            out.y = pack_half2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+            out.z = pack_half2(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv);
+            out.w = pack_half2(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c + j) = out;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);  // the O columns may take the next item's accumulator
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tm, SA_TMEM_COLS);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+template <int HD, int STAGES>
+int launch(const CUtensorMap& map, const SaArgs& a, cudaStream_t s) {
+  using Cfg = SaCfg<HD, STAGES>;
+  auto kern = small_attn_kernel<HD, STAGES>;
+  CC_OPT_IN_SMEM(kern, Cfg::kSmem);
+  const int resident = Cfg::kCtasPerSm * num_sms();
+  const int grid = a.n_items < resident ? a.n_items : resident;
+  CC_CUDA(launch_pdl(kern, dim3(grid), dim3(SA_THREADS), Cfg::kSmem, s, map, a));
+  return CC_OK;
+}
+
+}  // namespace
+
+bool small_attention_fits(int S, int hd, int64_t ld, int64_t ldo, const __half* q, const __half* k, const __half* v,
+                          const __half* o) {
+  static const bool off = [] {
+    const char* e = getenv("CLIPCAP_B200_NO_TC_SMALL_ATTN");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (off || S < 1 || S > 128 || (hd != 64 && hd != 128)) return false;
+  if (ld % 8 != 0 || ldo % 8 != 0) return false;
+  const long long kc = k - q, vc = v - q;
+  if (kc < 0 || vc < 0 || kc % 8 != 0 || vc % 8 != 0 || kc >= ld || vc >= ld) return false;
+  if ((reinterpret_cast<uintptr_t>(q) & 15) != 0 || (reinterpret_cast<uintptr_t>(o) & 15) != 0) return false;
+  return true;
+}
+
+int small_attention_run(const __half* q, const __half* k, const __half* v, int64_t ld, __half* o, int64_t ldo, int B, int S,
+                        int H, int hd, bool causal, float scale, cudaStream_t s) {
+  CC_REQUIRE(small_attention_fits(S, hd, ld, ldo, q, k, v, o), CC_ESHAPE, "small attention: unsupported shape");
+  const long long kc = k - q, vc = v - q;
+  const long long cols = (kc > vc ? kc : vc) + static_cast<long long>(H) * hd;
+  CC_REQUIRE(cols <= ld, CC_ESHAPE, "small attention: q/k/v column blocks exceed the row stride");
+  const int SP = (S + 31) / 32 * 32;
+  // sequences per 128-row tile: 4 slots of 32 rows, 2 of 64, or the whole tile
+  const int nslots = S <= 32 ? 4 : (S <= 64 ? 2 : 1);
+  const int slot_rows = 128 / nslots;
+  const int box_rows = nslots > 1 ? slot_rows : SP;
+  // 3-D map over the packed projection: {columns, S tokens, B sequences}; a box is {64 columns, box_rows tokens, nslots
+  // sequences}, tokens beyond S and sequences beyond B are zero-filled. Engines call with the same buffer for every layer:
+  // the last descriptor is cached.
+  struct Cached {
+    const __half* base = nullptr;
+    int64_t ld = 0;
+    long long cols = 0;
+    int B = 0, S = 0;
+    CUtensorMap map;
+  };
+  static thread_local Cached cache;
+  if (cache.base != q || cache.ld != ld || cache.cols != cols || cache.B != B || cache.S != S) {
+    EncodeTiledFn fn = encode_fn();
+    CC_REQUIRE(fn != nullptr, CC_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(S) * ld * 2};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(nslots)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&cache.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(q), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CC_REQUIRE(r == CUDA_SUCCESS, CC_ECUDA, "cuTensorMapEncodeTiled (small attention) failed (%d) S=%d B=%d ld=%lld", (int)r, S,
+               B, (long long)ld);
+    cache.base = q;
+    cache.ld = ld;
+    cache.cols = cols;
+    cache.B = B;
+    cache.S = S;
+  }
+  SaArgs a{};
+  a.o = o;
+  a.ldo = ldo;
+  a.B = B;
+  a.S = S;
+  a.H = H;
+  a.nslots = nslots;
+  a.slot_rows = slot_rows;
+  a.SP = SP;
+  a.NS = nslots > 1 ? 128 : SP;
+  a.box_rows = box_rows;
+  a.col_q = 0;
+  a.col_k = static_cast<int>(kc);
+  a.col_v = static_cast<int>(vc);
+  a.causal = causal ? 1 : 0;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  a.idesc_s = umma_idesc_f16(128, a.NS);
+  a.n_items = ((B + nslots - 1) / nslots) * H;
+  static const int stages128 = [] {
+    const char* e = getenv("CLIPCAP_B200_SMALL_ATTN_STAGES128");
+    return e != nullptr && e[0] == '2' ? 2 : 1;
+  }();
+  if (hd == 64) return launch<64, 2>(cache.map, a, s);
+  return stages128 == 2 ? launch<128, 2>(cache.map, a, s) : launch<128, 1>(cache.map, a, s);
+}
+
+}  // namespace cc

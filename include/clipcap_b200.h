@@ -311,7 +311,8 @@ void cc_comm_destroy(cc_comm* c);
  * SM partitions for the two-stage serving pipeline (clipcap_b200/pipeline.py). The path's stages have opposite
  * characters on a B200: image tower + mapper + prefill are tensor- and power-bound, the decode loop is a chain of
  * dependent launches that leaves most SMs idle. cc_partition_create splits the device's SMs (CUDA green contexts) into
- * a large partition (which = 0) and a small one (which = 1, >= small_sms SMs, rounded up to a multiple of 8) and creates
+ * a large partition (which = 0) and a small one (which = 1, >= small_sms SMs; multiples of 8 follow the GPC hierarchy, other
+ * counts use the driver's finer, hierarchy-agnostic split) and creates
  * one non-blocking stream in each; work enqueued on a partition's stream runs on its SMs only, so the decode of batch i
  * overlaps the image tower of batch i+1 without either stalling the other. No reference counterpart (single stream,
  * clipcap/inference/demo.py:30-45). */

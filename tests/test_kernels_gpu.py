@@ -119,9 +119,14 @@ def test_layernorm(cuda_device, rows, d):
 
 @pytest.mark.parametrize("cfg", [(2, 257, 16, 64, 0), (5, 257, 2, 64, 0), (3, 50, 8, 128, 0), (2, 20, 8, 96, 0),
                                  (2, 20, 16, 48, 0), (4, 40, 16, 64, 1), (1, 1, 2, 64, 1), (2, 130, 2, 64, 1),
-                                 (2, 256, 4, 64, 0), (2, 258, 4, 64, 0)])
+                                 (2, 256, 4, 64, 0), (2, 258, 4, 64, 0),
+                                 (5, 40, 16, 64, 1), (7, 20, 2, 128, 0), (3, 64, 2, 64, 1), (3, 65, 2, 64, 0),
+                                 (2, 128, 2, 128, 1), (9, 32, 2, 64, 1), (3, 33, 3, 128, 1), (300, 50, 8, 128, 0),
+                                 (1, 7, 1, 64, 0), (6, 107, 16, 64, 1)])
 def test_attention(cuda_device, cfg):
-    """(B, S, H, hd, causal); S = 257 with hd = 64 runs the tcgen05 kernel, everything else the generic one."""
+    """(B, S, H, hd, causal); S = 257 with hd = 64 runs the tcgen05 ViT kernel, S <= 128 with hd 64 / 128 the tcgen05
+    short-sequence kernel (1, 2 or 4 sequences per 128-row tile: odd batch sizes leave a slot empty), everything else the
+    generic one."""
     lib = _ffi.lib()
     B, S, H, hd, causal = cfg
     d = H * hd
