@@ -245,6 +245,11 @@ int launch_attn(const __half* q, const __half* k, const __half* v, int64_t ld, _
 constexpr int DEC_WARPS = 4;
 constexpr int DEC_KEYS = 16;  // keys per loop pass
 
+// Cache rows are stored with their eight 16-byte chunks rotated: chunk c (dims 8c .. 8c+7) of position t sits at chunk
+// c ^ (t & 7) of the 128-byte row. Eight consecutive rows read at one logical chunk then fall into eight different bank
+// groups of shared memory, so decode_attn_mma_kernel can feed ldmatrix straight from a plain bulk copy of the rows.
+__device__ __forceinline__ int kv_chunk(int t, int c) { return c ^ (t & 7); }
+
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const __half2* hp = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -274,7 +279,7 @@ decode_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, 
   const __half* vnew = qrow + 2 * d + c * 8;
   // append this step's k, v (lanes 0..7 copy k, 8..15 copy v)
   {
-    const long long dst = ((static_cast<long long>(seq) * H + h) * t_max + pos) * 64 + c * 8;
+    const long long dst = ((static_cast<long long>(seq) * H + h) * t_max + pos) * 64 + kv_chunk(pos, c) * 8;
     if (kq == 0) *reinterpret_cast<uint4*>(kcache + dst) = *reinterpret_cast<const uint4*>(knew);
     else if (kq == 1) *reinterpret_cast<uint4*>(vcache + dst) = *reinterpret_cast<const uint4*>(vnew);
   }
@@ -297,8 +302,8 @@ decode_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, 
       const int tt = t0 + 4 * j + kq;
       if (tt < pos) {
         const long long base = arow ? (static_cast<long long>(arow[tt]) * H + h) * t_max : own;
-        kk[j] = *reinterpret_cast<const uint4*>(kcache + (base + tt) * 64 + c * 8);
-        vv[j] = *reinterpret_cast<const uint4*>(vcache + (base + tt) * 64 + c * 8);
+        kk[j] = *reinterpret_cast<const uint4*>(kcache + (base + tt) * 64 + kv_chunk(tt, c) * 8);
+        vv[j] = *reinterpret_cast<const uint4*>(vcache + (base + tt) * 64 + kv_chunk(tt, c) * 8);
       } else if (tt == pos) {
         kk[j] = *reinterpret_cast<const uint4*>(knew);
         vv[j] = *reinterpret_cast<const uint4*>(vnew);
@@ -397,7 +402,7 @@ decode_attn_beam_kernel(const __half* __restrict__ qkv, __half* __restrict__ kca
   const uint4 knew = *reinterpret_cast<const uint4*>(qrow + d + c * 8);
   const uint4 vnew = *reinterpret_cast<const uint4*>(qrow + 2 * d + c * 8);
   {  // append this step's k, v to the row's own slot
-    const long long dst = ((static_cast<long long>(seq) * H + h) * t_max + pos) * 64 + c * 8;
+    const long long dst = ((static_cast<long long>(seq) * H + h) * t_max + pos) * 64 + kv_chunk(pos, c) * 8;
     if (kq == 0) *reinterpret_cast<uint4*>(kcache + dst) = knew;
     else if (kq == 1) *reinterpret_cast<uint4*>(vcache + dst) = vnew;
   }
@@ -422,12 +427,12 @@ decode_attn_beam_kernel(const __half* __restrict__ qkv, __half* __restrict__ kca
       if (tt < shared_len) {
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(kk[j].x), "=r"(kk[j].y), "=r"(kk[j].z), "=r"(kk[j].w)
-                     : "r"(kbuf + tt * 128 + c * 16));
+                     : "r"(kbuf + tt * 128 + kv_chunk(tt, c) * 16));
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(vv[j].x), "=r"(vv[j].y), "=r"(vv[j].z), "=r"(vv[j].w)
-                     : "r"(vbuf + tt * 128 + c * 16));
+                     : "r"(vbuf + tt * 128 + kv_chunk(tt, c) * 16));
       } else if (tt < pos) {
-        const long long base = ((static_cast<long long>(arow[tt]) * H + h) * t_max + tt) * 64 + c * 8;
+        const long long base = ((static_cast<long long>(arow[tt]) * H + h) * t_max + tt) * 64 + kv_chunk(tt, c) * 8;
         kk[j] = *reinterpret_cast<const uint4*>(kcache + base);
         vv[j] = *reinterpret_cast<const uint4*>(vcache + base);
       } else if (tt == pos) {
@@ -530,7 +535,7 @@ decode_attn_bulk_kernel(const __half* __restrict__ qkv, __half* __restrict__ kca
   const uint4 knew = *reinterpret_cast<const uint4*>(qrow + d + c * 8);
   const uint4 vnew = *reinterpret_cast<const uint4*>(qrow + 2 * d + c * 8);
   {  // append this step's k, v for later steps
-    const long long dst = (own + pos) * 64 + c * 8;
+    const long long dst = (own + pos) * 64 + kv_chunk(pos, c) * 8;
     if (kq == 0) *reinterpret_cast<uint4*>(kcache + dst) = knew;
     else if (kq == 1) *reinterpret_cast<uint4*>(vcache + dst) = vnew;
   }
@@ -551,10 +556,10 @@ decode_attn_bulk_kernel(const __half* __restrict__ qkv, __half* __restrict__ kca
       if (tt < pos) {
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(kk[j].x), "=r"(kk[j].y), "=r"(kk[j].z), "=r"(kk[j].w)
-                     : "r"(kbuf + tt * row_bytes + c * 16));
+                     : "r"(kbuf + tt * row_bytes + kv_chunk(tt, c) * 16));
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(vv[j].x), "=r"(vv[j].y), "=r"(vv[j].z), "=r"(vv[j].w)
-                     : "r"(vbuf + tt * row_bytes + c * 16));
+                     : "r"(vbuf + tt * row_bytes + kv_chunk(tt, c) * 16));
       } else if (tt == pos) {
         kk[j] = knew;
         vv[j] = vnew;
@@ -612,6 +617,162 @@ decode_attn_bulk_kernel(const __half* __restrict__ qkv, __half* __restrict__ kca
     out.z = pack_half2(acc[4] * inv, acc[5] * inv);
     out.w = pack_half2(acc[6] * inv, acc[7] * inv);
     *reinterpret_cast<uint4*>(o + static_cast<long long>(seq) * d + h * 64 + c * 8) = out;
+  }
+}
+
+// Greedy decode on the warp-level tensor-core path. One warp per (sequence, head) as above, but the two contractions are
+// matrix-vector products issued as mma.m16n8k16 with the query / probability row in row 0 of the A operand (the other 15
+// rows are zero: the tensor pipe is idle in this kernel, instruction issue is what a decode partition of a few SMs runs
+// out of — ~800 warp instructions per pair in decode_attn_bulk_kernel, ~300 here):
+//   s[1 x T]  = q[1 x 64] K^T      B = K rows as stored ([key][dim] is the col-major operand): ldmatrix.x4 per 8 keys x 32 dims
+//   o[1 x 64] = p[1 x T] V         A = p re-packed from the score accumulators in registers, B = V through ldmatrix.trans
+// The rotated chunk order of the cache rows (kv_chunk) makes every ldmatrix conflict-free after a plain bulk copy. Keys
+// are walked in blocks of 64 with an online softmax (one block at the caption lengths of the path). Rows pos+1 .. R-1 of
+// the staging buffers (R = T rounded up to 16 keys, the k extent of the second product) are never copied: the V rows
+// are zeroed so that 0 * garbage cannot produce a NaN; scores of those keys are masked by select.
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+decode_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, __half* __restrict__ vcache,
+                       __half* __restrict__ o, int nseq, int H, int t_max, int pos, float scale_log2) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __shared__ __align__(8) unsigned long long bars[DEC_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * DEC_WARPS + warp;
+  const uint32_t bar = smem_u32(&bars[warp]);
+  const int T = pos + 1, R = (T + 15) & ~15;
+  const uint32_t kbuf = smem_u32(dsm) + warp * 2 * R * 128;  // [R] K rows, then [R] V rows
+  const uint32_t vbuf = kbuf + R * 128;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  pdl_launch_dependents();
+  const bool live = pair < nseq * H;
+  const int seq = pair / H, h = pair % H;
+  const long long own = (static_cast<long long>(seq) * H + h) * t_max;
+  // cached rows (written by earlier steps / the prefill, never by the predecessor kernel) stream before griddepcontrol.wait
+  if (live && lane == 0 && pos > 0) {
+    mbar_arrive_expect_tx(bar, 2u * pos * 128u);
+    bulk_load(kbuf, kcache + own * 64, pos * 128u, bar);
+    bulk_load(vbuf, vcache + own * 64, pos * 128u, bar);
+  }
+  if (live) {
+    for (int i = lane; i < (R - pos) * 8; i += 32)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(vbuf + pos * 128 + i * 16), "r"(0u) : "memory");
+  }
+  pdl_wait();
+  if (!live) return;
+  const int d = H * 64;
+  const int t4 = lane & 3;
+  const __half* qrow = qkv + static_cast<long long>(seq) * 3 * d + h * 64;
+  // A fragments of q: word t4 of each 16-byte chunk, lanes 0..3 (row 0 of the 16-row operand) only
+  uint32_t qa[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qa[i] = lane < 4 ? reinterpret_cast<const uint32_t*>(qrow)[4 * i + lane] : 0u;
+  __syncwarp();  // the zero rows above are written before row `pos` below (same addresses for row pos)
+  if (lane < 16) {  // this step's k (lanes 0-7) and v (lanes 8-15): to the cache for later steps and to the staging row
+    const int c = lane & 7;
+    const uint4 x = *reinterpret_cast<const uint4*>(qrow + (lane < 8 ? d : 2 * d) + c * 8);
+    const int pc = kv_chunk(pos, c);
+    *reinterpret_cast<uint4*>((lane < 8 ? kcache : vcache) + (own + pos) * 64 + pc * 8) = x;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"((lane < 8 ? kbuf : vbuf) + pos * 128 + pc * 16), "r"(x.x),
+                 "r"(x.y), "r"(x.z), "r"(x.w)
+                 : "memory");
+  }
+  __syncwarp();
+  if (pos > 0) mbar_wait(bar, 0);
+
+  float acc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+  float mx = -INFINITY, lsum = 0.f;
+  const int lrow = lane & 7, lmat = lane >> 3;
+
+  for (int kb = 0; kb < R; kb += 64) {
+    const int nt = (R - kb) >= 64 ? 8 : (R - kb) >> 3;  // 8-key tiles in this block (even)
+    float sc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < nt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sc[j][i] = 0.f;
+        const int key = kb + 8 * j + lrow;
+        const uint32_t row = kbuf + key * 128;
+        uint32_t b[4];
+        ldmatrix_x4(b, row + (kv_chunk(key, lmat) << 4));  // dims 0 .. 31
+        {
+          const uint32_t a0[4] = {qa[0], 0u, qa[1], 0u}, a1[4] = {qa[2], 0u, qa[3], 0u};
+          mma_16816(sc[j], a0, b[0], b[1]);
+          mma_16816(sc[j], a1, b[2], b[3]);
+        }
+        ldmatrix_x4(b, row + (kv_chunk(key, lmat + 4) << 4));  // dims 32 .. 63
+        {
+          const uint32_t a2[4] = {qa[4], 0u, qa[5], 0u}, a3[4] = {qa[6], 0u, qa[7], 0u};
+          mma_16816(sc[j], a2, b[0], b[1]);
+          mma_16816(sc[j], a3, b[2], b[3]);
+        }
+      }
+    }
+    // lane t4 of the first quad holds the scores of keys kb + 8 j + 2 t4 (+1); the other quads hold zero rows
+    float bm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < nt) {
+        const int k0 = kb + 8 * j + 2 * t4;
+        sc[j][0] = k0 < T ? sc[j][0] : -INFINITY;
+        sc[j][1] = k0 + 1 < T ? sc[j][1] : -INFINITY;
+        bm = fmaxf(bm, fmaxf(sc[j][0], sc[j][1]));
+      }
+    }
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+    const float nm = fmaxf(mx, bm);  // finite: every block holds at least one valid key
+    const float corr = fast_exp2((mx - nm) * scale_log2);
+    mx = nm;
+    lsum *= corr;
+    if (kb > 0) {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        acc[n][0] *= corr;
+        acc[n][1] *= corr;
+      }
+    }
+    const float nms = nm * scale_log2;
+    uint32_t pa[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < nt) {
+        const float p0 = fast_exp2(sc[j][0] * scale_log2 - nms);  // exp2(-inf) = 0 for masked keys
+        const float p1 = fast_exp2(sc[j][1] * scale_log2 - nms);
+        lsum += p0 + p1;
+        pa[j] = pack_half2(p0, p1);
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      if (2 * kk < nt) {
+        const uint32_t a[4] = {pa[2 * kk], 0u, pa[2 * kk + 1], 0u};
+        const int key = kb + 16 * kk + lrow + 8 * (lmat & 1);
+        const uint32_t row = vbuf + key * 128;
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) {
+          uint32_t b[4];
+          ldmatrix_x4_trans(b, row + (kv_chunk(key, 2 * n2 + (lmat >> 1)) << 4));
+          mma_16816(acc[2 * n2], a, b[0], b[1]);
+          mma_16816(acc[2 * n2 + 1], a, b[2], b[3]);
+        }
+      }
+    }
+  }
+  lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
+  lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+  if (lane < 4) {
+    const float inv = 1.f / lsum;
+    uint32_t* orow = reinterpret_cast<uint32_t*>(o + static_cast<long long>(seq) * d + h * 64);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) orow[4 * n + lane] = pack_half2(acc[n][0] * inv, acc[n][1] * inv);
   }
 }
 
@@ -732,7 +893,7 @@ __global__ void kv_scatter_kernel(const __half* __restrict__ qkv, __half* __rest
     const int t = r % T;
     const int seq = r / T;
     const __half* src = qkv + (static_cast<long long>(seq) * T + t) * 3 * d + h * 64 + c * 8;
-    const long long dst = ((static_cast<long long>(seq) * slot_stride * H + h) * t_max + pos0 + t) * 64 + c * 8;
+    const long long dst = ((static_cast<long long>(seq) * slot_stride * H + h) * t_max + pos0 + t) * 64 + kv_chunk(pos0 + t, c) * 8;
     *reinterpret_cast<uint4*>(kcache + dst) = *reinterpret_cast<const uint4*>(src + d);
     *reinterpret_cast<uint4*>(vcache + dst) = *reinterpret_cast<const uint4*>(src + 2 * d);
   }
@@ -787,13 +948,29 @@ int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, cons
       return CC_OK;
     }
   }
-  // bulk-copy variant: no ancestry indirection, cache rows 16-byte aligned, staging fits beside two other CTAs
-  const size_t bulk_smem = static_cast<size_t>(DEC_WARPS) * 2 * pos * 128;  // the pos cached rows of K and V per warp
-  if (anc == nullptr && bulk_smem <= 72 * 1024) {
-    CC_OPT_IN_SMEM(decode_attn_bulk_kernel, 72 * 1024);
-    CC_CUDA(launch_pdl(decode_attn_bulk_kernel, dim3(grid), dim3(DEC_WARPS * 32), bulk_smem, s, qkv, kcache, vcache, o,
-                       nseq, H, t_max, pos, scale * 1.4426950408889634f));
-    return CC_OK;
+  // greedy (no ancestry indirection): rows of a (sequence, head) are contiguous — bulk copies into shared memory, staging
+  // sized to fit beside two other CTAs. Tensor-core matrix-vector kernel by default; CLIPCAP_B200_DECODE_ATTN_FMA=1 keeps
+  // the FMA kernel (fp32 probabilities) for comparison.
+  if (anc == nullptr) {
+    static const bool fma = [] {
+      const char* e = getenv("CLIPCAP_B200_DECODE_ATTN_FMA");
+      return e != nullptr && e[0] == '1';
+    }();
+    const int R = (pos + 1 + 15) & ~15;
+    const size_t mma_smem = static_cast<size_t>(DEC_WARPS) * 2 * R * 128;
+    if (!fma && mma_smem <= 72 * 1024) {
+      CC_OPT_IN_SMEM(decode_attn_mma_kernel, 72 * 1024);
+      CC_CUDA(launch_pdl(decode_attn_mma_kernel, dim3(grid), dim3(DEC_WARPS * 32), mma_smem, s, qkv, kcache, vcache, o,
+                         nseq, H, t_max, pos, scale * 1.4426950408889634f));
+      return CC_OK;
+    }
+    const size_t bulk_smem = static_cast<size_t>(DEC_WARPS) * 2 * pos * 128;  // the pos cached rows of K and V per warp
+    if (bulk_smem <= 72 * 1024) {
+      CC_OPT_IN_SMEM(decode_attn_bulk_kernel, 72 * 1024);
+      CC_CUDA(launch_pdl(decode_attn_bulk_kernel, dim3(grid), dim3(DEC_WARPS * 32), bulk_smem, s, qkv, kcache, vcache, o,
+                         nseq, H, t_max, pos, scale * 1.4426950408889634f));
+      return CC_OK;
+    }
   }
   CC_CUDA(launch_pdl(decode_attn_kernel, dim3(grid), dim3(DEC_WARPS * 32), 0, s, qkv, kcache, vcache, anc, o, nseq, H,
                      t_max, pos, scale * 1.4426950408889634f));

@@ -231,7 +231,8 @@ bool small_attention_fits(int S, int hd, int64_t ld, int64_t ldo, const __half* 
 int small_attention_run(const __half* q, const __half* k, const __half* v, int64_t ld, __half* o, int64_t ldo, int B, int S,
                         int H, int hd, bool causal, float scale, cudaStream_t s);
 
-// KV cache: [layer][k|v][slot][head][t_max][64] fp16. Decode step: append this step's k,v (from qkv[nseq,3d]) at position
+// KV cache: [layer][k|v][slot][head][t_max][64] fp16, the eight 16-byte chunks of a row rotated by its position (chunk c
+// of position t at chunk c ^ (t & 7), attention.cu kv_chunk). Decode step: append this step's k,v (from qkv[nseq,3d]) at position
 // `pos` of slot `seq`, then attend over positions 0..pos, position t being read from slot anc[seq*t_max + t]
 // (anc == nullptr: the sequence's own slot).
 // beam > 1 (with anc): rows seq = img * beam + b belong to one image and positions 0 .. shared_len-1 of all of them live

@@ -311,25 +311,35 @@ int small_attention_run(const __half* q, const __half* k, const __half* v, int64
     int B = 0, S = 0;
     CUtensorMap map;
   };
-  static thread_local Cached cache;
-  if (cache.base != q || cache.ld != ld || cache.cols != cols || cache.B != B || cache.S != S) {
+  // a few descriptors per thread (mapper, prefill and training buffers alternate): after the first step every call hits
+  static thread_local Cached slots[8];
+  static thread_local int next_slot = 0;
+  Cached* hit = nullptr;
+  for (Cached& c : slots)
+    if (c.base == q && c.ld == ld && c.cols == cols && c.B == B && c.S == S) hit = &c;
+  if (hit == nullptr) {
     EncodeTiledFn fn = encode_fn();
     CC_REQUIRE(fn != nullptr, CC_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    Cached& c = slots[next_slot];
+    next_slot = (next_slot + 1) % 8;
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(S) * ld * 2};
     cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(nslots)};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(&cache.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(q), dims, strides, box, estr,
+    c.base = nullptr;
+    CUresult r = fn(&c.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(q), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CC_REQUIRE(r == CUDA_SUCCESS, CC_ECUDA, "cuTensorMapEncodeTiled (small attention) failed (%d) S=%d B=%d ld=%lld", (int)r, S,
                B, (long long)ld);
-    cache.base = q;
-    cache.ld = ld;
-    cache.cols = cols;
-    cache.B = B;
-    cache.S = S;
+    c.base = q;
+    c.ld = ld;
+    c.cols = cols;
+    c.B = B;
+    c.S = S;
+    hit = &c;
   }
+  const CUtensorMap& map = hit->map;
   SaArgs a{};
   a.o = o;
   a.ldo = ldo;
@@ -352,8 +362,8 @@ int small_attention_run(const __half* q, const __half* k, const __half* v, int64
     const char* e = getenv("CLIPCAP_B200_SMALL_ATTN_STAGES128");
     return e != nullptr && e[0] == '2' ? 2 : 1;
   }();
-  if (hd == 64) return launch<64, 2>(cache.map, a, s);
-  return stages128 == 2 ? launch<128, 2>(cache.map, a, s) : launch<128, 1>(cache.map, a, s);
+  if (hd == 64) return launch<64, 2>(map, a, s);
+  return stages128 == 2 ? launch<128, 2>(map, a, s) : launch<128, 1>(map, a, s);
 }
 
 }  // namespace cc

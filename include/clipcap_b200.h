@@ -263,6 +263,9 @@ int cc_op_layernorm(const float* x, int64_t x_ld, const float* gamma, const floa
                     int d, float eps, void* stream);
 int cc_op_attention(const void* q, const void* k, const void* v, int64_t ld, void* o, int64_t ldo, int B, int S, int H,
                     int hd, int causal, float scale, void* stream);
+/* One decode step of attention: q, k, v of the step in qkv[nseq, 3 * H * 64]; caches [slot][head][t_max][64] fp16 whose
+ * 128-byte rows keep their eight 16-byte chunks rotated (chunk c of position t at chunk c ^ (t & 7): bank-conflict-free
+ * tensor-core operand fetches after a plain bulk copy, csrc/attention.cu kv_chunk); the step's k, v are appended at `pos`. */
 int cc_op_decode_attention(const void* qkv, void* kcache, void* vcache, const int32_t* anc, void* o, int nseq, int H,
                            int t_max, int pos, float scale, void* stream);
 /* Window tiling of a decoded square image (CLIPTransform.tile_image, clipcap/encoders/clip.py:60-82:

@@ -153,26 +153,38 @@ def test_vit_attention_large_scores(cuda_device):
     assert torch.isfinite(o.float()).all() and _rel(o, ref) < ATTN_TOL
 
 
+def _kv_rotate(x):
+    """Cache-row layout of the decode kernels: the eight 16-byte chunks of the row at position t sit at chunk c ^ (t & 7)
+    (csrc/attention.cu kv_chunk). The permutation is an involution, so the same function packs and unpacks. x: [..., t, 64]."""
+    t = torch.arange(x.shape[-2], device=x.device)
+    idx = (torch.arange(8, device=x.device)[None, :] ^ (t[:, None] & 7))  # [t, 8]: physical chunk p holds logical chunk p ^ (t & 7)
+    xs = x.reshape(*x.shape[:-1], 8, 8)
+    return torch.gather(xs, -2, idx[:, :, None].expand(*xs.shape[:-3], -1, -1, 8)).reshape(x.shape)
+
+
 @pytest.mark.parametrize("use_anc", [False, True])
 def test_decode_attention(cuda_device, use_anc):
+    """One query row per (sequence, head) over the cache + in-place append; greedy (no ancestry table) runs the tensor-core
+    matrix-vector kernel; positions cover one and several 16-key steps and two 64-key blocks."""
     lib = _ffi.lib()
-    nseq, H, t_max = 6, 4, 40
+    nseq, H, t_max = 6, 4, 80
     d = H * 64
-    kc = torch.randn(nseq, H, t_max, 64, device=cuda_device).half()
-    vc = torch.randn(nseq, H, t_max, 64, device=cuda_device).half()
-    for pos in (0, 1, 7, 16, 39):
+    kc_l = torch.randn(nseq, H, t_max, 64, device=cuda_device).half()  # logical [slot, head, position, dim]
+    vc_l = torch.randn(nseq, H, t_max, 64, device=cuda_device).half()
+    kc, vc = _kv_rotate(kc_l).contiguous(), _kv_rotate(vc_l).contiguous()
+    for pos in (0, 1, 7, 15, 16, 39, 63, 64, 79):
         anc = None
         if use_anc:  # beam ancestry: position t of row i lives in slot anc[i, t]
             anc = torch.randint(0, nseq, (nseq, t_max), device=cuda_device, dtype=torch.int32)
         qkv = torch.randn(nseq, 3 * d, device=cuda_device).half()
         o = torch.zeros(nseq, d, device=cuda_device, dtype=torch.half)
-        kc0, vc0 = kc.clone(), vc.clone()
+        kc0, vc0 = _kv_rotate(kc), _kv_rotate(vc)  # logical view of the cache before the call
         _ffi.check(lib.cc_op_decode_attention(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(),
                                               None if anc is None else anc.data_ptr(), o.data_ptr(), nseq, H, t_max, pos,
                                               0.125, _stream()))
         torch.cuda.synchronize()
         knew, vnew = qkv[:, d:2 * d].view(nseq, H, 64), qkv[:, 2 * d:].view(nseq, H, 64)
-        assert torch.equal(kc[:, :, pos], knew) and torch.equal(vc[:, :, pos], vnew)  # appended in place
+        assert torch.equal(_kv_rotate(kc)[:, :, pos], knew) and torch.equal(_kv_rotate(vc)[:, :, pos], vnew)  # appended in place
         if anc is None:
             kh, vh = kc0[:, :, :pos].float(), vc0[:, :, :pos].float()
         else:
