@@ -113,6 +113,7 @@ PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {
     "cc_op_skinny_gemm": (_i, [_vp, _vp, _vp, _f, _vp, _i64, _i, _vp, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "cc_op_attention_bwd": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "cc_op_decode_attention": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "cc_op_decode_attention_beam": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "cc_op_tile_image": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "cc_op_sample": (_i, [_vp, _i, _i, C.POINTER(cc_gen_cfg), _i, _vp, _vp, _vp, _vp]),
     "cc_train_create": (_i, [_pp, C.POINTER(cc_mapper_cfg), C.POINTER(cc_gpt2_cfg), C.POINTER(cc_tensor), _i, _i, _i]),

@@ -100,6 +100,19 @@ int cc_op_decode_attention(const void* qkv, void* kcache, void* vcache, const in
                               static_cast<cudaStream_t>(stream));
 }
 
+int cc_op_decode_attention_beam(const void* qkv, void* kcache, void* vcache, const int32_t* anc, void* o, int nseq, int H,
+                                int t_max, int pos, int beam, int shared_len, float scale, void* stream) {
+  using namespace cc;
+  CC_REQUIRE(qkv != nullptr && kcache != nullptr && vcache != nullptr && o != nullptr && anc != nullptr, CC_EINVAL,
+             "cc_op_decode_attention_beam: null argument");
+  CC_REQUIRE(beam >= 1 && nseq % beam == 0 && shared_len >= 0 && shared_len <= pos, CC_ESHAPE,
+             "cc_op_decode_attention_beam: beam %d, %d rows, shared_len %d, pos %d", beam, nseq, shared_len, pos);
+  CC_TRY(check_device_sm100());
+  return decode_attention_run(static_cast<const __half*>(qkv), static_cast<__half*>(kcache),
+                              static_cast<__half*>(vcache), anc, static_cast<__half*>(o), nseq, H, t_max, pos, scale,
+                              static_cast<cudaStream_t>(stream), beam, shared_len);
+}
+
 int cc_op_sample(const float* logits, int rows, int V, const cc_gen_cfg* g, int step, int32_t* tokens, int32_t* stopped,
                  int32_t* lengths, void* stream) {
   using namespace cc;

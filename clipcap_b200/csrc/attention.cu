@@ -620,32 +620,153 @@ decode_attn_bulk_kernel(const __half* __restrict__ qkv, __half* __restrict__ kca
   }
 }
 
-// Greedy decode on the warp-level tensor-core path. One warp per (sequence, head) as above, but the two contractions are
-// matrix-vector products issued as mma.m16n8k16 with the query / probability row in row 0 of the A operand (the other 15
-// rows are zero: the tensor pipe is idle in this kernel, instruction issue is what a decode partition of a few SMs runs
-// out of — ~800 warp instructions per pair in decode_attn_bulk_kernel, ~300 here):
+// ------------------------------------------------------------------ decode attention on the warp-level tensor-core path
+// One warp per (sequence, head): the two contractions are matrix-vector products issued as mma.m16n8k16 with the query /
+// probability row in row 0 of the A operand (the other 15 rows are zero: the tensor pipe is idle in these kernels,
+// instruction issue is what they run out of — ~800 warp instructions per pair in the FMA kernels, ~300 here):
 //   s[1 x T]  = q[1 x 64] K^T      B = K rows as stored ([key][dim] is the col-major operand): ldmatrix.x4 per 8 keys x 32 dims
 //   o[1 x 64] = p[1 x T] V         A = p re-packed from the score accumulators in registers, B = V through ldmatrix.trans
-// The rotated chunk order of the cache rows (kv_chunk) makes every ldmatrix conflict-free after a plain bulk copy. Keys
-// are walked in blocks of 64 with an online softmax (one block at the caption lengths of the path). Rows pos+1 .. R-1 of
-// the staging buffers (R = T rounded up to 16 keys, the k extent of the second product) are never copied: the V rows
-// are zeroed so that 0 * garbage cannot produce a NaN; scores of those keys are masked by select.
+// The rotated chunk order of the cache rows (kv_chunk) makes every ldmatrix conflict-free after a plain bulk copy.
+struct MvState {
+  float acc[8][4];  // o accumulators: tile n holds dims 8 n + 2 (lane & 3) (+1) in [0], [1] on lanes 0..3
+  float mx, lsum;
+};
+
+__device__ __forceinline__ void mv_init(MvState& st) {
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) st.acc[n][i] = 0.f;
+  st.mx = -INFINITY;
+  st.lsum = 0.f;
+}
+
+// A fragments of q: word (lane & 3) of each 16-byte chunk, lanes 0..3 (row 0 of the 16-row operand) only
+__device__ __forceinline__ void mv_load_q(const __half* qrow, int lane, uint32_t (&qa)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qa[i] = lane < 4 ? reinterpret_cast<const uint32_t*>(qrow)[4 * i + lane] : 0u;
+}
+
+// One block of up to 8 NT keys (NT = 8: 64, NT = 4: 32 — fewer live registers) with an online-softmax update. kbuf / vbuf: shared-memory rows of the block, row r holding
+// cache position t0 + r (which fixes its chunk rotation); only the nvalid (1 .. 8 NT) real rows exist in shared memory — the
+// products run over nvalid rounded up to 16 keys, and every operand fetch of a row >= nvalid is pointed at `zero16`, a
+// 16-byte chunk of zeros (ldmatrix takes one address per 8 x 8 matrix row), so padded keys contribute exactly 0 to p V and
+// no staging row has to be cleared; their scores are masked by select.
+template <int NT>
+__device__ __forceinline__ void mv_block(const uint32_t (&qa)[8], uint32_t kbuf, uint32_t vbuf, int t0, int nvalid,
+                                         uint32_t zero16, float scale_log2, int lane, MvState& st) {
+  const int t4 = lane & 3, lrow = lane & 7, lmat = lane >> 3;
+  const int nt = ((nvalid + 15) & ~15) >> 3;  // 8-key tiles (even)
+  float sc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    if (j < nt) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[j][i] = 0.f;
+      const int r = 8 * j + lrow;
+      const uint32_t row = kbuf + r * 128;
+      const bool real = r < nvalid;
+      uint32_t b[4];
+      ldmatrix_x4(b, real ? row + (kv_chunk(t0 + r, lmat) << 4) : zero16);  // dims 0 .. 31
+      {
+        const uint32_t a0[4] = {qa[0], 0u, qa[1], 0u}, a1[4] = {qa[2], 0u, qa[3], 0u};
+        mma_16816(sc[j], a0, b[0], b[1]);
+        mma_16816(sc[j], a1, b[2], b[3]);
+      }
+      ldmatrix_x4(b, real ? row + (kv_chunk(t0 + r, lmat + 4) << 4) : zero16);  // dims 32 .. 63
+      {
+        const uint32_t a2[4] = {qa[4], 0u, qa[5], 0u}, a3[4] = {qa[6], 0u, qa[7], 0u};
+        mma_16816(sc[j], a2, b[0], b[1]);
+        mma_16816(sc[j], a3, b[2], b[3]);
+      }
+    }
+  }
+  // lane t4 of the first quad holds the scores of keys 8 j + 2 t4 (+1); the other quads hold zero rows
+  float bm = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    if (j < nt) {
+      const int k0 = 8 * j + 2 * t4;
+      sc[j][0] = k0 < nvalid ? sc[j][0] : -INFINITY;
+      sc[j][1] = k0 + 1 < nvalid ? sc[j][1] : -INFINITY;
+      bm = fmaxf(bm, fmaxf(sc[j][0], sc[j][1]));
+    }
+  }
+  bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+  bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+  const float nm = fmaxf(st.mx, bm);  // finite: the block holds at least one valid key
+  const float corr = fast_exp2((st.mx - nm) * scale_log2);  // first block: exp2(-inf) = 0 over zero accumulators
+  st.mx = nm;
+  st.lsum *= corr;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    st.acc[n][0] *= corr;
+    st.acc[n][1] *= corr;
+  }
+  const float nms = nm * scale_log2;
+  uint32_t pa[NT];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    if (j < nt) {
+      const float p0 = fast_exp2(sc[j][0] * scale_log2 - nms);  // exp2(-inf) = 0 for masked keys
+      const float p1 = fast_exp2(sc[j][1] * scale_log2 - nms);
+      st.lsum += p0 + p1;
+      pa[j] = pack_half2(p0, p1);
+    }
+  }
+#pragma unroll
+  for (int kk = 0; kk < NT / 2; ++kk) {
+    if (2 * kk < nt) {
+      const uint32_t a[4] = {pa[2 * kk], 0u, pa[2 * kk + 1], 0u};
+      const int r = 16 * kk + lrow + 8 * (lmat & 1);
+      const uint32_t row = vbuf + r * 128;
+      const bool real = r < nvalid;
+#pragma unroll
+      for (int n2 = 0; n2 < 4; ++n2) {
+        uint32_t b[4];
+        ldmatrix_x4_trans(b, real ? row + (kv_chunk(t0 + r, 2 * n2 + (lmat >> 1)) << 4) : zero16);
+        mma_16816(st.acc[2 * n2], a, b[0], b[1]);
+        mma_16816(st.acc[2 * n2 + 1], a, b[2], b[3]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void mv_store(MvState& st, __half* orow, int lane) {
+  st.lsum += __shfl_xor_sync(0xffffffffu, st.lsum, 1);
+  st.lsum += __shfl_xor_sync(0xffffffffu, st.lsum, 2);
+  if (lane < 4) {
+    const float inv = 1.f / st.lsum;
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(orow);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) o32[4 * n + lane] = pack_half2(st.acc[n][0] * inv, st.acc[n][1] * inv);
+  }
+}
+
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& x) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+}
+
+// Greedy decode: the K / V rows of a (sequence, head) are contiguous in the cache; each warp pulls them with two bulk
+// copies issued before griddepcontrol.wait and adds this step's row behind them.
 __global__ void __launch_bounds__(DEC_WARPS * 32)
 decode_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, __half* __restrict__ vcache,
                        __half* __restrict__ o, int nseq, int H, int t_max, int pos, float scale_log2) {
   extern __shared__ __align__(128) uint8_t dsm[];
   __shared__ __align__(8) unsigned long long bars[DEC_WARPS];
+  __shared__ __align__(16) uint32_t zeros[4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * DEC_WARPS + warp;
   const uint32_t bar = smem_u32(&bars[warp]);
-  const int T = pos + 1, R = (T + 15) & ~15;
-  const uint32_t kbuf = smem_u32(dsm) + warp * 2 * R * 128;  // [R] K rows, then [R] V rows
-  const uint32_t vbuf = kbuf + R * 128;
+  const int T = pos + 1;
+  const uint32_t kbuf = smem_u32(dsm) + warp * 2 * T * 128;  // [T] K rows, then [T] V rows
+  const uint32_t vbuf = kbuf + T * 128;
   if (lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
-  __syncwarp();
+  if (threadIdx.x < 4) zeros[threadIdx.x] = 0u;
+  __syncthreads();
   pdl_launch_dependents();
   const bool live = pair < nseq * H;
   const int seq = pair / H, h = pair % H;
@@ -656,123 +777,151 @@ decode_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcac
     bulk_load(kbuf, kcache + own * 64, pos * 128u, bar);
     bulk_load(vbuf, vcache + own * 64, pos * 128u, bar);
   }
-  if (live) {
-    for (int i = lane; i < (R - pos) * 8; i += 32)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(vbuf + pos * 128 + i * 16), "r"(0u) : "memory");
-  }
   pdl_wait();
   if (!live) return;
   const int d = H * 64;
-  const int t4 = lane & 3;
   const __half* qrow = qkv + static_cast<long long>(seq) * 3 * d + h * 64;
-  // A fragments of q: word t4 of each 16-byte chunk, lanes 0..3 (row 0 of the 16-row operand) only
   uint32_t qa[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) qa[i] = lane < 4 ? reinterpret_cast<const uint32_t*>(qrow)[4 * i + lane] : 0u;
-  __syncwarp();  // the zero rows above are written before row `pos` below (same addresses for row pos)
+  mv_load_q(qrow, lane, qa);
   if (lane < 16) {  // this step's k (lanes 0-7) and v (lanes 8-15): to the cache for later steps and to the staging row
     const int c = lane & 7;
     const uint4 x = *reinterpret_cast<const uint4*>(qrow + (lane < 8 ? d : 2 * d) + c * 8);
     const int pc = kv_chunk(pos, c);
     *reinterpret_cast<uint4*>((lane < 8 ? kcache : vcache) + (own + pos) * 64 + pc * 8) = x;
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"((lane < 8 ? kbuf : vbuf) + pos * 128 + pc * 16), "r"(x.x),
-                 "r"(x.y), "r"(x.z), "r"(x.w)
-                 : "memory");
+    sts_v4((lane < 8 ? kbuf : vbuf) + pos * 128 + pc * 16, x);
   }
   __syncwarp();
   if (pos > 0) mbar_wait(bar, 0);
+  MvState st;
+  mv_init(st);
+  const uint32_t zero16 = smem_u32(zeros);
+  for (int kb = 0; kb < T; kb += 64)
+    mv_block<8>(qa, kbuf + kb * 128, vbuf + kb * 128, kb, min(T - kb, 64), zero16, scale_log2, lane, st);
+  mv_store(st, o + static_cast<long long>(seq) * d + h * 64, lane);
+}
 
-  float acc[8][4];
+// Beam search on the same path: one CTA per (image, head), beam + 1 warps. Positions 0 .. shared_len-1 of every beam live
+// in ONE cache slot (decode.cu beam_init / beam_step): the CTA stages them once (two bulk copies) and the LAST warp runs
+// them for all beams at once — the beams' queries are rows 0 .. beam-1 of the A operand, so the shared part costs one
+// pass of tensor-core work per image instead of one per beam (the warp-level MMA rate is what bounds this kernel when
+// every beam repeats the prefix). The generated positions of a beam sit wherever the ancestry table says: warp b gathers
+// beam b's rows (8 lanes per 128-byte row, all loads in flight before the first store) into a private staging area and
+// runs them with its query in row 0. The two partial softmaxes of a beam meet in shared memory (maximum, sum and the
+// unnormalised output row of the shared part) and warp b merges and stores. Replaces the FMA kernel above (kept behind
+// CLIPCAP_B200_DECODE_ATTN_FMA=1).
+constexpr int BEAM_GATHER = 5;  // 16-byte loads per lane and operand in flight: 20 rows per pass
+__global__ void __launch_bounds__((kMaxBeam + 1) * 32, 2)
+decode_attn_beam_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, __half* __restrict__ vcache,
+                            const int32_t* __restrict__ anc, __half* __restrict__ o, int beam, int H, int t_max, int pos,
+                            int shared_len, float scale_log2) {
+  extern __shared__ __align__(128) uint8_t bsm[];
+  __shared__ __align__(8) unsigned long long bbar;
+  __shared__ __align__(16) uint32_t zeros[4];
+  __shared__ float sh_o[kMaxBeam][64];
+  __shared__ float sh_m[kMaxBeam], sh_l[kMaxBeam];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.x / H, h = blockIdx.x % H;
+  const uint32_t bar = smem_u32(&bbar);
+  const int T = pos + 1;
+  const int ngen = T - shared_len;  // a beam's own positions (the last one is this step's)
+  const int d = H * 64;
+  const uint32_t kbuf = smem_u32(bsm), vbuf = kbuf + shared_len * 128;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 4) zeros[threadIdx.x] = 0u;
+  __syncthreads();
+  pdl_launch_dependents();
+  // The ancestry table and cache rows are read after the wait: a version that read them early (they are the product of
+  // launches far back in the stream) measured no gain and is not provably ordered behind beam_step.
+  pdl_wait();
+  const uint32_t zero16 = smem_u32(zeros);
+  MvState st;
+  mv_init(st);
+  if (warp == beam) {
+    // ---------------------------------------------------------------- shared positions, all beams: row g = beam g
+    if (lane == 0) {
+      const int32_t slot = anc[static_cast<long long>(img) * beam * t_max];  // slot of position 0 = the shared slot
+      const long long src = ((static_cast<long long>(slot) * H + h) * t_max) * 64;
+      mbar_arrive_expect_tx(bar, 2u * shared_len * 128u);
+      bulk_load(kbuf, kcache + src, shared_len * 128u, bar);
+      bulk_load(vbuf, vcache + src, shared_len * 128u, bar);
+    }
+    const int g = lane >> 2, t4 = lane & 3;
+    uint32_t qa[8];
+    const uint32_t* q32 = reinterpret_cast<const uint32_t*>(qkv + static_cast<long long>(img * beam + (g < beam ? g : 0)) * 3 * d + h * 64);
 #pragma unroll
-  for (int n = 0; n < 8; ++n)
+    for (int i = 0; i < 8; ++i) qa[i] = g < beam ? q32[4 * i + t4] : 0u;
+    mbar_wait(bar, 0);
+    for (int kb = 0; kb < shared_len; kb += 32)
+      mv_block<4>(qa, kbuf + kb * 128, vbuf + kb * 128, kb, min(shared_len - kb, 32), zero16, scale_log2, lane, st);
+    st.lsum += __shfl_xor_sync(0xffffffffu, st.lsum, 1);
+    st.lsum += __shfl_xor_sync(0xffffffffu, st.lsum, 2);
+    if (g < beam) {
+      if (t4 == 0) {
+        sh_m[g] = st.mx;
+        sh_l[g] = st.lsum;
+      }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
-  float mx = -INFINITY, lsum = 0.f;
-  const int lrow = lane & 7, lmat = lane >> 3;
-
-  for (int kb = 0; kb < R; kb += 64) {
-    const int nt = (R - kb) >= 64 ? 8 : (R - kb) >> 3;  // 8-key tiles in this block (even)
-    float sc[8][4];
+      for (int n = 0; n < 8; ++n)
+        *reinterpret_cast<float2*>(&sh_o[g][8 * n + 2 * t4]) = make_float2(st.acc[n][0], st.acc[n][1]);
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"((beam + 1) * 32) : "memory");
+    return;
+  }
+  // ------------------------------------------------------------------ warp b: beam b's own positions, query in row 0
+  const int seq = img * beam + warp;
+  const int32_t* arow = anc + static_cast<long long>(seq) * t_max;
+  const uint32_t kown = vbuf + shared_len * 128 + warp * 2 * ngen * 128, vown = kown + ngen * 128;
+  const int c = lane & 7;
+  for (int r0 = 0; r0 < ngen - 1; r0 += 4 * BEAM_GATHER) {  // rows r0 + 4 j + (lane >> 3), copied verbatim (rotation included)
+    uint4 kk[BEAM_GATHER], vv[BEAM_GATHER];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < nt) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sc[j][i] = 0.f;
-        const int key = kb + 8 * j + lrow;
-        const uint32_t row = kbuf + key * 128;
-        uint32_t b[4];
-        ldmatrix_x4(b, row + (kv_chunk(key, lmat) << 4));  // dims 0 .. 31
-        {
-          const uint32_t a0[4] = {qa[0], 0u, qa[1], 0u}, a1[4] = {qa[2], 0u, qa[3], 0u};
-          mma_16816(sc[j], a0, b[0], b[1]);
-          mma_16816(sc[j], a1, b[2], b[3]);
-        }
-        ldmatrix_x4(b, row + (kv_chunk(key, lmat + 4) << 4));  // dims 32 .. 63
-        {
-          const uint32_t a2[4] = {qa[4], 0u, qa[5], 0u}, a3[4] = {qa[6], 0u, qa[7], 0u};
-          mma_16816(sc[j], a2, b[0], b[1]);
-          mma_16816(sc[j], a3, b[2], b[3]);
-        }
+    for (int j = 0; j < BEAM_GATHER; ++j) {
+      const int r = r0 + 4 * j + (lane >> 3);
+      if (r < ngen - 1) {
+        const int t = shared_len + r;
+        const long long src = ((static_cast<long long>(arow[t]) * H + h) * t_max + t) * 64 + c * 8;
+        kk[j] = *reinterpret_cast<const uint4*>(kcache + src);
+        vv[j] = *reinterpret_cast<const uint4*>(vcache + src);
       }
     }
-    // lane t4 of the first quad holds the scores of keys kb + 8 j + 2 t4 (+1); the other quads hold zero rows
-    float bm = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < nt) {
-        const int k0 = kb + 8 * j + 2 * t4;
-        sc[j][0] = k0 < T ? sc[j][0] : -INFINITY;
-        sc[j][1] = k0 + 1 < T ? sc[j][1] : -INFINITY;
-        bm = fmaxf(bm, fmaxf(sc[j][0], sc[j][1]));
-      }
-    }
-    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
-    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
-    const float nm = fmaxf(mx, bm);  // finite: every block holds at least one valid key
-    const float corr = fast_exp2((mx - nm) * scale_log2);
-    mx = nm;
-    lsum *= corr;
-    if (kb > 0) {
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        acc[n][0] *= corr;
-        acc[n][1] *= corr;
-      }
-    }
-    const float nms = nm * scale_log2;
-    uint32_t pa[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < nt) {
-        const float p0 = fast_exp2(sc[j][0] * scale_log2 - nms);  // exp2(-inf) = 0 for masked keys
-        const float p1 = fast_exp2(sc[j][1] * scale_log2 - nms);
-        lsum += p0 + p1;
-        pa[j] = pack_half2(p0, p1);
-      }
-    }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      if (2 * kk < nt) {
-        const uint32_t a[4] = {pa[2 * kk], 0u, pa[2 * kk + 1], 0u};
-        const int key = kb + 16 * kk + lrow + 8 * (lmat & 1);
-        const uint32_t row = vbuf + key * 128;
-#pragma unroll
-        for (int n2 = 0; n2 < 4; ++n2) {
-          uint32_t b[4];
-          ldmatrix_x4_trans(b, row + (kv_chunk(key, 2 * n2 + (lmat >> 1)) << 4));
-          mma_16816(acc[2 * n2], a, b[0], b[1]);
-          mma_16816(acc[2 * n2 + 1], a, b[2], b[3]);
-        }
+    for (int j = 0; j < BEAM_GATHER; ++j) {
+      const int r = r0 + 4 * j + (lane >> 3);
+      if (r < ngen - 1) {
+        sts_v4(kown + r * 128 + c * 16, kk[j]);
+        sts_v4(vown + r * 128 + c * 16, vv[j]);
       }
     }
   }
-  lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
-  lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+  const __half* qrow = qkv + static_cast<long long>(seq) * 3 * d + h * 64;
+  uint32_t qa[8];
+  mv_load_q(qrow, lane, qa);
+  if (lane < 16) {  // this step's k, v: appended to the row's own slot and placed as the last private row
+    const uint4 x = *reinterpret_cast<const uint4*>(qrow + (lane < 8 ? d : 2 * d) + c * 8);
+    const int pc = kv_chunk(pos, c);
+    *reinterpret_cast<uint4*>((lane < 8 ? kcache : vcache) + ((static_cast<long long>(seq) * H + h) * t_max + pos) * 64 + pc * 8) = x;
+    sts_v4((lane < 8 ? kown : vown) + (ngen - 1) * 128 + pc * 16, x);
+  }
+  __syncwarp();
+  for (int kb = 0; kb < ngen; kb += 32)
+    mv_block<4>(qa, kown + kb * 128, vown + kb * 128, shared_len + kb, min(ngen - kb, 32), zero16, scale_log2, lane, st);
+  st.lsum += __shfl_xor_sync(0xffffffffu, st.lsum, 1);
+  st.lsum += __shfl_xor_sync(0xffffffffu, st.lsum, 2);
+  asm volatile("bar.sync 1, %0;" ::"r"((beam + 1) * 32) : "memory");  // the shared part of every beam is in shared memory
   if (lane < 4) {
-    const float inv = 1.f / lsum;
-    uint32_t* orow = reinterpret_cast<uint32_t*>(o + static_cast<long long>(seq) * d + h * 64);
+    const float ms = sh_m[warp], ls = sh_l[warp];
+    const float m = fmaxf(ms, st.mx);
+    const float es = fast_exp2((ms - m) * scale_log2), ep = fast_exp2((st.mx - m) * scale_log2);
+    const float inv = 1.f / (ls * es + st.lsum * ep);
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(o + static_cast<long long>(seq) * d + h * 64);
 #pragma unroll
-    for (int n = 0; n < 8; ++n) orow[4 * n + lane] = pack_half2(acc[n][0] * inv, acc[n][1] * inv);
+    for (int n = 0; n < 8; ++n) {
+      const float2 so = *reinterpret_cast<const float2*>(&sh_o[warp][8 * n + 2 * lane]);
+      o32[4 * n + lane] = pack_half2((so.x * es + st.acc[n][0] * ep) * inv, (so.y * es + st.acc[n][1] * ep) * inv);
+    }
   }
 }
 
@@ -940,6 +1089,17 @@ int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, cons
       const char* e = getenv("CLIPCAP_B200_NO_BEAM_ATTN");
       return e != nullptr && e[0] == '1';
     }();
+    static const bool fma = [] {
+      const char* e = getenv("CLIPCAP_B200_DECODE_ATTN_FMA");
+      return e != nullptr && e[0] == '1';
+    }();
+    const size_t mma_smem = static_cast<size_t>(2 * shared_len + beam * 2 * (pos + 1 - shared_len)) * 128;
+    if (!off && !fma && mma_smem <= 96 * 1024) {
+      CC_OPT_IN_SMEM(decode_attn_beam_mma_kernel, 96 * 1024);
+      CC_CUDA(launch_pdl(decode_attn_beam_mma_kernel, dim3((nseq / beam) * H), dim3((beam + 1) * 32), mma_smem, s, qkv, kcache,
+                         vcache, anc, o, beam, H, t_max, pos, shared_len, scale * 1.4426950408889634f));
+      return CC_OK;
+    }
     if (!off) {
       CC_OPT_IN_SMEM(decode_attn_beam_kernel, 64 * 1024);
       CC_CUDA(launch_pdl(decode_attn_beam_kernel, dim3((nseq / beam) * H), dim3(beam * 32),
@@ -956,8 +1116,7 @@ int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, cons
       const char* e = getenv("CLIPCAP_B200_DECODE_ATTN_FMA");
       return e != nullptr && e[0] == '1';
     }();
-    const int R = (pos + 1 + 15) & ~15;
-    const size_t mma_smem = static_cast<size_t>(DEC_WARPS) * 2 * R * 128;
+    const size_t mma_smem = static_cast<size_t>(DEC_WARPS) * 2 * (pos + 1) * 128;
     if (!fma && mma_smem <= 72 * 1024) {
       CC_OPT_IN_SMEM(decode_attn_mma_kernel, 72 * 1024);
       CC_CUDA(launch_pdl(decode_attn_mma_kernel, dim3(grid), dim3(DEC_WARPS * 32), mma_smem, s, qkv, kcache, vcache, o,

@@ -268,6 +268,10 @@ int cc_op_attention(const void* q, const void* k, const void* v, int64_t ld, voi
  * tensor-core operand fetches after a plain bulk copy, csrc/attention.cu kv_chunk); the step's k, v are appended at `pos`. */
 int cc_op_decode_attention(const void* qkv, void* kcache, void* vcache, const int32_t* anc, void* o, int nseq, int H,
                            int t_max, int pos, float scale, void* stream);
+/* The same step for beam search: rows seq = image * beam + b; positions 0 .. shared_len-1 of every beam of an image live in
+ * the slot anc names for position 0 (the image's prefix), later positions wherever anc[seq * t_max + t] says. */
+int cc_op_decode_attention_beam(const void* qkv, void* kcache, void* vcache, const int32_t* anc, void* o, int nseq, int H,
+                                int t_max, int pos, int beam, int shared_len, float scale, void* stream);
 /* Window tiling of a decoded square image (CLIPTransform.tile_image, clipcap/encoders/clip.py:60-82:
  * tensor.unfold(1, p, step).unfold(2, p, step)): image [3, size, size] fp32 on the device ->
  * tiles [tiles_per_axis^2, 3, p, p], tile (ty, tx) = pixels [ty*step, ty*step + p) x [tx*step, tx*step + p), row-major over

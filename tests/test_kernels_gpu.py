@@ -198,6 +198,43 @@ def test_decode_attention(cuda_device, use_anc):
         assert _rel(o, ref) < ATTN_TOL, (pos, use_anc)
 
 
+@pytest.mark.parametrize("beam,shared_len", [(5, 40), (3, 7), (8, 16), (2, 70)])
+def test_decode_attention_beam(cuda_device, beam, shared_len):
+    """Beam rows of an image share positions 0 .. shared_len-1 (one slot); later positions follow the ancestry table. The
+    tensor-core beam kernel (one CTA per image and head, warp per beam) against fp32 attention over the gathered history."""
+    lib = _ffi.lib()
+    nimg, H, t_max = 3, 4, 96
+    nseq, d = nimg * beam, H * 64
+    g = torch.Generator(device="cpu").manual_seed(beam * 100 + shared_len)
+    kc = _kv_rotate(torch.randn(nseq, H, t_max, 64, generator=g).half().to(cuda_device)).contiguous()
+    vc = _kv_rotate(torch.randn(nseq, H, t_max, 64, generator=g).half().to(cuda_device)).contiguous()
+    for pos in (shared_len, shared_len + 1, shared_len + 6, shared_len + 19):
+        # position t < shared_len of every beam: the image's first slot; later positions: any slot of the same image
+        anc = torch.zeros(nseq, t_max, dtype=torch.int32)
+        for i in range(nseq):
+            img = i // beam
+            anc[i, :shared_len] = img * beam
+            anc[i, shared_len:] = img * beam + torch.randint(0, beam, (t_max - shared_len,), generator=g)
+        anc = anc.to(cuda_device)
+        qkv = torch.randn(nseq, 3 * d, generator=g).half().to(cuda_device)
+        o = torch.zeros(nseq, d, device=cuda_device, dtype=torch.half)
+        kc0, vc0 = _kv_rotate(kc), _kv_rotate(vc)
+        _ffi.check(lib.cc_op_decode_attention_beam(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(), anc.data_ptr(), o.data_ptr(),
+                                                   nseq, H, t_max, pos, beam, shared_len, 0.125, _stream()))
+        torch.cuda.synchronize()
+        knew, vnew = qkv[:, d:2 * d].view(nseq, H, 64), qkv[:, 2 * d:].view(nseq, H, 64)
+        assert torch.equal(_kv_rotate(kc)[:, :, pos], knew) and torch.equal(_kv_rotate(vc)[:, :, pos], vnew)
+        sl = anc[:, :pos].long()
+        ar = torch.arange(pos, device=cuda_device)
+        kh = torch.stack([kc0[sl[i], :, ar] for i in range(nseq)]).transpose(1, 2).float()
+        vh = torch.stack([vc0[sl[i], :, ar] for i in range(nseq)]).transpose(1, 2).float()
+        kk = torch.cat((kh, knew[:, :, None].float()), dim=2)
+        vv = torch.cat((vh, vnew[:, :, None].float()), dim=2)
+        q = qkv[:, :d].view(nseq, H, 1, 64).float()
+        ref = torch.nn.functional.scaled_dot_product_attention(q, kk, vv).reshape(nseq, d)
+        assert _rel(o, ref) < ATTN_TOL, (pos, beam, shared_len)
+
+
 @pytest.mark.parametrize("M", [1, 5, 8, 9, 16])
 @pytest.mark.parametrize("shape", [(3072, 1024), (1024, 4096), (50257, 768), (2304, 768), (40, 64), (1000, 1600)])
 def test_skinny_gemm(cuda_device, M, shape):
