@@ -11,6 +11,9 @@ Two overlaps, both across consecutive batches:
   while the 19 decode steps of batch i — a chain of ~3200 dependent launches that leaves most of the machine idle — run
   on the small one. Two GPT-2 engines (same weights, separate KV caches) alternate between batches, so a prefill never
   touches the cache a decode loop is still reading. Token ids are the same function of the pixels either way.
+  At the two ends of a stream of batches one half of that pipeline has nothing to do: the front of the FIRST batch (no
+  decode loop is running yet) and the decode loop of the LAST batch (no front follows) are enqueued on a whole-device
+  stream instead of their partition, sized for all SMs.
 """
 from __future__ import annotations
 
@@ -65,6 +68,9 @@ class CaptionPipeline:
             self.partition = SmPartition(partition_sms, self.device)
             self._prefilled = [torch.cuda.Event() for _ in range(2)]  # engine i holds the prefix + first token of its batch
             self._decoded = [torch.cuda.Event() for _ in range(2)]    # engine i is free for the next prefill
+            self._whole_stream = torch.cuda.Stream(device=self.device)  # primary context: every SM
+            self._front_done = torch.cuda.Event()  # the image tower / mapper workspaces are free for the next front
+            self._front_pending = False
 
     # ------------------------------------------------------------------ staging
     def _stage(self, slot: int, pixels_host: torch.Tensor, first_use: bool) -> None:
@@ -90,9 +96,24 @@ class CaptionPipeline:
             self._lm = self.model.language_model.decode_engines(n, self.batch * self.beam, K + self.entry_length)
         return self._lm
 
-    def _enqueue(self, pixels: torch.Tensor, slot: int, index: int, staged: bool) -> None:
+    @contextlib.contextmanager
+    def _whole(self):
+        """The whole-device stream with launch heuristics sized for every SM (the ends of a run, see the module text)."""
+        from clipcap_b200 import _ffi
+        lib = _ffi.lib()
+        before = lib.cc_get_sm_budget()
+        lib.cc_set_sm_budget(0)
+        try:
+            with torch.cuda.stream(self._whole_stream):
+                yield self._whole_stream
+        finally:
+            lib.cc_set_sm_budget(before)
+
+    def _enqueue(self, pixels: torch.Tensor, slot: int, index: int, staged: bool, first: bool = False,
+                 last: bool = False) -> None:
         """Image tower -> mapper -> [prefix all-gather] -> prefill + first token on the front stream, the remaining decode
-        steps + the copy of the ids to the host on the back stream. Without a partition both are the caller's stream."""
+        steps + the copy of the ids to the host on the back stream. Without a partition both are the caller's stream.
+        `first` / `last`: no decode loop is running / no front follows — that half runs on the whole device."""
         part = self.partition
         rows = pixels.shape[0]
         K = self.model.transformer_mapper.prefix_length
@@ -100,7 +121,11 @@ class CaptionPipeline:
         kw = dict(mode=self.mode, beam=self.beam, entry_length=self.entry_length, stop_token=self.stop_token)
         rec = {} if self.trace is not None else None
         compute = torch.cuda.current_stream(self.device)
-        with (part.on(0) if part is not None else contextlib.nullcontext(compute)) as front:
+        front_ctx = contextlib.nullcontext(compute) if part is None else (self._whole() if first else part.on(0))
+        back_ctx = contextlib.nullcontext(compute) if part is None else (self._whole() if last else part.on(1))
+        with front_ctx as front:
+            if part is not None and self._front_pending:
+                front.wait_event(self._front_done)  # consecutive fronts may sit on different streams (whole device / partition)
             if staged:
                 front.wait_event(self._copied[slot])
             self._mark(rec, "front0", front)
@@ -135,7 +160,9 @@ class CaptionPipeline:
                 work.wait()
             if part is not None:
                 self._prefilled[slot].record(front)
-        with (part.on(1) if part is not None else contextlib.nullcontext(compute)) as back:
+                self._front_done.record(front)
+                self._front_pending = True
+        with back_ctx as back:
             if part is not None:
                 back.wait_event(self._prefilled[slot])
             self._mark(rec, "dec0", back)
@@ -168,7 +195,7 @@ class CaptionPipeline:
             # the caller produced the resident batches on its current stream: order both partitions after it
             ready = torch.cuda.Event()
             ready.record(compute)
-            for st in self.partition.streams:
+            for st in (*self.partition.streams, self._whole_stream):
                 st.wait_event(ready)
         i = 0
         pending = None  # (slot, rows) whose results have been enqueued but not yet handed out
@@ -181,7 +208,7 @@ class CaptionPipeline:
             if upcoming is not None and not resident:  # copy of batch i+1 overlaps the compute of batch i
                 self._stage(slot ^ 1, upcoming, i == 0)
             pixels = nxt if resident else self._px[slot][:rows]
-            self._enqueue(pixels, slot, i, not resident)
+            self._enqueue(pixels, slot, i, not resident, first=(i == 0), last=(upcoming is None))
             if pending is not None:  # hand out batch i-1 while batch i runs
                 ps, pr = pending
                 self._done[ps].synchronize()
