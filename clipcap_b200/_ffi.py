@@ -90,6 +90,7 @@ PROTOTYPES: Dict[str, Tuple[object, List[object]]] = {
     "cc_generate_prefill": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(cc_gen_cfg), _vp]),
     "cc_generate_decode": (_i, [_vp, _i, _i, C.POINTER(cc_gen_cfg), _vp, _vp, _vp, _vp]),
     "cc_gpt2_last_launches": (_i, [_vp]),
+    "cc_gpt2_set_prefill_defer": (_i, [_vp, _i]),
     "cc_gpt2_destroy": (None, [_vp]),
     "cc_comm_unique_id": (_i, [_vp]),
     "cc_comm_create": (_i, [_pp, _vp, _i, _i]),

@@ -48,7 +48,7 @@ struct cc_gpt2 {
   cudaStream_t grp_stream[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups] = {nullptr, nullptr, nullptr, nullptr};
   // (mode, B, Tp, beam, entry_length, stop_token, temperature bits, SM budget, capture stream, phase)
-  using Key = std::tuple<int, int, int, int, int, int, uint32_t, int, uintptr_t, int>;
+  using Key = std::tuple<int, int, int, int, int, int, uint32_t, int, uintptr_t, int, int>;
   struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     unsigned long long last_use = 0;
@@ -60,6 +60,7 @@ struct cc_gpt2 {
   bool use_graphs = true;
   int launches = 0;
   int phase_launches = 0;  // kernels of the last prefill phase (cc_generate_prefill), added to the decode phase's count
+  int prefill_defer = 0;   // two-phase generate: trailing prefill blocks that run at the head of the decode phase
 
   ~cc_gpt2() {
     for (auto& kv_ : graphs) cudaGraphExecDestroy(kv_.second.exec);
@@ -228,40 +229,57 @@ int enqueue_generate(cc_gpt2* m, int B, int Tp, const cc_gen_cfg& g, cudaStream_
   st.pend_splits = 0;
   int extra = 0;
   int cur = 0;  // ping-pong index of the beam token / ancestry tables
-  if (phase != PHASE_DECODE) {
   // ---- prefill: all Tp prefix positions at once; K,V go to slot img*beam
   // The first token needs only the last prefix position of the last block (LM head on row Tp-1): that block runs its
   // out-proj / MLP for those B rows alone (K, V of every position still go to the cache).
+  // Two-phase generate (cc_generate_prefill / cc_generate_decode on different SM partitions): the last `defer` blocks of
+  // the prefill, the LM head and the first token move to the head of the decode phase (cc_gpt2_set_prefill_defer) —
+  // the caller's way of shifting work between its two streams; the kernels and their order are the same.
   static const bool full_last = [] {
     const char* e = getenv("CLIPCAP_B200_FULL_LAST_LAYER");
     return e != nullptr && e[0] == '1';
   }();
   const bool last_row = !full_last && Tp > 1;
-  for (int l = 0; l < c.L - (last_row ? 1 : 0); ++l) CC_TRY(st.layer_full(l, B, Tp, &m->kv, beam, s));
-  if (last_row) CC_TRY(st.layer_last_row(c.L - 1, B, Tp, &m->kv, beam, s));
-  CC_TRY(layernorm_run(st.h + static_cast<size_t>(Tp - 1) * d, static_cast<int64_t>(Tp) * d, m->lnf_g, m->lnf_b,
-                       m->lnf16, d, B, d, c.eps, s));
-  extra += 1;
-  if (is_sample) {
-    CC_TRY(gen_reset_run(m->g_stopped, m->g_lengths, m->keys, m->g_scores, B, s));
-    CC_TRY(gemm_run(m->p_head_logits, B, s));
-    CC_TRY(sample_step(0));
+  const int defer = phase == PHASE_ALL ? 0 : m->prefill_defer;
+  const int l_split = c.L - defer;  // blocks [0, l_split) belong to the prefill phase
+  auto prefill_blocks = [&](int l0, int l1) -> int {
+    for (int l = l0; l < l1; ++l) {
+      if (l == c.L - 1 && last_row) CC_TRY(st.layer_last_row(l, B, Tp, &m->kv, beam, s));
+      else CC_TRY(st.layer_full(l, B, Tp, &m->kv, beam, s));
+    }
+    return CC_OK;
+  };
+  auto first_token = [&]() -> int {
+    CC_TRY(layernorm_run(st.h + static_cast<size_t>(Tp - 1) * d, static_cast<int64_t>(Tp) * d, m->lnf_g, m->lnf_b,
+                         m->lnf16, d, B, d, c.eps, s));
+    extra += 1;
+    if (is_sample) {
+      CC_TRY(gen_reset_run(m->g_stopped, m->g_lengths, m->keys, m->g_scores, B, s));
+      CC_TRY(gemm_run(m->p_head_logits, B, s));
+      CC_TRY(sample_step(0));
+    } else if (!is_beam) {
+      CC_TRY(gen_reset_run(m->g_stopped, m->g_lengths, m->keys, m->g_scores, B, s));
+      CC_TRY(gemm_run(m->p_head_keys, B, s));
+      CC_TRY(greedy_select_run(m->keys, m->g_tokens, EL, 0, m->g_stopped, m->g_lengths, g.stop_token, B, s));
+    } else {
+      CC_TRY(gemm_run(m->p_head_logits, B, s));
+      CC_TRY(row_topk_run(m->logits, m->v_ld, c.V, inv_temp, beam, nullptr, m->cand_val, m->cand_idx, B, s));
+      CC_TRY(beam_init_run(m->cand_val, m->cand_idx, m->beam, beam, EL, m->t_max, Tp, g.stop_token, B, s));
+    }
     extra += 3;
-  } else if (!is_beam) {
-    CC_TRY(gen_reset_run(m->g_stopped, m->g_lengths, m->keys, m->g_scores, B, s));
-    CC_TRY(gemm_run(m->p_head_keys, B, s));
-    CC_TRY(greedy_select_run(m->keys, m->g_tokens, EL, 0, m->g_stopped, m->g_lengths, g.stop_token, B, s));
-    extra += 3;
-  } else {
-    CC_TRY(gemm_run(m->p_head_logits, B, s));
-    CC_TRY(row_topk_run(m->logits, m->v_ld, c.V, inv_temp, beam, nullptr, m->cand_val, m->cand_idx, B, s));
-    CC_TRY(beam_init_run(m->cand_val, m->cand_idx, m->beam, beam, EL, m->t_max, Tp, g.stop_token, B, s));
-    extra += 3;
+    return CC_OK;
+  };
+  if (phase != PHASE_DECODE) {
+    CC_TRY(prefill_blocks(0, l_split));
+    if (defer == 0) CC_TRY(first_token());
   }
-  }  // prefill phase
   if (phase == PHASE_PREFILL) {
     m->launches = st.launches + extra;
     return CC_OK;
+  }
+  if (phase == PHASE_DECODE && defer > 0) {
+    CC_TRY(prefill_blocks(l_split, c.L));
+    CC_TRY(first_token());
   }
   if (is_sample) {
     for (int step = 1; step < EL; ++step) {
@@ -431,7 +449,7 @@ int run_phase(cc_gpt2* m, int B, int Tp, const cc_gen_cfg* g, cudaStream_t s, in
   const bool own = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread && sm_budget() > 0;
   cudaStream_t cs = own ? s : m->cap_stream;
   const cc_gpt2::Key key{g->mode, B, Tp, beam, EL, g->stop_token, tbits, sm_budget(),
-                         own ? reinterpret_cast<uintptr_t>(s) : 0, phase};
+                         own ? reinterpret_cast<uintptr_t>(s) : 0, phase, phase == PHASE_ALL ? 0 : m->prefill_defer};
   auto it = m->graphs.find(key);
   if (it == m->graphs.end()) {
     if (m->graphs.size() >= cc_gpt2::kMaxGraphs) {  // evict the least recently used graph (ragged batches, prompt lengths ...)
@@ -522,6 +540,14 @@ int cc_generate_decode(cc_gpt2* m, int B, int Tp, const cc_gen_cfg* g, int32_t* 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CC_TRY(run_phase(m, B, Tp, g, s, PHASE_DECODE));
   return generate_results(m, B, g->entry_length, tokens, lengths, scores, s);
+}
+
+int cc_gpt2_set_prefill_defer(cc_gpt2* m, int blocks) {
+  using namespace cc;
+  CC_REQUIRE(m != nullptr, CC_EINVAL, "cc_gpt2_set_prefill_defer: null handle");
+  CC_REQUIRE(blocks >= 0 && blocks < m->cfg.L, CC_ESHAPE, "cc_gpt2_set_prefill_defer: %d of %d blocks", blocks, m->cfg.L);
+  m->prefill_defer = blocks;
+  return CC_OK;
 }
 
 int cc_gpt2_last_launches(cc_gpt2* m) { return m ? m->launches : 0; }

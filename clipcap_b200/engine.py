@@ -311,6 +311,10 @@ class Gpt2Engine(_Handle):
                                                      scores.data_ptr(), _ffi.current_stream_ptr()))
         return tokens, lengths, scores
 
+    def set_prefill_defer(self, blocks: int) -> None:
+        """cc_gpt2_set_prefill_defer: the last `blocks` prefill blocks + the first token run at the head of `decode`."""
+        _ffi.check(_ffi.lib().cc_gpt2_set_prefill_defer(self._h, int(blocks)))
+
     @property
     def last_launches(self) -> int:
         return _ffi.lib().cc_gpt2_last_launches(self._h)

@@ -30,12 +30,14 @@ class CaptionPipeline:
                  stop_token: int = 50256, device="cuda", pixel_dtype: torch.dtype = torch.float32,
                  prefix_all: Optional[torch.Tensor] = None, input_shape: Optional[Tuple[int, ...]] = None,
                  partition_sms: int = 0, mode: str = "greedy", beam: int = 1, comm=None,
-                 prefix_dtype: Optional[torch.dtype] = None):
+                 prefix_dtype: Optional[torch.dtype] = None, prefill_defer: int = 0):
         """`comm` (distributed.PrefixComm, N > 1): the prefix all-gather runs through the C ABI, in place — the mapper
         writes this rank's slot of a [world * batch, K, d] buffer of `prefix_dtype` and cc_allgather_prefix completes it
         on a side stream (decode reads only the local slot, so nothing waits for the peers except the end of the step).
         `prefix_all` (legacy): torch.distributed all-gather into the given tensor. `prefix_dtype`: dtype of the prefix
-        handed from the mapper to the language model (default: the encoder output's)."""
+        handed from the mapper to the language model (default: the encoder output's). `prefill_defer` (with a partition):
+        that many trailing prefill blocks run at the head of the decode loop, on the small partition — the balance knob
+        between the two partitions (cc_gpt2_set_prefill_defer); ids do not depend on it."""
         self.encode_fn, self.model = encode_fn, model
         self.entry_length, self.stop_token = entry_length, stop_token
         self.mode, self.beam = mode, (beam if mode == "beam" else 1)
@@ -43,6 +45,7 @@ class CaptionPipeline:
         self.prefix_all = prefix_all
         self.comm, self.prefix_dtype = comm, prefix_dtype
         self.batch = batch
+        self.prefill_defer = prefill_defer if partition_sms > 0 else 0
         if comm is not None:
             K, d = model.transformer_mapper.prefix_length, model.transformer_mapper.lm_embedding_size
             self.prefix_all = torch.empty(comm.world * batch, K, d, device=self.device, dtype=prefix_dtype or pixel_dtype)
@@ -118,6 +121,7 @@ class CaptionPipeline:
         rows = pixels.shape[0]
         K = self.model.transformer_mapper.prefix_length
         eng = self._engines()[slot if part is not None else 0]
+        eng.set_prefill_defer(self.prefill_defer)
         kw = dict(mode=self.mode, beam=self.beam, entry_length=self.entry_length, stop_token=self.stop_token)
         rec = {} if self.trace is not None else None
         compute = torch.cuda.current_stream(self.device)

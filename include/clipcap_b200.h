@@ -184,6 +184,11 @@ int cc_generate(cc_gpt2* h, const void* prefix, int dtype, int B, int Tp, const 
 int cc_generate_prefill(cc_gpt2* h, const void* prefix, int dtype, int B, int Tp, const cc_gen_cfg* g, void* stream);
 int cc_generate_decode(cc_gpt2* h, int B, int Tp, const cc_gen_cfg* g, int32_t* tokens, int32_t* lengths, float* scores,
                        void* stream);
+/* Balance between the two halves: the last `blocks` transformer blocks of the prefill, the LM head and the first-token
+ * selection move from cc_generate_prefill to the head of cc_generate_decode (same kernels, same order, same results) —
+ * for callers whose prefill-side stream is the busier one. 0 (default) restores the split described above. Does not
+ * affect cc_generate. */
+int cc_gpt2_set_prefill_defer(cc_gpt2* h, int blocks);
 /* number of kernel launches (graph nodes) the last cc_generate (or prefill + decode pair) enqueued */
 int cc_gpt2_last_launches(cc_gpt2* h);
 void cc_gpt2_destroy(cc_gpt2* h);

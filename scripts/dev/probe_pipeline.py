@@ -24,7 +24,8 @@ px = [bench.synthetic_pixels(B, 1234 + i).to(dev) for i in range(2)]
 pxh = [p.cpu().pin_memory() for p in px]
 ref = None
 for sms in [int(x) for x in os.environ.get("PART", "0,24,32,40").split(",")]:
-    pipe = CaptionPipeline(encode_fn, model, B, 224, 20, 50256, dev, partition_sms=sms)
+    pipe = CaptionPipeline(encode_fn, model, B, 224, 20, 50256, dev, partition_sms=sms,
+                           prefill_defer=int(os.environ.get("DEFER", "0")))
     outs = [(t.clone(), l.clone()) for t, l in pipe.run((px[i & 1] for i in range(4)), resident=True)]
     torch.cuda.synchronize()
     if ref is None:

@@ -71,10 +71,20 @@ def test_partitioned_pipeline_equals_sequential(cuda_device):
     prefix = model.transformer_mapper(encode_fn(px.to(cuda_device)))
     t, l, _ = generate_greedy_tokens(model, prefix, EL, stop)
     assert torch.equal(want[2][0], t.cpu()) and torch.equal(want[2][1], l.cpu())
+    # trailing prefill blocks moved to the head of the decode loop (cc_gpt2_set_prefill_defer): same ids, greedy and beam;
+    # single-batch run (front and decode both on the whole-device stream) included
+    for defer in (1,):  # the test model has two blocks
+        moved = CaptionPipeline(encode_fn, model, B, vcfg.image_size, EL, stop, cuda_device, partition_sms=32,
+                                prefill_defer=defer)
+        got = [(t.clone(), l.clone()) for t, l in moved.run(batches)]
+        for (gt, gl), (wt, wl) in zip(got, want):
+            assert torch.equal(gt, wt) and torch.equal(gl, wl)
+        one = [(t.clone(), l.clone()) for t, l in moved.run(batches[:1])]
+        assert torch.equal(one[0][0], want[0][0]) and torch.equal(one[0][1], want[0][1])
     # beam mode through the same loop
     from clipcap_b200.inference.base import generate_beam_tokens
     beam_pipe = CaptionPipeline(encode_fn, model, B, vcfg.image_size, EL, stop, cuda_device, partition_sms=32, mode="beam",
-                                beam=3)
+                                beam=3, prefill_defer=1)
     got = [(t.clone(), l.clone()) for t, l in beam_pipe.run(batches[:3])]
     for px, (gt, gl) in zip(batches[:3], got):
         prefix = model.transformer_mapper(encode_fn(px.to(cuda_device)))
