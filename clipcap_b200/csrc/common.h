@@ -228,8 +228,11 @@ constexpr int kVitAttnTokens = 257;
 // one (sequence, head) = one 128-row tile (small_attention.cu). attention_run tries it after the ViT kernel.
 bool small_attention_fits(int S, int hd, int64_t ld, int64_t ldo, const __half* q, const __half* k, const __half* v,
                           const __half* o);
+// kcache / vcache != nullptr (head dim 64): the kernel also writes positions 0 .. S-1 of every (sequence, head) into the
+// decode cache [slot = seq * slot_stride][head][t_max][64] (what kv_scatter_run does as a separate pass).
 int small_attention_run(const __half* q, const __half* k, const __half* v, int64_t ld, __half* o, int64_t ldo, int B, int S,
-                        int H, int hd, bool causal, float scale, cudaStream_t s);
+                        int H, int hd, bool causal, float scale, cudaStream_t s, __half* kcache = nullptr,
+                        __half* vcache = nullptr, int t_max = 0, int slot_stride = 1);
 
 // KV cache: [layer][k|v][slot][head][t_max][64] fp16, the eight 16-byte chunks of a row rotated by its position (chunk c
 // of position t at chunk c ^ (t & 7), attention.cu kv_chunk). Decode step: append this step's k,v (from qkv[nseq,3d]) at position

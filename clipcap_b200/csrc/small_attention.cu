@@ -44,7 +44,17 @@ struct SaArgs {
   float scale_log2;
   uint32_t idesc_s;  // instruction descriptor of the S MMA (N is a run-time value)
   int n_items;
+  // GPT-2 prefill (head dim 64): the K / V tiles of a sequence, as TMA lands them, ARE its cache rows (position t = tile row,
+  // the 128-byte swizzle of row t = the cache's chunk rotation c ^ (t & 7)): one bulk store per operand copies them to
+  // [slot = seq * slot_stride][head][t_max][64] — the prefill needs no separate scatter pass. nullptr: no cache.
+  __half* kcache;
+  __half* vcache;
+  int t_max, slot_stride;
 };
+
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
   asm volatile(
@@ -122,6 +132,18 @@ small_attn_kernel(const __grid_constant__ CUtensorMap map, SaArgs a) {
         const uint32_t sQ = base + st * Cfg::kStage, sK = sQ + Cfg::kOperand, sV = sK + Cfg::kOperand;
         mbar_wait(bars + 8 * st, (it / STAGES) & 1u);
         tc_fence_after();
+        if (HD == 64 && a.kcache != nullptr) {  // the landed K / V rows of each sequence slot go to the cache as they are
+          const int bg = w / a.H, h = w - bg * a.H;
+          for (int sl = 0; sl < a.nslots; ++sl) {
+            const int b = bg * a.nslots + sl;
+            if (b < a.B) {
+              const long long dst = ((static_cast<long long>(b) * a.slot_stride * a.H + h) * a.t_max) * 64;
+              bulk_store(a.kcache + dst, sK + sl * a.slot_rows * 128, a.S * 128u);
+              bulk_store(a.vcache + dst, sV + sl * a.slot_rows * 128, a.S * 128u);
+            }
+          }
+          bulk_commit();
+        }
         // S[128 x NS] = Q K^T over the head dim
 #pragma unroll
         for (int sl = 0; sl < Cfg::kSlabs; ++sl) {
@@ -135,6 +157,7 @@ small_attn_kernel(const __grid_constant__ CUtensorMap map, SaArgs a) {
           // the next item's operands go to the stage the item before this one used: its P V MMA was issued an iteration ago
           const int stn = (it + 1) % STAGES;
           if (it + 1 >= STAGES) mbar_wait(bars + 16 + 8 * stn, ((it + 1) / STAGES - 1) & 1u);
+          if (HD == 64 && a.kcache != nullptr) bulk_wait_read<1>();  // the cache stores of that stage (all but this item's) have read it
           load(wn, stn);
         }
         // O[128 x hd] = P V over the NS keys: A = P from TMEM (8 columns per 16 keys), B = V rows (MN-major, 2 KB per step)
@@ -151,9 +174,11 @@ small_attn_kernel(const __grid_constant__ CUtensorMap map, SaArgs a) {
         umma_commit(bars + 16 + 8 * st);
         if (STAGES == 1 && wn < a.n_items) {
           mbar_wait(bars + 16, it & 1u);  // this item's MMAs have read the only stage
+          if (HD == 64 && a.kcache != nullptr) bulk_wait_read<0>();
           load(wn, 0);
         }
       }
+      if (HD == 64 && a.kcache != nullptr) bulk_wait<0>();  // cache rows are written before the CTA retires
     }
   } else {
     // ------------------------------------------------------------ softmax + epilogue, thread == query row
@@ -291,7 +316,10 @@ bool small_attention_fits(int S, int hd, int64_t ld, int64_t ldo, const __half* 
 }
 
 int small_attention_run(const __half* q, const __half* k, const __half* v, int64_t ld, __half* o, int64_t ldo, int B, int S,
-                        int H, int hd, bool causal, float scale, cudaStream_t s) {
+                        int H, int hd, bool causal, float scale, cudaStream_t s, __half* kcache, __half* vcache, int t_max,
+                        int slot_stride) {
+  CC_REQUIRE(kcache == nullptr || (hd == 64 && vcache != nullptr && S <= t_max), CC_ESHAPE,
+             "small attention: the fused cache write needs head dim 64 and %d <= t_max %d", S, t_max);
   CC_REQUIRE(small_attention_fits(S, hd, ld, ldo, q, k, v, o), CC_ESHAPE, "small attention: unsupported shape");
   const long long kc = k - q, vc = v - q;
   const long long cols = (kc > vc ? kc : vc) + static_cast<long long>(H) * hd;
@@ -358,6 +386,10 @@ int small_attention_run(const __half* q, const __half* k, const __half* v, int64
   a.scale_log2 = scale * 1.4426950408889634f;
   a.idesc_s = umma_idesc_f16(128, a.NS);
   a.n_items = ((B + nslots - 1) / nslots) * H;
+  a.kcache = kcache;
+  a.vcache = vcache;
+  a.t_max = t_max;
+  a.slot_stride = slot_stride;
   static const int stages128 = [] {
     const char* e = getenv("CLIPCAP_B200_SMALL_ATTN_STAGES128");
     return e != nullptr && e[0] == '2' ? 2 : 1;

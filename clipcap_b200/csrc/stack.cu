@@ -134,14 +134,20 @@ int Stack::layer_full(int l, int B, int S, KvCache* kv, int slot_stride, cudaStr
   const LayerW& w = layers[l];
   CC_TRY(layernorm_run(h, d, w.ln1_g, w.ln1_b, ln16, d, rows, d, eps, s));
   CC_TRY(gemm_run(p_qkv[l], rows, s));
+  bool kv_done = false;
   if (heads_S > 0) {
     CC_REQUIRE(S == heads_S, CC_ESHAPE, "stack: head-major QKV planned for %d tokens per image, got %d", heads_S, S);
     CC_TRY(vit_attention_heads_run(qkv16, att16, d, B, S, H, scale, s));
+  } else if (kv != nullptr && hd == 64 && small_attention_fits(S, hd, 3 * d, d, qkv16, qkv16 + d, qkv16 + 2 * d, att16)) {
+    // prefill: the short-sequence kernel holds every K / V tile in the cache's own row layout and stores it there itself
+    CC_TRY(small_attention_run(qkv16, qkv16 + d, qkv16 + 2 * d, 3 * d, att16, d, B, S, H, hd, causal, scale, s,
+                               kv->k + l * kv->layer_elems, kv->v + l * kv->layer_elems, kv->t_max, slot_stride));
+    kv_done = true;
   } else {
     CC_TRY(attention_run(qkv16, qkv16 + d, qkv16 + 2 * d, 3 * d, att16, d, B, S, H, hd, causal, scale, s));
   }
   launches += 3;
-  if (kv != nullptr) {
+  if (kv != nullptr && !kv_done) {
     CC_TRY(kv_scatter_run(qkv16, kv->k + l * kv->layer_elems, kv->v + l * kv->layer_elems, B, S, H, kv->t_max, 0,
                           slot_stride, s));
     launches += 1;
