@@ -810,7 +810,8 @@ decode_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcac
 // unnormalised output row of the shared part) and warp b merges and stores. Replaces the FMA kernel above (kept behind
 // CLIPCAP_B200_DECODE_ATTN_FMA=1).
 constexpr int BEAM_GATHER = 5;  // 16-byte loads per lane and operand in flight: 20 rows per pass
-__global__ void __launch_bounds__((kMaxBeam + 1) * 32, 2)
+template <int MAX_WARPS, int MIN_CTAS>  // <6, 4>: beams up to 5 with four CTAs per SM (80 registers); <9, 2>: up to kMaxBeam
+__global__ void __launch_bounds__(MAX_WARPS * 32, MIN_CTAS)
 decode_attn_beam_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcache, __half* __restrict__ vcache,
                             const int32_t* __restrict__ anc, __half* __restrict__ o, int beam, int H, int t_max, int pos,
                             int shared_len, float scale_log2) {
@@ -1178,9 +1179,17 @@ int decode_attention_run(const __half* qkv, __half* kcache, __half* vcache, cons
     }();
     const size_t mma_smem = static_cast<size_t>(2 * shared_len + beam * 2 * (pos + 1 - shared_len)) * 128;
     if (!off && !fma && mma_smem <= 96 * 1024) {
-      CC_OPT_IN_SMEM(decode_attn_beam_mma_kernel, 96 * 1024);
-      CC_CUDA(launch_pdl(decode_attn_beam_mma_kernel, dim3((nseq / beam) * H), dim3((beam + 1) * 32), mma_smem, s, qkv, kcache,
-                         vcache, anc, o, beam, H, t_max, pos, shared_len, scale * 1.4426950408889634f));
+      if (beam <= 5) {
+        auto kern = decode_attn_beam_mma_kernel<6, 4>;
+        CC_OPT_IN_SMEM(kern, 96 * 1024);
+        CC_CUDA(launch_pdl(kern, dim3((nseq / beam) * H), dim3((beam + 1) * 32), mma_smem, s, qkv, kcache, vcache, anc, o,
+                           beam, H, t_max, pos, shared_len, scale * 1.4426950408889634f));
+      } else {
+        auto kern = decode_attn_beam_mma_kernel<kMaxBeam + 1, 2>;
+        CC_OPT_IN_SMEM(kern, 96 * 1024);
+        CC_CUDA(launch_pdl(kern, dim3((nseq / beam) * H), dim3((beam + 1) * 32), mma_smem, s, qkv, kcache, vcache, anc, o,
+                           beam, H, t_max, pos, shared_len, scale * 1.4426950408889634f));
+      }
       return CC_OK;
     }
     if (!off) {
