@@ -743,6 +743,141 @@ __device__ __forceinline__ void mv_store(MvState& st, __half* orow, int lane) {
   }
 }
 
+// ---- the same products with the KEYS in the M dimension of the MMA (what the single-query kernels use) ----
+// With the query in row 0 of A, 15 of 16 MMA rows are padding — and the warp-level MMA is slow enough on this part
+// (~32 cycles per m16n8k16 per SM sub-partition, measured through the greedy kernel on a 32-SM partition: 38 us = 64 MMAs per
+// pair x 32 pairs per sub-partition x 32 cycles) that the padding, not instruction issue, sets the pace. Transposed, the
+// padding moves to the 8-wide N dimension and the MMA count halves:
+//   s^T[keys x 8] = K[16 keys x 16 dims] q^T        A = K rows through ldmatrix.x4, B = q broadcast to all 8 columns
+//   o^T[dims x 8] = V^T[16 dims x 16 keys] p^T      A = V through ldmatrix.x4.trans, B = p broadcast (re-packed by shuffles)
+// Every column of an accumulator holds the same number; lane (g, t) = (lane >> 2, lane & 3) reads keys / dims g and g + 8 of
+// each 16-row tile from registers [0] and [2].
+struct Mv2State {
+  float acc[4][4];  // tile n: [0] = dim 16 n + g, [2] = dim 16 n + 8 + g (unnormalised)
+  float mx, lsum;   // lsum: this lane's keys only until mv2_finish
+};
+
+__device__ __forceinline__ void mv2_init(Mv2State& st) {
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) st.acc[n][i] = 0.f;
+  st.mx = -INFINITY;
+  st.lsum = 0.f;
+}
+
+// B fragments of q for the four 16-dim steps: word (lane & 3) of each 16-byte chunk, every lane
+__device__ __forceinline__ void mv2_load_q(const __half* qrow, int lane, uint32_t (&qb)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qb[i] = reinterpret_cast<const uint32_t*>(qrow)[4 * i + (lane & 3)];
+}
+
+// One block of up to 16 MT keys (MT = 4: 64, MT = 2: 32) with an online-softmax update; arguments as mv_block.
+template <int MT>
+__device__ __forceinline__ void mv2_block(const uint32_t (&qb)[8], uint32_t kbuf, uint32_t vbuf, int t0, int nvalid,
+                                          uint32_t zero16, float scale_log2, int lane, Mv2State& st) {
+  const int g = lane >> 2, t4 = lane & 3, l7 = lane & 7;
+  const int mt = (nvalid + 15) >> 4;  // 16-key tiles
+  float sc[MT][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    if (m < mt) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[m][i] = 0.f;
+      const int r = 16 * m + l7 + ((lane >> 3) & 1) * 8;  // matrices: keys 0-7 / 8-15 at chunk 2 ks, then at chunk 2 ks + 1
+      const bool real = r < nvalid;
+      const uint32_t row = kbuf + r * 128;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a[4];
+        ldmatrix_x4(a, real ? row + (kv_chunk(t0 + r, 2 * ks + (lane >> 4)) << 4) : zero16);
+        mma_16816(sc[m], a, qb[2 * ks], qb[2 * ks + 1]);
+      }
+    }
+  }
+  float bm = -INFINITY;
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    if (m < mt) {
+      sc[m][0] = 16 * m + g < nvalid ? sc[m][0] : -INFINITY;
+      sc[m][2] = 16 * m + 8 + g < nvalid ? sc[m][2] : -INFINITY;
+      bm = fmaxf(bm, fmaxf(sc[m][0], sc[m][2]));
+    }
+  }
+  bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 4));
+  bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
+  bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+  const float nm = fmaxf(st.mx, bm);  // finite: the block holds at least one valid key
+  const float corr = fast_exp2((st.mx - nm) * scale_log2);  // first block: exp2(-inf) = 0 over zero accumulators
+  st.mx = nm;
+  st.lsum *= corr;
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    st.acc[n][0] *= corr;
+    st.acc[n][2] *= corr;
+  }
+  const float nms = nm * scale_log2;
+  uint32_t pb[MT][2];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    if (m < mt) {
+      const float plo = fast_exp2(sc[m][0] * scale_log2 - nms);  // exp2(-inf) = 0 for masked keys
+      const float phi = fast_exp2(sc[m][2] * scale_log2 - nms);
+      st.lsum += plo + phi;
+      // B fragment of p for this key step: keys 2 t, 2 t + 1 (from the lanes with g = 2 t, 2 t + 1) and the same + 8
+      const int s0 = 8 * t4 + t4, s1 = s0 + 4;  // lanes (g = 2 t4, t4) and (g = 2 t4 + 1, t4)
+      const float a0 = __shfl_sync(0xffffffffu, plo, s0), a1 = __shfl_sync(0xffffffffu, plo, s1);
+      const float b0 = __shfl_sync(0xffffffffu, phi, s0), b1 = __shfl_sync(0xffffffffu, phi, s1);
+      pb[m][0] = pack_half2(a0, a1);
+      pb[m][1] = pack_half2(b0, b1);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    if (m < mt) {
+      const int r = 16 * m + l7 + (lane >> 4) * 8;  // matrices: keys 0-7 at chunks 2 n, 2 n + 1, then keys 8-15
+      const bool real = r < nvalid;
+      const uint32_t row = vbuf + r * 128;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        uint32_t a[4];
+        ldmatrix_x4_trans(a, real ? row + (kv_chunk(t0 + r, 2 * n + ((lane >> 3) & 1)) << 4) : zero16);
+        mma_16816(st.acc[n], a, pb[m][0], pb[m][1]);
+      }
+    }
+  }
+}
+
+// row sum over all keys of the warp (the t replicas of a lane hold the same numbers: reduce over g only)
+__device__ __forceinline__ void mv2_finish(Mv2State& st) {
+  st.lsum += __shfl_xor_sync(0xffffffffu, st.lsum, 4);
+  st.lsum += __shfl_xor_sync(0xffffffffu, st.lsum, 8);
+  st.lsum += __shfl_xor_sync(0xffffffffu, st.lsum, 16);
+}
+
+// this lane's two output dims of tile n == lane & 3: dim 16 n + g ([0]) and 16 n + 8 + g ([2]), scaled
+__device__ __forceinline__ void mv2_mine(const Mv2State& st, int lane, float scale, float& lo, float& hi) {
+  const int t4 = lane & 3;
+  lo = (t4 == 0 ? st.acc[0][0] : t4 == 1 ? st.acc[1][0] : t4 == 2 ? st.acc[2][0] : st.acc[3][0]) * scale;
+  hi = (t4 == 0 ? st.acc[0][2] : t4 == 1 ? st.acc[1][2] : t4 == 2 ? st.acc[2][2] : st.acc[3][2]) * scale;
+}
+
+// normalised fp16 row -> global: every lane stores one 32-bit pair (even g: dims 16 t + g, + 1; odd g: 16 t + 8 + g - 1, + g)
+__device__ __forceinline__ void mv2_store_pairs(float lo, float hi, __half* orow, int lane) {
+  const int g = lane >> 2, t4 = lane & 3;
+  const float plo = __shfl_xor_sync(0xffffffffu, lo, 4), phi = __shfl_xor_sync(0xffffffffu, hi, 4);  // partner g ^ 1
+  uint32_t* o32 = reinterpret_cast<uint32_t*>(orow);
+  if ((g & 1) == 0) o32[(16 * t4 + g) >> 1] = pack_half2(lo, plo);
+  else o32[(16 * t4 + 8 + g - 1) >> 1] = pack_half2(phi, hi);
+}
+
+__device__ __forceinline__ void mv2_store(Mv2State& st, __half* orow, int lane) {
+  mv2_finish(st);
+  float lo, hi;
+  mv2_mine(st, lane, 1.f / st.lsum, lo, hi);
+  mv2_store_pairs(lo, hi, orow, lane);
+}
+
 __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& x) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
 }
@@ -782,7 +917,7 @@ decode_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcac
   const int d = H * 64;
   const __half* qrow = qkv + static_cast<long long>(seq) * 3 * d + h * 64;
   uint32_t qa[8];
-  mv_load_q(qrow, lane, qa);
+  mv2_load_q(qrow, lane, qa);
   if (lane < 16) {  // this step's k (lanes 0-7) and v (lanes 8-15): to the cache for later steps and to the staging row
     const int c = lane & 7;
     const uint4 x = *reinterpret_cast<const uint4*>(qrow + (lane < 8 ? d : 2 * d) + c * 8);
@@ -792,12 +927,12 @@ decode_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ kcac
   }
   __syncwarp();
   if (pos > 0) mbar_wait(bar, 0);
-  MvState st;
-  mv_init(st);
+  Mv2State st;
+  mv2_init(st);
   const uint32_t zero16 = smem_u32(zeros);
   for (int kb = 0; kb < T; kb += 64)
-    mv_block<8>(qa, kbuf + kb * 128, vbuf + kb * 128, kb, min(T - kb, 64), zero16, scale_log2, lane, st);
-  mv_store(st, o + static_cast<long long>(seq) * d + h * 64, lane);
+    mv2_block<4>(qa, kbuf + kb * 128, vbuf + kb * 128, kb, min(T - kb, 64), zero16, scale_log2, lane, st);
+  mv2_store(st, o + static_cast<long long>(seq) * d + h * 64, lane);
 }
 
 // Beam search on the same path: one CTA per (image, head), beam + 1 warps. Positions 0 .. shared_len-1 of every beam live
@@ -871,7 +1006,7 @@ decode_attn_beam_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__
     asm volatile("bar.sync 1, %0;" ::"r"((beam + 1) * 32) : "memory");
     return;
   }
-  // ------------------------------------------------------------------ warp b: beam b's own positions, query in row 0
+  // ------------------------------------------------------------------ warp b: beam b's own positions (keys in the M dimension)
   const int seq = img * beam + warp;
   const int32_t* arow = anc + static_cast<long long>(seq) * t_max;
   const uint32_t kown = vbuf + shared_len * 128 + warp * 2 * ngen * 128, vown = kown + ngen * 128;
@@ -899,7 +1034,7 @@ decode_attn_beam_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__
   }
   const __half* qrow = qkv + static_cast<long long>(seq) * 3 * d + h * 64;
   uint32_t qa[8];
-  mv_load_q(qrow, lane, qa);
+  mv2_load_q(qrow, lane, qa);
   if (lane < 16) {  // this step's k, v: appended to the row's own slot and placed as the last private row
     const uint4 x = *reinterpret_cast<const uint4*>(qrow + (lane < 8 ? d : 2 * d) + c * 8);
     const int pc = kv_chunk(pos, c);
@@ -907,22 +1042,23 @@ decode_attn_beam_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__
     sts_v4((lane < 8 ? kown : vown) + (ngen - 1) * 128 + pc * 16, x);
   }
   __syncwarp();
+  Mv2State ps;
+  mv2_init(ps);
   for (int kb = 0; kb < ngen; kb += 32)
-    mv_block<4>(qa, kown + kb * 128, vown + kb * 128, shared_len + kb, min(ngen - kb, 32), zero16, scale_log2, lane, st);
-  st.lsum += __shfl_xor_sync(0xffffffffu, st.lsum, 1);
-  st.lsum += __shfl_xor_sync(0xffffffffu, st.lsum, 2);
+    mv2_block<2>(qa, kown + kb * 128, vown + kb * 128, shared_len + kb, min(ngen - kb, 32), zero16, scale_log2, lane, ps);
+  mv2_finish(ps);
   asm volatile("bar.sync 1, %0;" ::"r"((beam + 1) * 32) : "memory");  // the shared part of every beam is in shared memory
-  if (lane < 4) {
+  {
+    const int g = lane >> 2, t4 = lane & 3;
     const float ms = sh_m[warp], ls = sh_l[warp];
-    const float m = fmaxf(ms, st.mx);
-    const float es = fast_exp2((ms - m) * scale_log2), ep = fast_exp2((st.mx - m) * scale_log2);
-    const float inv = 1.f / (ls * es + st.lsum * ep);
-    uint32_t* o32 = reinterpret_cast<uint32_t*>(o + static_cast<long long>(seq) * d + h * 64);
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const float2 so = *reinterpret_cast<const float2*>(&sh_o[warp][8 * n + 2 * lane]);
-      o32[4 * n + lane] = pack_half2((so.x * es + st.acc[n][0] * ep) * inv, (so.y * es + st.acc[n][1] * ep) * inv);
-    }
+    const float m = fmaxf(ms, ps.mx);
+    const float es = fast_exp2((ms - m) * scale_log2), ep = fast_exp2((ps.mx - m) * scale_log2);
+    const float inv = 1.f / (ls * es + ps.lsum * ep);
+    float lo, hi;
+    mv2_mine(ps, lane, ep, lo, hi);
+    lo = (sh_o[warp][16 * t4 + g] * es + lo) * inv;
+    hi = (sh_o[warp][16 * t4 + 8 + g] * es + hi) * inv;
+    mv2_store_pairs(lo, hi, o + static_cast<long long>(seq) * d + h * 64, lane);
   }
 }
 
@@ -1071,26 +1207,26 @@ cls_attn_mma_kernel(const __half* __restrict__ qkv, long long sb, long long sw, 
     }
   }
   uint32_t qa[8];
-  mv_load_q(base + qrow * st, lane, qa);
+  mv2_load_q(base + qrow * st, lane, qa);
   __syncthreads();
-  MvState ms;
-  mv_init(ms);
+  Mv2State ms;
+  mv2_init(ms);
   const uint32_t zero16 = smem_u32(zeros);
   bool any = false;
   for (int kb = 64 * warp; kb < S; kb += 256) {
-    mv_block<8>(qa, kbuf + kb * 128, vbuf + kb * 128, kb, min(S - kb, 64), zero16, scale_log2, lane, ms);
+    mv2_block<4>(qa, kbuf + kb * 128, vbuf + kb * 128, kb, min(S - kb, 64), zero16, scale_log2, lane, ms);
     any = true;
   }
-  ms.lsum += __shfl_xor_sync(0xffffffffu, ms.lsum, 1);
-  ms.lsum += __shfl_xor_sync(0xffffffffu, ms.lsum, 2);
-  if (lane < 4) {
+  mv2_finish(ms);
+  {
+    float lo, hi;
+    mv2_mine(ms, lane, 1.f, lo, hi);
+    sh_o[warp][16 * (lane & 3) + (lane >> 2)] = lo;
+    sh_o[warp][16 * (lane & 3) + 8 + (lane >> 2)] = hi;
     if (lane == 0) {
       sh_m[warp] = any ? ms.mx : -INFINITY;
       sh_l[warp] = any ? ms.lsum : 0.f;
     }
-#pragma unroll
-    for (int n = 0; n < 8; ++n)
-      *reinterpret_cast<float2*>(&sh_o[warp][8 * n + 2 * lane]) = make_float2(ms.acc[n][0], ms.acc[n][1]);
   }
   __syncthreads();
   if (warp == 0) {  // lane owns dims 2 lane, 2 lane + 1
