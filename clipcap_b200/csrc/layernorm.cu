@@ -109,6 +109,18 @@ layernorm_row_kernel(float* __restrict__ x, long long x_ld, const float* __restr
   const int row = blockIdx.x;
   const int nv = d >> 2;
   pdl_launch_dependents();
+  // parameters are never written by a kernel of the stream: gamma / beta / bias are in registers before the wait, so the
+  // chain behind it is row + partial sums -> two block reductions -> store
+  float4 g[NV], be[NV], bi[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = threadIdx.x + i * LNR_THREADS;
+    const bool in = c < nv;
+    g[i] = in ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    be[i] = in ? __ldg(reinterpret_cast<const float4*>(beta) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bi[i] = in && splits > 0 && bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias) + c)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   pdl_wait();
   float4* xr = reinterpret_cast<float4*>(x + row * x_ld);
   float4 v[NV];
@@ -118,23 +130,17 @@ layernorm_row_kernel(float* __restrict__ x, long long x_ld, const float* __restr
     v[i] = c < nv ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (splits > 0) {
-    if (bias != nullptr) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = threadIdx.x + i * LNR_THREADS;
-        if (c < nv) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c);
-          v[i].x += b.x;
-          v[i].y += b.y;
-          v[i].z += b.z;
-          v[i].w += b.w;
-        }
-      }
+    for (int i = 0; i < NV; ++i) {  // bias first, then the splits in ascending order: the sum is deterministic
+      v[i].x += bi[i].x;
+      v[i].y += bi[i].y;
+      v[i].z += bi[i].z;
+      v[i].w += bi[i].w;
     }
     const float4* pr = reinterpret_cast<const float4*>(partial + row * static_cast<long long>(d));
     const long long ss = split_stride >> 2;
-#pragma unroll 4
-    for (int sp = 0; sp < splits; ++sp) {  // ascending split order: the sum is deterministic
+#pragma unroll 8
+    for (int sp = 0; sp < splits; ++sp) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = threadIdx.x + i * LNR_THREADS;
@@ -167,17 +173,14 @@ layernorm_row_kernel(float* __restrict__ x, long long x_ld, const float* __restr
     }
   }
   const float rstd = rsqrtf(block_sum_128(q, red) / static_cast<float>(d) + eps);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
   uint2* yr = reinterpret_cast<uint2*>(y + row * y_ld);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = threadIdx.x + i * LNR_THREADS;
     if (c < nv) {
-      const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
       uint2 o;
-      o.x = pack_half2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
-      o.y = pack_half2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      o.x = pack_half2((v[i].x - mean) * rstd * g[i].x + be[i].x, (v[i].y - mean) * rstd * g[i].y + be[i].y);
+      o.y = pack_half2((v[i].z - mean) * rstd * g[i].z + be[i].z, (v[i].w - mean) * rstd * g[i].w + be[i].w);
       yr[c] = o;
     }
   }
