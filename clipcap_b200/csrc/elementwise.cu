@@ -91,10 +91,14 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int rows, int 
 // ---------------------------------------------------------------- ViT
 // Non-overlapping 14x14 patches: row (b, py, px) of the GEMM operand gathers 3 x 14 x 14 pixels, column order
 // (c, ky, kx) = the flattening of conv1.weight [w, 3, 14, 14]; columns >= 588 are zero padding (16-byte rows for TMA).
-template <typename SRC>
+// PATCH > 0: the patch size as a compile-time constant (the divisions of the index arithmetic become multiplications:
+// ViT-L/14 and ViT-B/16 / B/32 take this path), 0: run-time patch size.
+template <typename SRC, int PATCH>
 __global__ void __launch_bounds__(256)
-vit_im2col_kernel(const SRC* __restrict__ px, __half* __restrict__ out, int img, int patch, int k_pad) {
+vit_im2col_kernel(const SRC* __restrict__ px, __half* __restrict__ out, int img, int patch_rt, int k_pad_rt) {
   // one CTA per (image, patch row): 32-bit index arithmetic only, the output rows of the CTA are contiguous
+  const int patch = PATCH > 0 ? PATCH : patch_rt;
+  const int k_pad = PATCH > 0 ? (3 * PATCH * PATCH + 7) / 8 * 8 : k_pad_rt;  // the host checks that this is the row length
   const int grid_w = img / patch;
   const int pp = patch * patch, kk = 3 * pp;
   const int b = blockIdx.x / grid_w, pyi = blockIdx.x - b * grid_w;
@@ -292,14 +296,24 @@ int pack_weight_run(const float* src, int rows, int cols, bool transpose, __half
 
 int vit_im2col_run(const void* pixels, int dtype, __half* out, int B, int img, int patch, int k_pad, cudaStream_t s) {
   const int gw = img / patch;
-  if (dtype == CC_F32)
-    vit_im2col_kernel<float><<<B * gw, 256, 0, s>>>(static_cast<const float*>(pixels), out, img, patch, k_pad);
-  else if (dtype == CC_F16)
-    vit_im2col_kernel<__half><<<B * gw, 256, 0, s>>>(static_cast<const __half*>(pixels), out, img, patch, k_pad);
-  else {
+  if (dtype != CC_F32 && dtype != CC_F16) {
     set_error("vit: unknown pixel dtype %d", dtype);
     return CC_EINVAL;
   }
+#define CC_IM2COL(SRC, P)                                                                                          \
+  vit_im2col_kernel<SRC, P><<<B * gw, 256, 0, s>>>(static_cast<const SRC*>(pixels), out, img, patch, k_pad)
+#define CC_IM2COL_DT(P)                    \
+  do {                                     \
+    if (dtype == CC_F32) CC_IM2COL(float, P); \
+    else CC_IM2COL(__half, P);             \
+  } while (0)
+  const bool ct = k_pad == (3 * patch * patch + 7) / 8 * 8;  // the padded row length the constant-patch kernels assume
+  if (ct && patch == 14) CC_IM2COL_DT(14);
+  else if (ct && patch == 16) CC_IM2COL_DT(16);
+  else if (ct && patch == 32) CC_IM2COL_DT(32);
+  else CC_IM2COL_DT(0);
+#undef CC_IM2COL_DT
+#undef CC_IM2COL
   CC_CUDA(cudaGetLastError());
   return CC_OK;
 }
