@@ -49,16 +49,17 @@ __device__ __forceinline__ void mv2_block(const uint32_t (&qb)[8], uint32_t kbuf
   float sc[MT][4];
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
-    if (m < mt) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) sc[m][i] = 0.f;
+    for (int i = 0; i < 4; ++i) sc[m][i] = 0.f;
+    if (m < mt) {  // warp-uniform; no shuffles inside (tiles beyond mt are masked below and cost two ex2 of -inf)
       const int r = 16 * m + l7 + ((lane >> 3) & 1) * 8;  // matrices: keys 0-7 / 8-15 at chunk 2 ks, then at chunk 2 ks + 1
       const bool real = r < nvalid;
       const uint32_t row = kbuf + r * 128;
+      const int rot = (t0 + r) & 7;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t a[4];
-        ldmatrix_x4(a, real ? row + (kv_chunk(t0 + r, 2 * ks + (lane >> 4)) << 4) : zero16);
+        ldmatrix_x4(a, real ? row + (((2 * ks + (lane >> 4)) ^ rot) << 4) : zero16);
         mma_16816(sc[m], a, qb[2 * ks], qb[2 * ks + 1]);
       }
     }
@@ -66,11 +67,9 @@ __device__ __forceinline__ void mv2_block(const uint32_t (&qb)[8], uint32_t kbuf
   float bm = -INFINITY;
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
-    if (m < mt) {
-      sc[m][0] = 16 * m + g < nvalid ? sc[m][0] : -INFINITY;
-      sc[m][2] = 16 * m + 8 + g < nvalid ? sc[m][2] : -INFINITY;
-      bm = fmaxf(bm, fmaxf(sc[m][0], sc[m][2]));
-    }
+    sc[m][0] = 16 * m + g < nvalid ? sc[m][0] : -INFINITY;
+    sc[m][2] = 16 * m + 8 + g < nvalid ? sc[m][2] : -INFINITY;
+    bm = fmaxf(bm, fmaxf(sc[m][0], sc[m][2]));
   }
   bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 4));
   bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
@@ -86,19 +85,17 @@ __device__ __forceinline__ void mv2_block(const uint32_t (&qb)[8], uint32_t kbuf
   }
   const float nms = nm * scale_log2;
   uint32_t pb[MT][2];
+  const int s0 = 8 * t4 + t4, s1 = s0 + 4;  // lanes (g = 2 t4, t4) and (g = 2 t4 + 1, t4)
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
-    if (m < mt) {
-      const float plo = fast_exp2(sc[m][0] * scale_log2 - nms);  // exp2(-inf) = 0 for masked keys
-      const float phi = fast_exp2(sc[m][2] * scale_log2 - nms);
-      st.lsum += plo + phi;
-      // B fragment of p for this key step: keys 2 t, 2 t + 1 (from the lanes with g = 2 t, 2 t + 1) and the same + 8
-      const int s0 = 8 * t4 + t4, s1 = s0 + 4;  // lanes (g = 2 t4, t4) and (g = 2 t4 + 1, t4)
-      const float a0 = __shfl_sync(0xffffffffu, plo, s0), a1 = __shfl_sync(0xffffffffu, plo, s1);
-      const float b0 = __shfl_sync(0xffffffffu, phi, s0), b1 = __shfl_sync(0xffffffffu, phi, s1);
-      pb[m][0] = pack_half2(a0, a1);
-      pb[m][1] = pack_half2(b0, b1);
-    }
+    const float plo = fast_exp2(sc[m][0] * scale_log2 - nms);  // exp2(-inf) = 0 for masked keys
+    const float phi = fast_exp2(sc[m][2] * scale_log2 - nms);
+    st.lsum += plo + phi;
+    // B fragment of p for this key step: keys 2 t, 2 t + 1 (from the lanes with g = 2 t, 2 t + 1) and the same + 8
+    const float a0 = __shfl_sync(0xffffffffu, plo, s0), a1 = __shfl_sync(0xffffffffu, plo, s1);
+    const float b0 = __shfl_sync(0xffffffffu, phi, s0), b1 = __shfl_sync(0xffffffffu, phi, s1);
+    pb[m][0] = pack_half2(a0, a1);
+    pb[m][1] = pack_half2(b0, b1);
   }
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
@@ -106,10 +103,11 @@ __device__ __forceinline__ void mv2_block(const uint32_t (&qb)[8], uint32_t kbuf
       const int r = 16 * m + l7 + (lane >> 4) * 8;  // matrices: keys 0-7 at chunks 2 n, 2 n + 1, then keys 8-15
       const bool real = r < nvalid;
       const uint32_t row = vbuf + r * 128;
+      const int rot = (t0 + r) & 7;
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         uint32_t a[4];
-        ldmatrix_x4_trans(a, real ? row + (kv_chunk(t0 + r, 2 * n + ((lane >> 3) & 1)) << 4) : zero16);
+        ldmatrix_x4_trans(a, real ? row + (((2 * n + ((lane >> 3) & 1)) ^ rot) << 4) : zero16);
         mma_16816(st.acc[n], a, pb[m][0], pb[m][1]);
       }
     }
