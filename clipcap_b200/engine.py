@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import sys
 from typing import Dict, Iterable, Optional, Tuple
 
 import torch
@@ -32,7 +33,12 @@ class _Handle:
             self._h = C.c_void_p()
 
     def __del__(self):
+        # At interpreter shutdown objects die in no particular order: a green context destroyed before the torch streams
+        # and events that live in it makes torch's own destructors throw ("context is destroyed") and abort the process.
+        # The driver reclaims everything at exit anyway, so handles are only destroyed while the interpreter is alive.
         try:
+            if sys.is_finalizing():
+                return
             self.close()
         except Exception:
             pass
